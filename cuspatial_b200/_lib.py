@@ -1,0 +1,104 @@
+"""ctypes loader of libcuspatial_b200.so (the C ABI declared in include/cuspatial_b200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or a call fails, the error is
+raised.  Nothing here (or anywhere in this package) imports oracle/.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcuspatial_b200.so")
+
+BSJ_SUCCESS, BSJ_INVALID_ARGUMENT, BSJ_CUDA_ERROR, BSJ_OUT_OF_MEMORY = 0, 1, 2, 3
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p)
+FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p)
+
+
+class bsj_allocator(C.Structure):
+    _fields_ = [("allocate", ALLOC_FN), ("deallocate", FREE_FN), ("ctx", C.c_void_p)]
+
+
+class bsj_quadtree(C.Structure):
+    _fields_ = [
+        ("point_indices", C.c_void_p), ("num_points", C.c_uint64),
+        ("key", C.c_void_p), ("level", C.c_void_p), ("is_internal_node", C.c_void_p),
+        ("length", C.c_void_p), ("offset", C.c_void_p), ("num_nodes", C.c_uint64),
+    ]
+
+
+class bsj_pairs(C.Structure):
+    _fields_ = [("first", C.c_void_p), ("second", C.c_void_p), ("size", C.c_uint64)]
+
+
+# every symbol include/cuspatial_b200.h declares
+EXPORTED_SYMBOLS = [
+    "bsj_quadtree_on_points", "bsj_join_quadtree_and_bounding_boxes",
+    "bsj_quadtree_point_in_polygon", "bsj_point_in_polygon", "bsj_polygon_bounding_boxes",
+    "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
+    "bsj_kernel_launch_count", "bsj_set_profiling", "bsj_get_profile",
+]
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "cuspatial_b200: %s not found. Build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `make -C cuspatial_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u64, dbl, i32 = C.c_void_p, C.c_uint64, C.c_double, C.c_int32
+    L.bsj_quadtree_on_points.argtypes = [vp, vp, C.c_int, u64, dbl, dbl, dbl, dbl, dbl, C.c_int8,
+                                         i32, C.POINTER(bsj_allocator), vp,
+                                         C.POINTER(bsj_quadtree)]
+    L.bsj_join_quadtree_and_bounding_boxes.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp,
+                                                       C.c_int, u64, dbl, dbl, dbl, dbl, dbl,
+                                                       C.c_int8, C.POINTER(bsj_allocator), vp,
+                                                       C.POINTER(bsj_pairs)]
+    L.bsj_quadtree_point_in_polygon.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, u64, vp, vp, vp,
+                                                C.c_int, u64, vp, u64, vp, u64, vp, vp, u64,
+                                                C.POINTER(bsj_allocator), vp, C.POINTER(bsj_pairs)]
+    L.bsj_point_in_polygon.argtypes = [vp, vp, C.c_int, u64, vp, u64, vp, u64, vp, vp, u64, vp, vp]
+    L.bsj_polygon_bounding_boxes.argtypes = [vp, u64, vp, u64, vp, vp, C.c_int, u64, dbl, vp,
+                                             vp, vp, vp, vp]
+    L.bsj_free.argtypes = [vp, vp]
+    L.bsj_last_error.restype = C.c_char_p
+    L.bsj_version.restype = C.c_char_p
+    L.bsj_kernel_launch_count.restype = u64
+    L.bsj_set_profiling.argtypes = [C.c_int]
+    L.bsj_get_profile.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    L.bsj_get_profile.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc == BSJ_SUCCESS:
+        return
+    msg = lib().bsj_last_error().decode(errors="replace")
+    if rc == BSJ_INVALID_ARGUMENT:
+        # the reference's cuspatial::logic_error surfaces in Python as RuntimeError (Cython `except +`)
+        raise RuntimeError(msg)
+    if rc == BSJ_OUT_OF_MEMORY:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def kernel_launch_count():
+    return int(lib().bsj_kernel_launch_count())
+
+
+def set_profiling(on):
+    lib().bsj_set_profiling(1 if on else 0)
+
+
+def get_profile():
+    names = (C.c_char_p * 64)()
+    ms = (C.c_float * 64)()
+    n = lib().bsj_get_profile(names, ms, 64)
+    return [(names[i].decode(), float(ms[i])) for i in range(n)]

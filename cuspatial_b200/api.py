@@ -1,0 +1,279 @@
+"""Python drop-in for the reference's quadtree point-in-polygon join entry points.
+
+Same names, positional order, pre-processing, warnings, column names and dtypes as
+  cuspatial.quadtree_on_points               (python/cuspatial/cuspatial/core/spatial/indexing.py:15-199)
+  cuspatial.join_quadtree_and_bounding_boxes (core/spatial/join.py:105-175)
+  cuspatial.quadtree_point_in_polygon        (core/spatial/join.py:178-262)
+  cuspatial.point_in_polygon                 (core/spatial/join.py:23-102)
+  cuspatial.polygon_bounding_boxes           (core/spatial/bounding.py:19-80)
+but over plain device tensors through the C ABI -- no cuDF, RMM or GeoSeries on the hot path:
+  points   : (x, y) tensors, an (N, 2) tensor, or a flat interleaved xy tensor (GeoArrow)
+  polygons : (part_offset, ring_offset, x, y) tensors (GeoArrow: one polygon per geometry)
+Inputs must live on a CUDA device (torch tensors; anything exposing __cuda_array_interface__ is
+wrapped with torch.as_tensor).  Outputs are torch tensors allocated through torch's caching
+allocator (handed to the library as its output allocator, the analogue of the reference's `mr`).
+"""
+import ctypes as C
+import warnings
+
+import torch
+
+from . import _lib
+from .frame import Frame
+
+_DTYPE_CODE = {torch.float32: 0, torch.float64: 1}
+
+
+class _TorchAllocator:
+    """bsj_allocator backed by torch.empty: output columns become ordinary torch tensors."""
+
+    def __init__(self, device):
+        self.device = device
+        self.live = {}
+        self._alloc = _lib.ALLOC_FN(self._allocate)
+        self._free = _lib.FREE_FN(self._deallocate)
+        self.struct = _lib.bsj_allocator(self._alloc, self._free, None)
+
+    def _allocate(self, nbytes, stream, ctx):
+        try:
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        except Exception:
+            return None
+        self.live[t.data_ptr()] = t
+        return t.data_ptr()
+
+    def _deallocate(self, ptr, nbytes, stream, ctx):
+        self.live.pop(ptr, None)
+
+    def take(self, ptr, n, dtype):
+        """The tensor behind `ptr`, viewed as n elements of dtype."""
+        if n == 0 or not ptr:
+            return torch.empty(0, dtype=dtype, device=self.device)
+        t = self.live.pop(ptr)
+        return t.view(dtype)[:n]
+
+
+def _as_cuda(t, dtype=None, name="input"):
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t, device="cuda") if not hasattr(t, "__cuda_array_interface__") \
+            else torch.as_tensor(t, device="cuda")
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (no CPU fallback on this path)" % name)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _split_points(points):
+    """(x, y) | (N,2) | flat interleaved xy  ->  contiguous x, y (reference: geoseries .x/.y
+    make strided copies of the interleaved buffer, core/geoseries.py:238-243)."""
+    if isinstance(points, (tuple, list)) and len(points) == 2:
+        x, y = _as_cuda(points[0], name="points.x"), _as_cuda(points[1], name="points.y")
+    else:
+        p = _as_cuda(points, name="points")
+        if p.dim() == 2 and p.shape[1] == 2:
+            x, y = p[:, 0].contiguous(), p[:, 1].contiguous()
+        elif p.dim() == 1 and p.numel() % 2 == 0:
+            x, y = p[0::2].contiguous(), p[1::2].contiguous()
+        else:
+            raise ValueError("points must be (x, y), an (N, 2) tensor or interleaved xy")
+    if x.dtype != y.dtype or x.dtype not in _DTYPE_CODE:
+        raise TypeError("point coordinates must both be float32 or float64")
+    if x.shape[0] != y.shape[0]:
+        raise RuntimeError("x and y columns must have the same length")
+    return x, y
+
+
+def _split_polygons(polygons):
+    if hasattr(polygons, "part_offset"):
+        polygons = (polygons.part_offset, polygons.ring_offset, polygons.x, polygons.y)
+    if not (isinstance(polygons, (tuple, list)) and len(polygons) == 4):
+        raise ValueError("polygons must be (part_offset, ring_offset, x, y)")
+    po, ro, vx, vy = polygons
+    vx, vy = _as_cuda(vx, name="polygons.x"), _as_cuda(vy, name="polygons.y")
+    return po, ro, vx, vy
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr() if t.numel() else 0)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _quadtree_columns(quadtree):
+    cols = []
+    for name, dt in (("key", torch.uint32), ("level", torch.uint8),
+                     ("is_internal_node", torch.bool), ("length", torch.uint32),
+                     ("offset", torch.uint32)):
+        t = _as_cuda(quadtree[name], name="quadtree." + name)
+        if t.dtype != dt:
+            t = t.to(dt)
+        cols.append(t)
+    return cols
+
+
+def _clamp_scale(x_min, x_max, y_min, y_max, scale, max_depth):
+    # indexing.py:165-186 / join.py:144-166 -- float64 arithmetic in Python, before the cast to T
+    x_min, x_max, y_min, y_max = (min(x_min, x_max), max(x_min, x_max),
+                                  min(y_min, y_max), max(y_min, y_max))
+    min_scale = max(x_max - x_min, y_max - y_min) / ((1 << max_depth) + 2)
+    if scale < min_scale:
+        warnings.warn("scale {} is less than required minimum ".format(scale)
+                      + "scale {}. Clamping to minimum scale".format(min_scale))
+    return x_min, x_max, y_min, y_max, max(scale, min_scale)
+
+
+def quadtree_on_points(points, x_min, x_max, y_min, y_max, scale, max_depth, max_size):
+    """Construct a quadtree from a set of points for a given area-of-interest bounding box.
+
+    Returns (point_indices uint32 tensor, Frame[key u32, level u8, is_internal_node bool,
+    length u32, offset u32]) -- reference: indexing.py:15-199, dtypes per test_indexing.py:27-31.
+    """
+    x, y = _split_points(points)
+    x_min, x_max, y_min, y_max, scale = _clamp_scale(x_min, x_max, y_min, y_max, scale, max_depth)
+    dev = x.device
+    with torch.cuda.device(dev):
+        alloc = _TorchAllocator(dev)
+        out = _lib.bsj_quadtree()
+        rc = _lib.lib().bsj_quadtree_on_points(
+            _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], float(x_min), float(x_max),
+            float(y_min), float(y_max), float(scale), int(max_depth), int(max_size),
+            C.byref(alloc.struct), _stream(dev), C.byref(out))
+        _lib.check(rc)
+    n, q = int(out.num_points), int(out.num_nodes)
+    point_indices = alloc.take(out.point_indices, n, torch.uint32)
+    tree = Frame([
+        ("key", alloc.take(out.key, q, torch.uint32)),
+        ("level", alloc.take(out.level, q, torch.uint8)),
+        ("is_internal_node", alloc.take(out.is_internal_node, q, torch.bool)),
+        ("length", alloc.take(out.length, q, torch.uint32)),
+        ("offset", alloc.take(out.offset, q, torch.uint32)),
+    ])
+    return point_indices, tree
+
+
+def join_quadtree_and_bounding_boxes(quadtree, bounding_boxes, x_min, x_max, y_min, y_max, scale,
+                                     max_depth):
+    """Search a quadtree for polygon or linestring bounding box intersections.
+
+    Returns Frame[bbox_offset u32, quad_offset u32] -- reference: join.py:105-175.
+    `bounding_boxes`: Frame/dict with minx, miny, maxx, maxy or a 4-tuple in that order.
+    """
+    x_min, x_max, y_min, y_max, scale = _clamp_scale(x_min, x_max, y_min, y_max, scale, max_depth)
+    if isinstance(bounding_boxes, (tuple, list)):
+        bcols = list(bounding_boxes)
+    else:
+        bcols = [bounding_boxes[c] for c in ("minx", "miny", "maxx", "maxy")]
+    if len(bcols) != 4:
+        raise RuntimeError("bbox table must have 4 columns")
+    bcols = [_as_cuda(b, name="bounding_boxes") for b in bcols]
+    if bcols[0].dtype not in _DTYPE_CODE or any(b.dtype != bcols[0].dtype for b in bcols):
+        raise TypeError("bounding box columns must all be float32 or float64")
+    tcols = _quadtree_columns(quadtree)
+    dev = bcols[0].device
+    with torch.cuda.device(dev):
+        alloc = _TorchAllocator(dev)
+        out = _lib.bsj_pairs()
+        rc = _lib.lib().bsj_join_quadtree_and_bounding_boxes(
+            *[_ptr(t) for t in tcols], tcols[0].shape[0], *[_ptr(b) for b in bcols],
+            _DTYPE_CODE[bcols[0].dtype], bcols[0].shape[0], float(x_min), float(x_max),
+            float(y_min), float(y_max), float(scale), int(max_depth), C.byref(alloc.struct),
+            _stream(dev), C.byref(out))
+        _lib.check(rc)
+    p = int(out.size)
+    return Frame([("bbox_offset", alloc.take(out.first, p, torch.uint32)),
+                  ("quad_offset", alloc.take(out.second, p, torch.uint32))])
+
+
+def quadtree_point_in_polygon(poly_quad_pairs, quadtree, point_indices, points, polygons):
+    """Test whether the specified points are inside any of the specified polygons.
+
+    Returns Frame[polygon_index u32, point_index u32]; point_index indexes `point_indices`
+    ("an index to an index") -- reference: join.py:178-262.
+    """
+    x, y = _split_points(points)
+    po, ro, vx, vy = _split_polygons(polygons)
+    if vx.dtype != vy.dtype:
+        raise RuntimeError("polygon columns must have the same data type")
+    if x.dtype != vx.dtype:
+        raise RuntimeError("points and polygons must have the same data type")
+    po = _as_cuda(po, torch.uint32 if getattr(po, "dtype", None) != torch.int32 else None)
+    ro = _as_cuda(ro, torch.uint32 if getattr(ro, "dtype", None) != torch.int32 else None)
+    if isinstance(poly_quad_pairs, (tuple, list)):
+        pp, pq = poly_quad_pairs
+    else:
+        names = list(poly_quad_pairs.columns) if hasattr(poly_quad_pairs, "columns") \
+            else list(poly_quad_pairs.keys())
+        if len(names) != 2:
+            raise RuntimeError("a quadrant-polygon table must have 2 columns")
+        pp, pq = poly_quad_pairs[names[0]], poly_quad_pairs[names[1]]
+    pp = _as_cuda(pp, torch.uint32)
+    pq = _as_cuda(pq, torch.uint32)
+    pi = _as_cuda(point_indices, torch.uint32)
+    if pi.shape[0] != x.shape[0]:
+        raise RuntimeError("number of points must be the same for both x and y columns")
+    tcols = _quadtree_columns(quadtree)
+    dev = x.device
+    with torch.cuda.device(dev):
+        alloc = _TorchAllocator(dev)
+        out = _lib.bsj_pairs()
+        rc = _lib.lib().bsj_quadtree_point_in_polygon(
+            _ptr(pp), _ptr(pq), pp.shape[0], *[_ptr(t) for t in tcols], tcols[0].shape[0],
+            _ptr(pi), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], _ptr(po), po.shape[0],
+            _ptr(ro), ro.shape[0], _ptr(vx), _ptr(vy), vx.shape[0], C.byref(alloc.struct),
+            _stream(dev), C.byref(out))
+        _lib.check(rc)
+    h = int(out.size)
+    return Frame([("polygon_index", alloc.take(out.first, h, torch.uint32)),
+                  ("point_index", alloc.take(out.second, h, torch.uint32))])
+
+
+def point_in_polygon_bitmask(points, polygons):
+    """The libcuspatial result of point_in_polygon: one INT32 per point, bit i = inside polygon i
+    (cpp/include/cuspatial/point_in_polygon.hpp:75-82)."""
+    x, y = _split_points(points)
+    po, ro, vx, vy = _split_polygons(polygons)
+    if x.dtype != vx.dtype or vx.dtype != vy.dtype:
+        raise RuntimeError("All points much have the same type for both x and y")
+    po = _as_cuda(po, torch.int32)
+    ro = _as_cuda(ro, torch.int32)
+    out = torch.empty(x.shape[0], dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().bsj_point_in_polygon(
+            _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], _ptr(po), po.shape[0], _ptr(ro),
+            ro.shape[0], _ptr(vx), _ptr(vy), vx.shape[0], _stream(x.device), _ptr(out))
+        _lib.check(rc)
+    return out
+
+
+def point_in_polygon(points, polygons):
+    """Compute from a set of points and a set of polygons which points fall within which polygons.
+
+    Returns a Frame with one bool column per polygon (column i <-> polygon i), reference:
+    join.py:23-102 (bitmask unpacked as utils/join_utils.py:12-46 does).
+    """
+    po = polygons[0] if isinstance(polygons, (tuple, list)) else polygons.part_offset
+    n_poly = max(int(po.shape[0]) - 1, 0)
+    if n_poly == 0:
+        return Frame([])
+    mask = point_in_polygon_bitmask(points, polygons)
+    return Frame([(i, ((mask >> i) & 1).to(torch.bool)) for i in range(n_poly)])
+
+
+def polygon_bounding_boxes(polygons, expansion_radius=0.0):
+    """Axis-aligned bounding box of every polygon -> Frame[minx, miny, maxx, maxy]
+    (reference: core/spatial/bounding.py:19-80)."""
+    po, ro, vx, vy = _split_polygons(polygons)
+    po = _as_cuda(po, torch.uint32 if getattr(po, "dtype", None) != torch.int32 else None)
+    ro = _as_cuda(ro, torch.uint32 if getattr(ro, "dtype", None) != torch.int32 else None)
+    n = max(int(po.shape[0]) - 1, 0)
+    outs = [torch.empty(n, dtype=vx.dtype, device=vx.device) for _ in range(4)]
+    with torch.cuda.device(vx.device):
+        rc = _lib.lib().bsj_polygon_bounding_boxes(
+            _ptr(po), po.shape[0], _ptr(ro), ro.shape[0], _ptr(vx), _ptr(vy),
+            _DTYPE_CODE[vx.dtype], vx.shape[0], float(expansion_radius), _stream(vx.device),
+            *[_ptr(o) for o in outs])
+        _lib.check(rc)
+    return Frame(zip(("minx", "miny", "maxx", "maxy"), outs))

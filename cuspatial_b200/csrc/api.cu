@@ -1,0 +1,283 @@
+// api.cu -- the C ABI (include/cuspatial_b200.h): validation, error translation, allocation
+// plumbing.  The reference-side checks are cited next to each condition.
+#include "common.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace bsj {
+
+std::atomic<u64> g_launch_count{0};
+
+// implemented in quadtree.cu / bbox_join.cu / pip.cu
+void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, double x_min,
+                             double x_max, double y_min, double y_max, double scale,
+                             int max_depth, int max_size, const bsj_allocator* mr, cudaStream_t s,
+                             bsj_quadtree* out);
+void join_quadtree_and_bounding_boxes_impl(const u32* key, const u8* level, const u8* internal,
+                                           const u32* length, const u32* offset, u64 q,
+                                           const void* bx0, const void* by0, const void* bx1,
+                                           const void* by1, int dtype, u64 n_boxes, double x_min,
+                                           double x_max, double y_min, double y_max, double scale,
+                                           int max_depth, const bsj_allocator* mr, cudaStream_t s,
+                                           bsj_pairs* out);
+void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, u64 n_pairs,
+                                    const u32* key, const u8* level, const u8* internal,
+                                    const u32* length, const u32* offset, u64 num_nodes,
+                                    const u32* point_indices, const void* px, const void* py,
+                                    int dtype, u64 n_points, const u32* poly_offsets,
+                                    u64 n_poly_offsets, const u32* ring_offsets,
+                                    u64 n_ring_offsets, const void* vx, const void* vy,
+                                    u64 n_verts, const bsj_allocator* mr, cudaStream_t s,
+                                    bsj_pairs* out);
+void point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_points,
+                           const i32* poly_offsets, u64 n_poly_offsets, const i32* ring_offsets,
+                           u64 n_ring_offsets, const void* vx, const void* vy, u64 n_verts,
+                           cudaStream_t s, i32* out_mask);
+void polygon_bounding_boxes_impl(const u32* poly_offsets, u64 n_poly_offsets,
+                                 const u32* ring_offsets, u64 n_ring_offsets, const void* vx,
+                                 const void* vy, int dtype, u64 n_verts, double r, cudaStream_t s,
+                                 void* x0, void* y0, void* x1, void* y1);
+
+namespace {
+thread_local std::string t_err;
+thread_local std::vector<std::pair<std::string, float>> t_profile;
+std::atomic<int> g_profiling{0};
+std::mutex g_pool_mutex;
+bool g_pool_done[64] = {};
+}  // namespace
+
+void ensure_pool_configured()
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  if (g_pool_done[dev]) return;
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  if (g_pool_done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = ~0ull;  // keep freed blocks cached in the pool
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  g_pool_done[dev] = true;
+}
+
+stage_timer::stage_timer(cudaStream_t stream) : s(stream), on(g_profiling.load() != 0)
+{
+  if (on) mark("begin");
+}
+void stage_timer::mark(const char* name)
+{
+  if (!on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  marks.emplace_back(name, e);
+}
+void stage_timer::finish()
+{
+  if (!on) return;
+  cudaStreamSynchronize(s);
+  for (size_t i = 1; i < marks.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+    t_profile.emplace_back(marks[i].first, ms);
+  }
+}
+stage_timer::~stage_timer()
+{
+  for (auto& m : marks) cudaEventDestroy(m.second);
+}
+
+namespace {
+template <typename F>
+int guarded(F&& f)
+{
+  try {
+    t_err.clear();
+    f();
+    return BSJ_SUCCESS;
+  } catch (error const& e) {
+    t_err = e.msg;
+    return e.code;
+  } catch (std::bad_alloc const&) {
+    t_err = "host allocation failed";
+    return BSJ_OUT_OF_MEMORY;
+  } catch (std::exception const& e) {
+    t_err = e.what();
+    return BSJ_CUDA_ERROR;
+  }
+}
+void check_dtype(int dtype)
+{
+  // cpp/src/indexing/point_quadtree.cu:55-62
+  BSJ_EXPECTS(dtype == BSJ_FLOAT32 || dtype == BSJ_FLOAT64,
+              "Only floating-point types are supported");
+}
+}  // namespace
+}  // namespace bsj
+
+using namespace bsj;
+
+extern "C" {
+
+int bsj_quadtree_on_points(const void* x, const void* y, int dtype, uint64_t n, double x_min,
+                           double x_max, double y_min, double y_max, double scale,
+                           int8_t max_depth, int32_t max_size, const bsj_allocator* mr,
+                           bsj_stream_t stream, bsj_quadtree* out)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
+    *out = bsj_quadtree{};
+    check_dtype(dtype);
+    BSJ_EXPECTS(n == 0 || (x != nullptr && y != nullptr),
+                "x and y columns must have the same length");  // point_quadtree.cu:166
+    quadtree_on_points_impl(x, y, dtype, n, x_min, x_max, y_min, y_max, scale, max_depth, max_size,
+                            mr, (cudaStream_t)stream, out);
+  });
+}
+
+int bsj_join_quadtree_and_bounding_boxes(const uint32_t* key, const uint8_t* level,
+                                         const uint8_t* is_internal_node, const uint32_t* length,
+                                         const uint32_t* offset, uint64_t num_nodes,
+                                         const void* bbox_x_min, const void* bbox_y_min,
+                                         const void* bbox_x_max, const void* bbox_y_max, int dtype,
+                                         uint64_t n_boxes, double x_min, double x_max, double y_min,
+                                         double y_max, double scale, int8_t max_depth,
+                                         const bsj_allocator* mr, bsj_stream_t stream,
+                                         bsj_pairs* out)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
+    *out = bsj_pairs{};
+    check_dtype(dtype);
+    // quadtree_bbox_filtering.cu:100-101 (a table is passed as its columns here)
+    BSJ_EXPECTS(num_nodes == 0 || (key && level && is_internal_node && length && offset),
+                "quadtree table must have 5 columns");
+    BSJ_EXPECTS(n_boxes == 0 || (bbox_x_min && bbox_y_min && bbox_x_max && bbox_y_max),
+                "bbox table must have 4 columns");
+    join_quadtree_and_bounding_boxes_impl(key, level, is_internal_node, length, offset, num_nodes,
+                                          bbox_x_min, bbox_y_min, bbox_x_max, bbox_y_max, dtype,
+                                          n_boxes, x_min, x_max, y_min, y_max, scale, max_depth, mr,
+                                          (cudaStream_t)stream, out);
+  });
+}
+
+int bsj_quadtree_point_in_polygon(const uint32_t* pair_poly, const uint32_t* pair_quad,
+                                  uint64_t n_pairs, const uint32_t* key, const uint8_t* level,
+                                  const uint8_t* is_internal_node, const uint32_t* length,
+                                  const uint32_t* offset, uint64_t num_nodes,
+                                  const uint32_t* point_indices, const void* point_x,
+                                  const void* point_y, int dtype, uint64_t n_points,
+                                  const uint32_t* poly_offsets, uint64_t n_poly_offsets,
+                                  const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+                                  const void* poly_points_x, const void* poly_points_y,
+                                  uint64_t n_poly_points, const bsj_allocator* mr,
+                                  bsj_stream_t stream, bsj_pairs* out)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
+    *out = bsj_pairs{};
+    check_dtype(dtype);
+    // quadtree_point_in_polygon.cu:154-169 (sizes/types are implied by the flat signature)
+    BSJ_EXPECTS(n_pairs == 0 || (pair_poly && pair_quad),
+                "a quadrant-polygon table must have 2 columns");
+    BSJ_EXPECTS(num_nodes == 0 || (length && offset), "a quadtree table must have 5 columns");
+    BSJ_EXPECTS(n_points == 0 || (point_indices && point_x && point_y),
+                "number of points must be the same for both x and y columns");
+    BSJ_EXPECTS(n_poly_points == 0 || (poly_points_x && poly_points_y),
+                "numbers of vertices must be the same for both x and y columns");
+    quadtree_point_in_polygon_impl(pair_poly, pair_quad, n_pairs, key, level, is_internal_node,
+                                   length, offset, num_nodes, point_indices, point_x, point_y,
+                                   dtype, n_points, poly_offsets, n_poly_offsets, ring_offsets,
+                                   n_ring_offsets, poly_points_x, poly_points_y, n_poly_points, mr,
+                                   (cudaStream_t)stream, out);
+  });
+}
+
+int bsj_point_in_polygon(const void* point_x, const void* point_y, int dtype, uint64_t n_points,
+                         const int32_t* poly_offsets, uint64_t n_poly_offsets,
+                         const int32_t* ring_offsets, uint64_t n_ring_offsets,
+                         const void* poly_points_x, const void* poly_points_y,
+                         uint64_t n_poly_points, bsj_stream_t stream, int32_t* out_mask)
+{
+  return guarded([&] {
+    check_dtype(dtype);
+    // point_in_polygon.cu:118-121
+    BSJ_EXPECTS(n_points == 0 || (point_x && point_y && out_mask),
+                "All points must have both x and y values");
+    point_in_polygon_impl(point_x, point_y, dtype, n_points, poly_offsets, n_poly_offsets,
+                          ring_offsets, n_ring_offsets, poly_points_x, poly_points_y, n_poly_points,
+                          (cudaStream_t)stream, out_mask);
+  });
+}
+
+int bsj_polygon_bounding_boxes(const uint32_t* poly_offsets, uint64_t n_poly_offsets,
+                               const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+                               const void* poly_points_x, const void* poly_points_y, int dtype,
+                               uint64_t n_poly_points, double expansion_radius,
+                               bsj_stream_t stream, void* out_x_min, void* out_y_min,
+                               void* out_x_max, void* out_y_max)
+{
+  return guarded([&] {
+    check_dtype(dtype);
+    // polygon_bounding_boxes.cu:144-151
+    BSJ_EXPECTS(expansion_radius >= 0, "expansion radius must be greater or equal than 0");
+    polygon_bounding_boxes_impl(poly_offsets, n_poly_offsets, ring_offsets, n_ring_offsets,
+                                poly_points_x, poly_points_y, dtype, n_poly_points,
+                                expansion_radius, (cudaStream_t)stream, out_x_min, out_y_min,
+                                out_x_max, out_y_max);
+  });
+}
+
+void bsj_free(void* ptr, bsj_stream_t stream)
+{
+  if (ptr) cudaFreeAsync(ptr, (cudaStream_t)stream);
+}
+void bsj_free_quadtree(bsj_quadtree* t, bsj_stream_t stream)
+{
+  if (!t) return;
+  bsj_free(t->point_indices, stream);
+  bsj_free(t->key, stream);
+  bsj_free(t->level, stream);
+  bsj_free(t->is_internal_node, stream);
+  bsj_free(t->length, stream);
+  bsj_free(t->offset, stream);
+  *t = bsj_quadtree{};
+}
+void bsj_free_pairs(bsj_pairs* p, bsj_stream_t stream)
+{
+  if (!p) return;
+  bsj_free(p->first, stream);
+  bsj_free(p->second, stream);
+  *p = bsj_pairs{};
+}
+
+const char* bsj_last_error(void) { return t_err.c_str(); }
+const char* bsj_version(void) { return "cuspatial_b200 0.1 (sm_100a)"; }
+uint64_t bsj_kernel_launch_count(void) { return g_launch_count.load(); }
+
+void bsj_set_profiling(int enabled)
+{
+  g_profiling.store(enabled);
+  t_profile.clear();
+}
+int bsj_get_profile(const char** names, float* millis, int capacity)
+{
+  static thread_local std::vector<std::string> keep;
+  keep.clear();
+  int n = 0;
+  for (auto& e : t_profile) {
+    if (n >= capacity) break;
+    keep.push_back(e.first);
+    ++n;
+  }
+  for (int i = 0; i < n; ++i) {
+    names[i]  = keep[i].c_str();
+    millis[i] = t_profile[i].second;
+  }
+  t_profile.clear();
+  return n;
+}
+
+}  // extern "C"

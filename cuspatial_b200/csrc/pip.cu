@@ -1,0 +1,649 @@
+// pip.cu -- B200-native point-in-polygon refinement
+// (replaces cuspatial::quadtree_point_in_polygon and the bitmask cuspatial::point_in_polygon).
+//
+// Reference behaviour restated:
+//   cpp/include/cuspatial/detail/join/quadtree_point_in_polygon.cuh:41-94,104-235 (candidate
+//   enumeration in (pair, local point) order, stable compaction),
+//   detail/algorithm/is_point_in_polygon.cuh:46-101 (crossings-multiply, on-edge => false),
+//   detail/utility/floating_point.cuh:96-130 (4-ULP float_equal),
+//   detail/point_in_polygon.cuh:43-102 (bitmask over <= 31 polygons).
+//
+// Design (not a port).  The reference tests every candidate against EVERY vertex of its polygon
+// after a ~19-step binary search and two dependent random gathers per candidate.  Here:
+//   * pairs that share a quadrant form a RUN (the join emits them adjacent); one warp owns a run,
+//     gathers the quadrant's points ONCE (256-point tiles, 8 per lane, coordinates in registers)
+//     and reuses them for every polygon of the run;
+//   * per (tile, polygon) the warp scans the polygon's edges 32 at a time and keeps only the
+//     edges that can influence a point of the tile -- the predicate is
+//         inside = XOR_e crossing(e)  AND NOT  OR_e on_edge(e),
+//     crossing(e) needs the point's y inside the edge's y-range, on_edge(e) needs the point within
+//     a few ULP of the segment (or the edge vertical and x equal) -- so edges whose (slightly
+//     widened) y-range misses the tile's y-range, and that are not vertical edges inside the
+//     tile's x-range, are skipped EXACTLY.  Surviving edges are broadcast by shuffle and evaluated
+//     with the reference's own arithmetic, operation for operation (separately rounded products,
+//     no FMA: __dmul_rn/__dsub_rn);
+//   * results leave as 32-bit ballot words in (pair, point) order; a 64-bit scan of the per-pair
+//     hit counts gives every pair its output offset and a second kernel expands the words into
+//     (polygon_index, point_index) rows -- the reference's stable copy_if order, exact output size,
+//     no worst-case buffer (quadtree_point_in_polygon.cuh:195-196) and no OOM retry.
+//   The exact-skipping argument needs products that neither underflow nor overflow; polygons or
+//   point tiles with coordinates outside [2^-200, 2^200] (fp32: [2^-30, 2^30]), NaN or Inf fall
+//   back to evaluating every edge in the reference's order (pip_reference below).
+#include "scan.cuh"
+
+#include <cstdlib>
+
+namespace bsj {
+
+namespace {
+
+template <typename T>
+struct fpp;
+template <>
+struct fpp<float> {
+  using bits_t = u32;
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ u32 bits(float a) { return __float_as_uint(a); }
+  static __host__ __device__ constexpr float tiny() { return 9.313225746154785e-10f; }  // 2^-30
+  static __host__ __device__ constexpr float huge() { return 1073741824.0f; }           // 2^30
+  static __host__ __device__ constexpr float eps() { return 6.103515625e-05f; }         // 2^-14
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <>
+struct fpp<double> {
+  using bits_t = u64;
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ u64 bits(double a) { return (u64)__double_as_longlong(a); }
+  static __host__ __device__ constexpr double tiny() { return 6.223015277861142e-61; }   // 2^-200
+  static __host__ __device__ constexpr double huge() { return 1.6069380442589903e+60; }  // 2^200
+  static __host__ __device__ constexpr double eps() { return 9.094947017729282e-13; }    // 2^-40
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
+};
+
+// floating_point.cuh:118-130 (max_ulp = 4)
+template <typename T>
+__device__ __forceinline__ bool float_equal(T a, T b)
+{
+  using B = typename fpp<T>::bits_t;
+  if (a != a || b != b) return false;
+  B const sign = (B)1 << (sizeof(B) * 8 - 1);
+  B const ia = fpp<T>::bits(a), ib = fpp<T>::bits(b);
+  B const ba = (ia & sign) ? (B)(~ia + 1) : (B)(ia | sign);
+  B const bb = (ib & sign) ? (B)(~ib + 1) : (B)(ib | sign);
+  return ba >= bb ? (ba - bb) <= 4 : (bb - ba) <= 4;
+}
+
+// |c| is zero or a "comfortable" normal number (see header comment)
+template <typename T>
+__device__ __forceinline__ bool comfy(T c)
+{
+  T const a = fabs(c);
+  return a == (T)0 || (a >= fpp<T>::tiny() && a <= fpp<T>::huge());  // false for NaN/Inf
+}
+template <typename T>
+__device__ __forceinline__ bool comfy_delta(T d)  // edge run/rise
+{
+  T const a = fabs(d);
+  return a == (T)0 || (a >= fpp<T>::tiny() && a <= (T)2 * fpp<T>::huge());
+}
+
+// is_point_in_polygon.cuh:46-101, operation for operation (fallback path, any input).
+template <typename T>
+__device__ bool pip_reference(T px, T py, const u32* __restrict__ ring_offsets, u32 r0, u32 r1,
+                              const T* __restrict__ vx, const T* __restrict__ vy)
+{
+  bool within  = false;
+  bool on_edge = false;
+  for (u32 r = r0; r < r1; ++r) {
+    u32 const v0 = ring_offsets[r], v1 = ring_offsets[r + 1];
+    if (v1 <= v0) continue;  // the reference would read out of bounds
+    T bx    = __ldg(vx + v1 - 1);
+    T by    = __ldg(vy + v1 - 1);
+    bool y0 = by > py;
+    for (u32 i = v0; i < v1; ++i) {
+      T const ax = __ldg(vx + i), ay = __ldg(vy + i);
+      T const run  = fpp<T>::sub(bx, ax);
+      T const rise = fpp<T>::sub(by, ay);
+      if (float_equal(run, (T)0) && float_equal(rise, (T)0)) continue;  // b NOT advanced (:65-66)
+      T const rtp  = fpp<T>::sub(py, ay);
+      T const rntp = fpp<T>::sub(px, ax);
+      T const u    = fpp<T>::mul(run, rtp);
+      T const v    = fpp<T>::mul(rntp, rise);
+      if (float_equal(u, v)) {
+        T const lo = ax > bx ? bx : ax, hi = ax > bx ? ax : bx;
+        if (lo <= px && px <= hi) {
+          on_edge = true;
+          break;
+        }
+      }
+      bool const y1 = ay > py;
+      if (y1 != y0) {
+        if ((v < u) != y1) within = !within;
+      }
+      bx = ax;
+      by = ay;
+      y0 = y1;
+    }
+    if (on_edge) {
+      within = false;
+      break;
+    }
+  }
+  return within;
+}
+
+// Per-polygon facts computed once per call.
+template <typename T>
+struct poly_meta {
+  T xmin, ymin, xmax, ymax;
+  u32 ring_begin, ring_end;
+  u32 safe;  // every coordinate / edge delta "comfy": exact edge skipping is allowed
+  u32 pad;
+};
+
+// one warp per polygon
+template <typename T>
+__global__ void __launch_bounds__(128)
+poly_meta_kernel(const u32* __restrict__ poly_offsets, u32 n_poly,
+                 const u32* __restrict__ ring_offsets, u32 n_rings, const T* __restrict__ vx,
+                 const T* __restrict__ vy, u32 n_verts, poly_meta<T>* __restrict__ meta)
+{
+  u32 const p    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  u32 const lane = lane_id();
+  if (p >= n_poly) return;
+  u32 const r0 = poly_offsets[p], r1 = poly_offsets[p + 1];
+  T xmin = fpp<T>::inf(), ymin = fpp<T>::inf(), xmax = -fpp<T>::inf(), ymax = -fpp<T>::inf();
+  bool safe = r0 <= r1 && r1 <= n_rings;
+  if (safe) {
+    for (u32 r = r0; r < r1; ++r) {
+      u32 const v0 = ring_offsets[r], v1 = ring_offsets[r + 1];
+      if (v1 > n_verts || v0 > v1) {
+        safe = false;
+        break;
+      }
+      for (u32 i = v0 + lane; i < v1; i += 32) {
+        u32 const pr = i == v0 ? v1 - 1 : i - 1;
+        T const ax = vx[i], ay = vy[i], bx = vx[pr], by = vy[pr];
+        xmin = fmin(xmin, ax); xmax = fmax(xmax, ax);
+        ymin = fmin(ymin, ay); ymax = fmax(ymax, ay);
+        safe = safe && comfy(ax) && comfy(ay) && comfy_delta(fpp<T>::sub(bx, ax)) &&
+               comfy_delta(fpp<T>::sub(by, ay));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+    xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+  }
+  safe = __all_sync(0xffffffffu, safe);
+  if (lane == 0) {
+    poly_meta<T> m;
+    m.xmin = xmin; m.ymin = ymin; m.xmax = xmax; m.ymax = ymax;
+    m.ring_begin = r0; m.ring_end = r1; m.safe = safe ? 1u : 0u; m.pad = 0;
+    meta[p] = m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair bookkeeping
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pair_prep_kernel(const u32* __restrict__ pair_quad, u32 n_pairs, const u32* __restrict__ length,
+                 u32 num_nodes, u32* __restrict__ words, u32* __restrict__ heads)
+{
+  u32 const j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pairs) return;
+  u32 const q   = pair_quad[j];
+  u32 const len = q < num_nodes ? length[q] : 0u;
+  words[j]      = len / 32 + ((len & 31) != 0);
+  heads[j]      = (j == 0 || pair_quad[j - 1] != q) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+run_start_kernel(const u32* __restrict__ heads, const u64* __restrict__ run_idx, u32 n_pairs,
+                 const u64* __restrict__ n_runs, u32* __restrict__ run_start)
+{
+  u32 const j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pairs) return;
+  if (heads[j]) run_start[run_idx[j]] = j;
+  if (j == n_pairs - 1) run_start[*n_runs] = n_pairs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// evaluation: one warp per run of pairs sharing a quadrant
+// ---------------------------------------------------------------------------------------------
+constexpr int kPipWarps = 4;
+constexpr int kPPL      = 8;          // points per lane
+constexpr int kPipTile  = 32 * kPPL;  // points per tile
+
+template <typename T>
+__global__ void __launch_bounds__(kPipWarps * 32)
+pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad,
+                const u32* __restrict__ run_start, const u64* __restrict__ n_runs_ptr,
+                const u32* __restrict__ length, const u32* __restrict__ offset, u32 num_nodes,
+                const u32* __restrict__ point_indices, u32 n_points, const T* __restrict__ px,
+                const T* __restrict__ py, const poly_meta<T>* __restrict__ meta, u32 n_poly,
+                const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
+                const T* __restrict__ vy, const u64* __restrict__ wbase,
+                u32* __restrict__ mask_words, u32* __restrict__ hits, u32* __restrict__ ticket,
+                int force_reference)
+{
+  u32 const lane   = lane_id();
+  u32 const n_runs = (u32)*n_runs_ptr;
+
+  while (true) {
+    u32 r = 0;
+    if (lane == 0) r = atomicAdd(ticket, 1u);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= n_runs) break;
+
+    u32 const j0 = run_start[r], j1 = run_start[r + 1];
+    u32 const quad = pair_quad[j0];
+    if (quad >= num_nodes) {  // malformed pair: no candidates (words == 0 as well)
+      for (u32 j = j0 + lane; j < j1; j += 32) hits[j] = 0;
+      continue;
+    }
+    u32 const len = length[quad], off = offset[quad];
+    if (len == 0) {
+      for (u32 j = j0 + lane; j < j1; j += 32) hits[j] = 0;
+      continue;
+    }
+
+    for (u32 base = 0; base < len; base += kPipTile) {
+      // ---- gather this tile's points once (quadtree_point_in_polygon.cuh:66,170)
+      u32 idx[kPPL];
+      u32 valid = 0;
+#pragma unroll
+      for (int i = 0; i < kPPL; ++i) {
+        u32 const l = base + i * 32 + lane;
+        bool const ok = l < len && off + l < n_points;
+        valid |= (u32)ok << i;
+        idx[i] = ok ? __ldcs(point_indices + off + l) : 0xFFFFFFFFu;
+      }
+      T x[kPPL], y[kPPL];
+#pragma unroll
+      for (int i = 0; i < kPPL; ++i) {
+        bool const ok = idx[i] < n_points;
+        if (!ok) valid &= ~(1u << i);
+        x[i] = ok ? __ldg(px + idx[i]) : (T)0;
+        y[i] = ok ? __ldg(py + idx[i]) : (T)0;
+      }
+      // invalid slots mirror the tile's first point so they neither widen the bbox nor trap
+      T const fx = __shfl_sync(0xffffffffu, x[0], 0), fy = __shfl_sync(0xffffffffu, y[0], 0);
+      T tx0 = fx, tx1 = fx, ty0 = fy, ty1 = fy;
+      bool pts_ok = true;
+#pragma unroll
+      for (int i = 0; i < kPPL; ++i) {
+        if (!((valid >> i) & 1u)) {
+          x[i] = fx;
+          y[i] = fy;
+        }
+        tx0 = fmin(tx0, x[i]); tx1 = fmax(tx1, x[i]);
+        ty0 = fmin(ty0, y[i]); ty1 = fmax(ty1, y[i]);
+        pts_ok = pts_ok && comfy(x[i]) && comfy(y[i]);
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        tx0 = fmin(tx0, __shfl_xor_sync(0xffffffffu, tx0, o));
+        ty0 = fmin(ty0, __shfl_xor_sync(0xffffffffu, ty0, o));
+        tx1 = fmax(tx1, __shfl_xor_sync(0xffffffffu, tx1, o));
+        ty1 = fmax(ty1, __shfl_xor_sync(0xffffffffu, ty1, o));
+      }
+      bool const tile_safe = __all_sync(0xffffffffu, pts_ok) && !force_reference;
+      u32 const tile_words = (min(len - base, (u32)kPipTile) + 31) / 32;  // <= 8
+
+      for (u32 j = j0; j < j1; ++j) {
+        u32 const poly = pair_poly[j];
+        u32 inside     = 0;  // bit i: point i of this lane is inside
+        if (poly < n_poly) {
+          poly_meta<T> const m = meta[poly];
+          if (tile_safe && m.safe) {
+            T const mx = fpp<T>::eps() * fmax(fabs(m.xmin), fabs(m.xmax));
+            bool const miss = ty1 < m.ymin || ty0 >= m.ymax || tx1 < m.xmin - mx ||
+                              tx0 > m.xmax + mx;
+            if (!miss) {
+              u32 within = 0, onedge = 0;
+              for (u32 ring = m.ring_begin; ring < m.ring_end; ++ring) {
+                u32 const v0 = ring_offsets[ring], v1 = ring_offsets[ring + 1];
+                u32 const nv = v1 - v0;
+                for (u32 c0 = 0; c0 < nv; c0 += 32) {
+                  u32 const e    = c0 + lane;
+                  bool const has = e < nv;
+                  T ax = 0, ay = 0, bx = 0, by = 0;
+                  bool rel = false;
+                  if (has) {
+                    u32 const pr = e == 0 ? nv - 1 : e - 1;
+                    ax = __ldg(vx + v0 + e);  ay = __ldg(vy + v0 + e);
+                    bx = __ldg(vx + v0 + pr); by = __ldg(vy + v0 + pr);
+                    T const ylo = fmin(ay, by), yhi = fmax(ay, by);
+                    T const dl  = fpp<T>::eps() * fmax(fabs(ay), fabs(by));
+                    bool const yrel = ty1 >= ylo - dl && ty0 <= yhi + dl;
+                    bool const vert = ax == bx && tx0 <= ax && ax <= tx1;
+                    rel = !(ax == bx && ay == by) && (yrel || vert);
+                  }
+                  u32 em = __ballot_sync(0xffffffffu, rel);
+                  while (em) {
+                    int const src = __ffs(em) - 1;
+                    em &= em - 1;
+                    T const eax = __shfl_sync(0xffffffffu, ax, src);
+                    T const eay = __shfl_sync(0xffffffffu, ay, src);
+                    T const ebx = __shfl_sync(0xffffffffu, bx, src);
+                    T const eby = __shfl_sync(0xffffffffu, by, src);
+                    T const run  = fpp<T>::sub(ebx, eax);
+                    T const rise = fpp<T>::sub(eby, eay);
+                    T const lo = fmin(eax, ebx), hi = fmax(eax, ebx);
+#pragma unroll
+                    for (int i = 0; i < kPPL; ++i) {
+                      T const rtp  = fpp<T>::sub(y[i], eay);
+                      T const rntp = fpp<T>::sub(x[i], eax);
+                      T const u    = fpp<T>::mul(run, rtp);
+                      T const v    = fpp<T>::mul(rntp, rise);
+                      if (lo <= x[i] && x[i] <= hi) {
+                        if (float_equal(u, v)) onedge |= 1u << i;
+                      }
+                      bool const y1 = eay > y[i], y0 = eby > y[i];
+                      bool const cross = (y1 != y0) && ((v < u) != y1);
+                      within ^= (u32)cross << i;
+                    }
+                  }
+                }
+              }
+              inside = within & ~onedge;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < kPPL; ++i)  // unrolled: x[]/y[] must stay in registers
+              if ((valid >> i) & 1u)
+                inside |= (u32)pip_reference<T>(x[i], y[i], ring_offsets, m.ring_begin,
+                                                m.ring_end, vx, vy)
+                          << i;
+          }
+        }
+        inside &= valid;
+        // ---- ballot words in (pair, local point) order: word i covers points base+32i .. +31
+        u32 mine = 0, cnt = 0;
+#pragma unroll
+        for (int i = 0; i < kPPL; ++i) {
+          u32 const w = __ballot_sync(0xffffffffu, (inside >> i) & 1u);
+          if (lane == (u32)i) mine = w;
+          cnt += __popc(w);
+        }
+        if (lane < tile_words) mask_words[wbase[j] + base / 32 + lane] = mine;
+        if (lane == 0) hits[j] = (base == 0 ? 0u : hits[j]) + cnt;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// expansion of ballot words into (polygon_index, point_index) rows; one warp per pair
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad, u32 n_pairs,
+                const u32* __restrict__ length, const u32* __restrict__ offset, u32 num_nodes,
+                const u64* __restrict__ wbase, const u64* __restrict__ obase,
+                const u32* __restrict__ hits, const u32* __restrict__ mask_words,
+                u32* __restrict__ out_poly, u32* __restrict__ out_point)
+{
+  u32 const lane    = lane_id();
+  u32 const warps   = (gridDim.x * blockDim.x) >> 5;
+  for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_pairs; j += warps) {
+    if (hits[j] == 0) continue;
+    u32 const quad = pair_quad[j];
+    if (quad >= num_nodes) continue;
+    u32 const poly = pair_poly[j], len = length[quad], off = offset[quad];
+    u32 const words = len / 32 + ((len & 31) != 0);
+    u64 const wb    = wbase[j];
+    u64 o           = obase[j];
+    for (u32 w0 = 0; w0 < words; w0 += 32) {
+      u32 w = w0 + lane < words ? __ldcs(mask_words + wb + w0 + lane) : 0u;
+      u32 const c    = __popc(w);
+      u32 const incl = warp_inclusive_scan(c);
+      u64 at         = o + incl - c;
+      u32 const pt0  = off + (w0 + lane) * 32;
+      while (w) {
+        int const b = __ffs(w) - 1;
+        w &= w - 1;
+        out_poly[at]  = poly;
+        out_point[at] = pt0 + b;
+        ++at;
+      }
+      o += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bitmask point_in_polygon (<= 31 polygons): one thread per point
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+pip_bitmask_kernel(const T* __restrict__ px, const T* __restrict__ py, u64 n_points,
+                   const poly_meta<T>* __restrict__ meta, u32 n_poly,
+                   const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
+                   const T* __restrict__ vy, i32* __restrict__ out, int force_reference)
+{
+  __shared__ poly_meta<T> s_meta[31];
+  for (u32 i = threadIdx.x; i < n_poly; i += blockDim.x) s_meta[i] = meta[i];
+  __syncthreads();
+  u64 const stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += stride) {
+    T const x = __ldcs(px + i), y = __ldcs(py + i);
+    bool const p_ok = comfy(x) && comfy(y) && !force_reference;
+    i32 mask = 0;
+    for (u32 p = 0; p < n_poly; ++p) {
+      poly_meta<T> const& m = s_meta[p];
+      if (p_ok && m.safe) {
+        // exact rejections: no edge can straddle y outside [ymin, ymax); x beyond the widened
+        // extent decides every crossing comparison with certainty (parity even => outside)
+        T const mx = fpp<T>::eps() * fmax(fabs(m.xmin), fabs(m.xmax));
+        if (y < m.ymin || y >= m.ymax || x < m.xmin - mx || x > m.xmax + mx) continue;
+      }
+      mask |= (i32)pip_reference<T>(x, y, ring_offsets, m.ring_begin, m.ring_end, vx, vy) << p;
+    }
+    __stcs(out + i, mask);
+  }
+}
+
+// per-polygon bounding boxes (detail/bounding_boxes.cuh:36-60,136-184): min/max of (v -+ r)
+template <typename T>
+__global__ void __launch_bounds__(128)
+poly_bbox_kernel(const u32* __restrict__ poly_offsets, u32 n_poly,
+                 const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
+                 const T* __restrict__ vy, u32 n_verts, T r, T* __restrict__ ox0,
+                 T* __restrict__ oy0, T* __restrict__ ox1, T* __restrict__ oy1)
+{
+  u32 const p    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  u32 const lane = lane_id();
+  if (p >= n_poly) return;
+  u32 const v0 = ring_offsets[poly_offsets[p]];
+  u32 const v1 = min(ring_offsets[poly_offsets[p + 1]], n_verts);
+  T xmin = fpp<T>::inf(), ymin = fpp<T>::inf(), xmax = -fpp<T>::inf(), ymax = -fpp<T>::inf();
+  for (u32 i = v0 + lane; i < v1; i += 32) {
+    T const ax = vx[i], ay = vy[i];
+    xmin = fmin(xmin, fpp<T>::sub(ax, r)); ymin = fmin(ymin, fpp<T>::sub(ay, r));
+    xmax = fmax(xmax, ax + r);             ymax = fmax(ymax, ay + r);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+    xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+  }
+  if (lane == 0) {
+    ox0[p] = xmin; oy0[p] = ymin; ox1[p] = xmax; oy1[p] = ymax;
+  }
+}
+
+int force_reference_mode()
+{
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("BSJ_PIP_REFERENCE_LOOP");
+    v             = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
+template <typename T>
+void qpip_impl_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const u32* length,
+                 const u32* offset, u64 num_nodes, const u32* point_indices, const void* px,
+                 const void* py, u64 n_points, const u32* poly_offsets, u64 n_poly_offsets,
+                 const u32* ring_offsets, u64 n_ring_offsets, const void* vx, const void* vy,
+                 u64 n_verts, const bsj_allocator* mr, cudaStream_t s, bsj_pairs* out)
+{
+  stage_timer tm(s);
+  u32 const n_poly = (u32)(n_poly_offsets - 1);
+  dev_buf<poly_meta<T>> meta(std::max<u32>(n_poly, 1), s);
+  if (n_poly) {
+    poly_meta_kernel<T><<<div_up((u64)n_poly * 32, 128), 128, 0, s>>>(
+      poly_offsets, n_poly, ring_offsets, (u32)(n_ring_offsets ? n_ring_offsets - 1 : 0),
+      (const T*)vx, (const T*)vy, (u32)n_verts, meta.get());
+    BSJ_CHECK_LAUNCH();
+  }
+  dev_buf<u32> words(n_pairs, s), heads(n_pairs, s), hits(n_pairs, s), run_start(n_pairs + 1, s);
+  dev_buf<u64> wbase(n_pairs, s), run_idx(n_pairs, s), obase(n_pairs, s), totals(4, s);
+  dev_buf<u32> ticket(1, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
+  pair_prep_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(pair_quad, (u32)n_pairs, length,
+                                                        (u32)num_nodes, words.get(), heads.get());
+  BSJ_CHECK_LAUNCH();
+  exclusive_scan_u32_to_u64(words.get(), wbase.get(), n_pairs, totals.get() + 0, s);
+  exclusive_scan_u32_to_u64(heads.get(), run_idx.get(), n_pairs, totals.get() + 1, s);
+  run_start_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(heads.get(), run_idx.get(), (u32)n_pairs,
+                                                        totals.get() + 1, run_start.get());
+  BSJ_CHECK_LAUNCH();
+  u64 h_tot[2] = {0, 0};
+  BSJ_CUDA_TRY(cudaMemcpyAsync(h_tot, totals.get(), 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+  u64 const total_words = h_tot[0], n_runs = h_tot[1];
+  tm.mark("pair_prep");
+
+  dev_buf<u32> mask_words(std::max<u64>(total_words, 1), s);
+  {
+    int const grid = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_runs, kPipWarps));
+    pip_eval_kernel<T><<<std::max(grid, 1), kPipWarps * 32, 0, s>>>(
+      pair_poly, pair_quad, run_start.get(), totals.get() + 1, length, offset, (u32)num_nodes,
+      point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly, ring_offsets,
+      (const T*)vx, (const T*)vy, wbase.get(), mask_words.get(), hits.get(), ticket.get(),
+      force_reference_mode());
+    BSJ_CHECK_LAUNCH();
+  }
+  tm.mark("pip_eval");
+  exclusive_scan_u32_to_u64(hits.get(), obase.get(), n_pairs, totals.get() + 2, s);
+  u64 h_hits = 0;
+  BSJ_CUDA_TRY(cudaMemcpyAsync(&h_hits, totals.get() + 2, sizeof(u64), cudaMemcpyDeviceToHost, s));
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+  out_alloc oa(mr, s);
+  out->size = h_hits;
+  if (h_hits) {
+    out->first  = oa.get<u32>(h_hits);
+    out->second = oa.get<u32>(h_hits);
+    int const grid = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_pairs * 32, 256));
+    pip_emit_kernel<<<std::max(grid, 1), 256, 0, s>>>(
+      pair_poly, pair_quad, (u32)n_pairs, length, offset, (u32)num_nodes, wbase.get(),
+      obase.get(), hits.get(), mask_words.get(), out->first, out->second);
+    BSJ_CHECK_LAUNCH();
+  }
+  tm.mark("pip_emit");
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+  tm.finish();
+  oa.commit();
+}
+
+template <typename T>
+void pip_bitmask_t(const void* px, const void* py, u64 n_points, const u32* poly_offsets,
+                   u64 n_poly_offsets, const u32* ring_offsets, u64 n_ring_offsets,
+                   const void* vx, const void* vy, u64 n_verts, cudaStream_t s, i32* out)
+{
+  stage_timer tm(s);
+  u32 const n_poly = (u32)(n_poly_offsets ? n_poly_offsets - 1 : 0);
+  dev_buf<poly_meta<T>> meta(std::max<u32>(n_poly, 1), s);
+  if (n_poly) {
+    poly_meta_kernel<T><<<div_up((u64)n_poly * 32, 128), 128, 0, s>>>(
+      poly_offsets, n_poly, ring_offsets, (u32)(n_ring_offsets ? n_ring_offsets - 1 : 0),
+      (const T*)vx, (const T*)vy, (u32)n_verts, meta.get());
+    BSJ_CHECK_LAUNCH();
+  }
+  int const grid = (int)std::min<u64>((u64)kNumSMs * 16, (u64)div_up(n_points, 256));
+  pip_bitmask_kernel<T><<<std::max(grid, 1), 256, 0, s>>>(
+    (const T*)px, (const T*)py, n_points, meta.get(), n_poly, ring_offsets, (const T*)vx,
+    (const T*)vy, out, force_reference_mode());
+  BSJ_CHECK_LAUNCH();
+  tm.mark("pip_bitmask");
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+  tm.finish();
+}
+
+}  // namespace
+
+void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, u64 n_pairs,
+                                    const u32* key, const u8* level, const u8* internal,
+                                    const u32* length, const u32* offset, u64 num_nodes,
+                                    const u32* point_indices, const void* px, const void* py,
+                                    int dtype, u64 n_points, const u32* poly_offsets,
+                                    u64 n_poly_offsets, const u32* ring_offsets,
+                                    u64 n_ring_offsets, const void* vx, const void* vy,
+                                    u64 n_verts, const bsj_allocator* mr, cudaStream_t s,
+                                    bsj_pairs* out)
+{
+  (void)key; (void)level; (void)internal;
+  *out = bsj_pairs{};
+  // empty inputs: cpp/src/join/quadtree_point_in_polygon.cu:171-178
+  if (n_pairs == 0 || num_nodes == 0 || n_points == 0 || n_poly_offsets == 0) return;
+  BSJ_EXPECTS(n_pairs < 0xFFFFFFFFull && num_nodes < 0xFFFFFFFFull && n_points <= 0xFFFFFFFFull,
+              "table too large");
+  BSJ_EXPECTS(n_ring_offsets >= 1 || n_poly_offsets <= 1, "ring offsets must not be empty");
+  if (dtype == BSJ_FLOAT32)
+    qpip_impl_t<float>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes, point_indices, px,
+                       py, n_points, poly_offsets, n_poly_offsets, ring_offsets, n_ring_offsets,
+                       vx, vy, n_verts, mr, s, out);
+  else
+    qpip_impl_t<double>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes, point_indices,
+                        px, py, n_points, poly_offsets, n_poly_offsets, ring_offsets,
+                        n_ring_offsets, vx, vy, n_verts, mr, s, out);
+}
+
+void point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_points,
+                           const i32* poly_offsets, u64 n_poly_offsets, const i32* ring_offsets,
+                           u64 n_ring_offsets, const void* vx, const void* vy, u64 n_verts,
+                           cudaStream_t s, i32* out_mask)
+{
+  // detail/point_in_polygon.cuh:93-94
+  BSJ_EXPECTS(n_poly_offsets == 0 || n_poly_offsets - 1 <= 31, "Number of polygons cannot exceed 31");
+  if (n_points == 0) return;
+  // offsets are non-negative int32: reinterpreting as uint32 is value preserving
+  if (dtype == BSJ_FLOAT32)
+    pip_bitmask_t<float>(px, py, n_points, (const u32*)poly_offsets, n_poly_offsets,
+                         (const u32*)ring_offsets, n_ring_offsets, vx, vy, n_verts, s, out_mask);
+  else
+    pip_bitmask_t<double>(px, py, n_points, (const u32*)poly_offsets, n_poly_offsets,
+                          (const u32*)ring_offsets, n_ring_offsets, vx, vy, n_verts, s, out_mask);
+}
+
+void polygon_bounding_boxes_impl(const u32* poly_offsets, u64 n_poly_offsets,
+                                 const u32* ring_offsets, u64 n_ring_offsets, const void* vx,
+                                 const void* vy, int dtype, u64 n_verts, double r, cudaStream_t s,
+                                 void* x0, void* y0, void* x1, void* y1)
+{
+  if (n_poly_offsets < 2 || n_ring_offsets < 2 || n_verts == 0) return;
+  u32 const n_poly = (u32)(n_poly_offsets - 1);
+  if (dtype == BSJ_FLOAT32)
+    poly_bbox_kernel<float><<<div_up((u64)n_poly * 32, 128), 128, 0, s>>>(
+      poly_offsets, n_poly, ring_offsets, (const float*)vx, (const float*)vy, (u32)n_verts,
+      (float)r, (float*)x0, (float*)y0, (float*)x1, (float*)y1);
+  else
+    poly_bbox_kernel<double><<<div_up((u64)n_poly * 32, 128), 128, 0, s>>>(
+      poly_offsets, n_poly, ring_offsets, (const double*)vx, (const double*)vy, (u32)n_verts, r,
+      (double*)x0, (double*)y0, (double*)x1, (double*)y1);
+  BSJ_CHECK_LAUNCH();
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+}
+
+}  // namespace bsj

@@ -1,0 +1,424 @@
+// quadtree.cu -- B200-native quadtree builder (replaces cuspatial::quadtree_on_points).
+//
+// Reference behaviour restated: cpp/include/cuspatial/detail/point_quadtree.cuh:238-272 (clamps),
+// detail/index/construction/phase_1.cuh:60-95 (Morton keys + stable sort),
+// phase_1.cuh:108-381 + phase_2.cuh:56-345 + detail/point_quadtree.cuh:43-188 (tree arrays).
+//
+// Design (not a port): the reference materialises every non-empty cell of every level bottom-up
+// (~2.5 N nodes, ~18 GB transient for 100 M points) and prunes afterwards.  Here the tree is built
+// TOP-DOWN from the sorted keys: a node is a key range [start, start+cnt) of the sorted array, its
+// children are found with binary searches inside that range, and only nodes that survive the
+// max_size rule are ever created.  Rows come out directly in the reference's (level, key) order
+// with children contiguous, so `offset`/`length` need no post-pass.  Work is O(Q log(N/Q)) instead
+// of O(N * depth); the N-sized work is the Morton encode (+ fused digit histograms) and the
+// onesweep sort.
+#include "radix_sort.cuh"
+
+namespace bsj {
+
+namespace {
+
+// z_order.cuh:62-77 -- arithmetic dilation instead of the reference's lookup tables
+__device__ __forceinline__ u32 dilate16(u32 v)
+{
+  v &= 0xFFFFu;
+  v = (v | (v << 8)) & 0x00FF00FFu;
+  v = (v | (v << 4)) & 0x0F0F0F0Fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+
+template <typename T>
+struct fp;
+template <>
+struct fp<float> {
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ u32 to_u32(float v) { return __float2uint_rz(v); }
+};
+template <>
+struct fp<double> {
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ u32 to_u32(double v) { return __double2uint_rz(v); }
+};
+
+// phase_1.cuh:78-85.  static_cast<uint16_t>(T) compiles to cvt.rzi.u32 (saturating, NaN -> 0)
+// followed by & 0xFFFF, restated explicitly.  IEEE division (the reference builds with the default
+// -prec-div=true), no reciprocal multiply.
+template <typename T>
+__device__ __forceinline__ u32 point_key(T x, T y, T min_x, T min_y, T max_x, T max_y, T scale,
+                                         u32 oob_key)
+{
+  if (x < min_x || x > max_x || y < min_y || y > max_y) return oob_key;
+  u32 const ix = fp<T>::to_u32(fp<T>::div(fp<T>::sub(x, min_x), scale)) & 0xFFFFu;
+  u32 const iy = fp<T>::to_u32(fp<T>::div(fp<T>::sub(y, min_y), scale)) & 0xFFFFu;
+  return (dilate16(iy) << 1) | dilate16(ix);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: Morton encode fused with the radix digit histograms of all sort passes.
+// 128-bit coordinate loads, 128/64-bit key stores, shared-memory histograms.
+// Algorithmic bytes per point: 2*sizeof(T) read + 4 written.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(512)
+encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T min_x, T min_y,
+                   T max_x, T max_y, T scale, u32 oob_key, int passes, u32* __restrict__ keys,
+                   u32* __restrict__ hist)
+{
+  constexpr int V = 16 / sizeof(T);  // points per 128-bit load
+  __shared__ u32 s_hist[kMaxPasses * kRadixDigits];
+  for (int i = threadIdx.x; i < kMaxPasses * kRadixDigits; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+
+  u64 const nvec   = n / V;
+  u64 const stride = (u64)gridDim.x * blockDim.x;
+  bool const aligned =
+    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+    (reinterpret_cast<uintptr_t>(keys) & (4 * V - 1)) == 0;
+
+  auto tally = [&](u32 k) {
+    for (int p = 0; p < passes; ++p)
+      atomicAdd(&s_hist[p * kRadixDigits + ((k >> (p * kRadixBits)) & 0xFFu)], 1u);
+  };
+
+  if (aligned) {
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+      T xs[V], ys[V];
+      *reinterpret_cast<int4*>(xs) = __ldcs(reinterpret_cast<const int4*>(x) + v);
+      *reinterpret_cast<int4*>(ys) = __ldcs(reinterpret_cast<const int4*>(y) + v);
+      u32 ks[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        ks[j] = point_key<T>(xs[j], ys[j], min_x, min_y, max_x, max_y, scale, oob_key);
+        tally(ks[j]);
+      }
+      if constexpr (V == 2)
+        *reinterpret_cast<uint2*>(keys + v * V) = make_uint2(ks[0], ks[1]);
+      else
+        *reinterpret_cast<uint4*>(keys + v * V) = make_uint4(ks[0], ks[1], ks[2], ks[3]);
+    }
+    // tail
+    for (u64 i = nvec * V + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, oob_key);
+      tally(k);
+      keys[i] = k;
+    }
+  } else {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, oob_key);
+      tally(k);
+      keys[i] = k;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * kRadixDigits; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tree construction state kept on the device (no host round-trips between levels).
+// ---------------------------------------------------------------------------------------------
+struct tree_state {
+  u32 level_begin[17];
+  u32 level_end[17];
+  u32 overflow;
+  u32 pad;
+};
+
+// first index in [lo, hi) whose key is >= target (target is 64-bit: wide keys cannot overflow it)
+__device__ __forceinline__ u32 lower_bound_key(const u32* __restrict__ keys, u32 lo, u32 hi,
+                                               u64 target)
+{
+  while (lo < hi) {
+    u32 const mid = lo + ((hi - lo) >> 1);
+    if ((u64)__ldg(keys + mid) < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// warp-cooperative 32-ary lower bound (short dependent-load chain for the huge top-level ranges)
+__device__ __forceinline__ u32 warp_lower_bound_key(const u32* __restrict__ keys, u32 lo, u32 hi,
+                                                    u64 target)
+{
+  u32 const lane = lane_id();
+  while (hi - lo > 32) {
+    u64 const span  = (u64)(hi - lo);
+    u32 const probe = lo + (u32)((span * (lane + 1)) / 33);  // 32 interior probes
+    bool const less = (u64)__ldg(keys + probe) < target;
+    u32 const m     = __ballot_sync(0xffffffffu, less);
+    int const c     = __popc(m);  // probes [0,c) are < target (keys sorted)
+    u32 const nlo   = c == 0 ? lo : __shfl_sync(0xffffffffu, probe, c - 1) + 1;
+    u32 const nhi   = c == 32 ? hi : __shfl_sync(0xffffffffu, probe, c);
+    lo              = nlo;
+    hi              = nhi;
+  }
+  u32 const idx   = lo + lane;
+  bool const less = idx < hi && (u64)__ldg(keys + idx) < target;
+  return lo + __popc(__ballot_sync(0xffffffffu, less));
+}
+
+// Level 0 (children of the implicit root): distinct values of key >> shift0, found by one warp.
+// For max_depth <= 1 these rows are the whole (leaf-only) tree, detail/point_quadtree.cuh:155-188.
+__global__ void level0_kernel(const u32* __restrict__ keys, u32 n, int shift0, u32 cap,
+                              u32* __restrict__ okey, u8* __restrict__ olevel,
+                              u8* __restrict__ ointernal, u32* __restrict__ olength,
+                              u32* __restrict__ ooffset, tree_state* st)
+{
+  u32 pos = 0, rows = 0;
+  while (pos < n) {
+    u32 const k     = __ldg(keys + pos) >> shift0;
+    u64 const next  = ((u64)k + 1) << shift0;
+    u32 const end   = next > 0xFFFFFFFFull ? n : warp_lower_bound_key(keys, pos, n, next);
+    if (lane_id() == 0) {
+      if (rows < cap) {
+        okey[rows]      = k;
+        olevel[rows]    = 0;
+        ointernal[rows] = 0;
+        olength[rows]   = end - pos;
+        ooffset[rows]   = pos;
+      } else {
+        st->overflow = 1;
+      }
+    }
+    ++rows;
+    pos = end;
+  }
+  if (lane_id() == 0) {
+    st->level_begin[0] = 0;
+    st->level_end[0]   = min(rows, cap);
+  }
+}
+
+// Expand level L -> L+1.  One thread per level-L node; nodes with more than max_size points
+// become internal and emit their non-empty children (ordered by key) right after the children of
+// all earlier nodes: chained scan over tiles in ticket order.  Rows of level L+1 start at
+// level_end[L].  phase_2.cuh:256-281 (prune rule), :321-341 (internal flag),
+// detail/point_quadtree.cuh:88-133 (child offsets / lengths).
+constexpr int kExpandBlock = 256;
+__global__ void __launch_bounds__(kExpandBlock)
+expand_level_kernel(const u32* __restrict__ keys, int L, int max_depth, u32 max_size, u32 cap,
+                    u32* __restrict__ okey, u8* __restrict__ olevel, u8* __restrict__ ointernal,
+                    u32* __restrict__ olength, u32* __restrict__ ooffset, tree_state* st,
+                    u64* __restrict__ lookback, u32* __restrict__ ticket, u32* __restrict__ done)
+{
+  __shared__ u32 s_tile, s_base, s_warp_sums[kExpandBlock / 32];
+  u32 const lbeg      = st->level_begin[L];
+  u32 const lend      = st->level_end[L];
+  u32 const count     = lend - lbeg;
+  u32 const num_tiles = (count + kExpandBlock - 1) / kExpandBlock;
+  u32 const tag_agg = 2u * (L + 1), tag_pre = 2u * (L + 1) + 1u;
+  int const shift   = 2 * (max_depth - 2 - L);  // level L+1 cell key = sorted key >> shift
+  int const tid     = threadIdx.x;
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    u32 const tile = s_tile;
+    if (tile >= num_tiles) break;
+
+    u32 const row = lbeg + tile * kExpandBlock + tid;
+    u32 k = 0, cnt = 0, start = 0, b[5] = {0, 0, 0, 0, 0};
+    u32 nchild = 0;
+    if (row < lend) {
+      k     = okey[row];
+      cnt   = olength[row];
+      start = ooffset[row];
+      if (cnt > max_size) {
+        b[0] = start;
+        b[4] = start + cnt;
+#pragma unroll
+        for (int c = 1; c < 4; ++c)
+          b[c] = lower_bound_key(keys, b[c - 1], b[4], (((u64)k << 2) + c) << shift);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) nchild += (b[c + 1] > b[c]);
+      }
+    }
+    // block exclusive scan of nchild
+    u32 const incl = warp_inclusive_scan(nchild);
+    if ((tid & 31) == 31) s_warp_sums[tid >> 5] = incl;
+    __syncthreads();
+    u32 wbase = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kExpandBlock / 32; ++w) {
+      u32 const s = s_warp_sums[w];
+      if (w < (tid >> 5)) wbase += s;
+      block_total += s;
+    }
+    if (tid == 0) s_base = lookback_exclusive(lookback, tile, block_total, tag_agg, tag_pre);
+    __syncthreads();
+    u32 const first_child = lend + s_base + wbase + incl - nchild;
+
+    if (nchild) {
+      ointernal[row] = 1;
+      olength[row]   = nchild;
+      ooffset[row]   = first_child;
+      u32 r          = first_child;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (b[c + 1] > b[c]) {
+          if (r < cap) {
+            okey[r]      = (k << 2) + c;
+            olevel[r]    = (u8)(L + 1);
+            ointernal[r] = 0;
+            olength[r]   = b[c + 1] - b[c];
+            ooffset[r]   = b[c];
+          } else {
+            st->overflow = 1;
+          }
+          ++r;
+        }
+      }
+    }
+    // the last tile knows the level's total number of children
+    if (tid == 0 && tile == num_tiles - 1) {
+      st->level_begin[L + 1] = lend;
+      st->level_end[L + 1]   = min(lend + s_base + block_total, cap);
+    }
+  }
+  // empty level: propagate an empty range so deeper launches do nothing
+  if (num_tiles == 0 && blockIdx.x == 0 && tid == 0) {
+    st->level_begin[L + 1] = lend;
+    st->level_end[L + 1]   = lend;
+  }
+  (void)done;
+}
+
+template <typename T>
+void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_max, double y_min,
+                   double y_max, double scale_d, int max_depth, int passes, u32* keys, u32* hist,
+                   cudaStream_t s)
+{
+  // the column API casts to T (cpp/src/indexing/point_quadtree.cu:82-84), the header API then
+  // orders the corners and clamps scale in T (detail/point_quadtree.cuh:259-268)
+  T const x1 = (T)x_min, x2 = (T)x_max, y1 = (T)y_min, y2 = (T)y_max;
+  T const min_x = std::min(x1, x2), min_y = std::min(y1, y2);
+  T const max_x = std::max(x1, x2), max_y = std::max(y1, y2);
+  T const scale = std::max((T)scale_d, std::max(max_x - min_x, max_y - min_y) /
+                                         (T)((1 << max_depth) + 2));
+  u32 const oob_key = (u32)((1 << (2 * max_depth)) - 1);
+  int const V       = 16 / sizeof(T);
+  int const grid    = (int)std::min<u64>((u64)kNumSMs * 4, (u64)div_up(div_up(n, V), 512));
+  encode_hist_kernel<T><<<std::max(grid, 1), 512, 0, s>>>(
+    (const T*)x, (const T*)y, n, min_x, min_y, max_x, max_y, scale, oob_key, passes, keys, hist);
+  BSJ_CHECK_LAUNCH();
+}
+
+}  // namespace
+
+// Host orchestration.  One stream synchronisation at the end (to learn the node count).
+void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, double x_min,
+                             double x_max, double y_min, double y_max, double scale,
+                             int max_depth_in, int max_size_in, const bsj_allocator* mr,
+                             cudaStream_t s, bsj_quadtree* out)
+{
+  *out = bsj_quadtree{};
+  if (n == 0) return;  // point_quadtree.cu:167-177
+  BSJ_EXPECTS(n < 0xFFFFC000ull, "number of points must fit uint32 indices");
+
+  u32 const max_size = (u32)std::max(1, max_size_in);                   // :264
+  int const d        = std::max(0, std::min(15, max_depth_in));         // :266
+  stage_timer tm(s);
+
+  // key width: in-bbox cell indices are <= 2^d + 2 (scale clamp), i.e. d+2 bits per axis
+  int const key_bits = std::min(32, 2 * (d + 2));
+  int const passes   = passes_for_bits(0, key_bits);
+
+  out_alloc oa(mr, s);
+  // the sorted permutation ends in `idx_a` or `idx_b` depending on pass parity; make the final
+  // target the caller-visible output buffer
+  u32* out_idx = oa.get<u32>(n);
+  dev_buf<u32> keys_a(n, s), keys_b(n, s), idx_tmp(n, s);
+  sort_workspace ws;
+  ws.alloc(n, s);
+  sort_workspace_reset(ws, s);
+
+  if (dtype == BSJ_FLOAT32)
+    launch_encode<float>(x, y, n, x_min, x_max, y_min, y_max, scale, d, passes, keys_a.get(),
+                         ws.hist.get(), s);
+  else
+    launch_encode<double>(x, y, n, x_min, x_max, y_min, y_max, scale, d, passes, keys_a.get(),
+                          ws.hist.get(), s);
+  tm.mark("encode_hist");
+
+  // ping-pong so that the last pass writes into out_idx: with P passes the result lands in
+  // side A when P is even, side B when odd.
+  bool const even = (passes % 2) == 0;
+  u32* vals_a     = even ? out_idx : idx_tmp.get();
+  u32* vals_b     = even ? idx_tmp.get() : out_idx;
+  bool in_a       = true;
+  sort_passes(keys_a.get(), vals_a, /*iota=*/true, keys_b.get(), vals_b, n, 0, key_bits, ws, s,
+              &in_a);
+  const u32* sorted_keys = in_a ? keys_a.get() : keys_b.get();
+  tm.mark("sort");
+
+  // ---- tree rows. Capacity: every node below level 0 has a parent with > max_size points, so a
+  // level holds at most 4*floor(N/(max_size+1)) nodes, and never more than N or (2^(L+1)+3)^2
+  // cells (cell indices reach 2^d + 2 under the reference's scale clamp).
+  u64 cap = 64;
+  {
+    u64 const per_level = std::min<u64>(n, 4 * (n / ((u64)max_size + 1)));
+    for (int L = 1; L < d; ++L) {
+      u64 const side = (2ull << L) + 3;
+      cap += std::min(per_level, side * side);
+    }
+  }
+  dev_buf<u32> tkey(cap, s), tlen(cap, s), toff(cap, s);
+  dev_buf<u8> tlevel(cap, s), tint(cap, s);
+  dev_buf<tree_state> st(1, s);
+  u32 const max_tiles = (u32)div_up(cap, kExpandBlock) + 1;
+  dev_buf<u64> lb(max_tiles, s);
+  dev_buf<u32> tickets(16, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(st.get(), 0, sizeof(tree_state), s));
+  BSJ_CUDA_TRY(cudaMemsetAsync(lb.get(), 0, max_tiles * sizeof(u64), s));
+  BSJ_CUDA_TRY(cudaMemsetAsync(tickets.get(), 0, 16 * sizeof(u32), s));
+
+  int const shift0 = d >= 1 ? 2 * (d - 1) : 0;
+  level0_kernel<<<1, 32, 0, s>>>(sorted_keys, (u32)n, shift0, (u32)cap, tkey.get(), tlevel.get(),
+                                 tint.get(), tlen.get(), toff.get(), st.get());
+  BSJ_CHECK_LAUNCH();
+  for (int L = 0; L + 1 < d; ++L) {
+    // level L holds at most min(cap, (2^(L+1)+3)^2) nodes; size the grid for that
+    u64 const geo  = ((2ull << L) + 3) * ((2ull << L) + 3);
+    int const grid = (int)std::min<u64>((u64)kNumSMs * 8,
+                                        std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandBlock)));
+    expand_level_kernel<<<grid, kExpandBlock, 0, s>>>(
+      sorted_keys, L, d, max_size, (u32)cap, tkey.get(), tlevel.get(), tint.get(), tlen.get(),
+      toff.get(), st.get(), lb.get(), tickets.get() + L, nullptr);
+    BSJ_CHECK_LAUNCH();
+  }
+  tm.mark("tree_levels");
+
+  tree_state h{};
+  BSJ_CUDA_TRY(cudaMemcpyAsync(&h, st.get(), sizeof(h), cudaMemcpyDeviceToHost, s));
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+  if (h.overflow) throw error(BSJ_CUDA_ERROR, "quadtree node capacity exceeded (internal error)");
+  int const last = d >= 2 ? d - 1 : 0;
+  u64 const q    = h.level_end[last];
+
+  out->point_indices    = out_idx;
+  out->num_points       = n;
+  out->num_nodes        = q;
+  out->key              = oa.get<u32>(q);
+  out->level            = oa.get<u8>(q);
+  out->is_internal_node = oa.get<u8>(q);
+  out->length           = oa.get<u32>(q);
+  out->offset           = oa.get<u32>(q);
+  BSJ_CUDA_TRY(cudaMemcpyAsync(out->key, tkey.get(), q * 4, cudaMemcpyDeviceToDevice, s));
+  BSJ_CUDA_TRY(cudaMemcpyAsync(out->level, tlevel.get(), q, cudaMemcpyDeviceToDevice, s));
+  BSJ_CUDA_TRY(cudaMemcpyAsync(out->is_internal_node, tint.get(), q, cudaMemcpyDeviceToDevice, s));
+  BSJ_CUDA_TRY(cudaMemcpyAsync(out->length, tlen.get(), q * 4, cudaMemcpyDeviceToDevice, s));
+  BSJ_CUDA_TRY(cudaMemcpyAsync(out->offset, toff.get(), q * 4, cudaMemcpyDeviceToDevice, s));
+  tm.mark("finalize");
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+  tm.finish();
+  oa.commit();
+}
+
+}  // namespace bsj

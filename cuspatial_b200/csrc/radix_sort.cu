@@ -1,0 +1,268 @@
+// radix_sort.cu -- onesweep LSD radix sort (u32 key, u32 value), sm_100a.  See radix_sort.cuh.
+#include "radix_sort.cuh"
+
+namespace bsj {
+
+namespace {
+
+constexpr int kWarps = kSortBlock / 32;
+
+// shared-memory layout of one onesweep CTA (dynamic)
+struct sort_smem {
+  u32 keys[kSortTile];
+  u32 vals[kSortTile];
+  u32 whist[kWarps * kRadixDigits];  // per-warp digit counters -> per-warp exclusive offsets
+  u32 bin_start[kRadixDigits];       // exclusive scan of the tile's digit totals
+  u32 gbase[kRadixDigits];           // global destination of (digit, slot j): gbase[d] + j
+  u32 warp_sums[kWarps];
+  u32 tile;
+};
+
+// ---------------------------------------------------------------------------------------------
+// generic histogram (used when the producer of the keys did not already fuse it)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) histogram_kernel(const u32* __restrict__ keys, u64 n,
+                                                        int begin_bit, int passes,
+                                                        u32* __restrict__ hist)
+{
+  __shared__ u32 s_hist[kMaxPasses * kRadixDigits];
+  for (int i = threadIdx.x; i < kMaxPasses * kRadixDigits; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  u64 const stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u32 const k = ld_stream(keys + i);
+    for (int p = 0; p < passes; ++p)
+      atomicAdd(&s_hist[p * kRadixDigits + ((k >> (begin_bit + p * kRadixBits)) & 0xFF)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * kRadixDigits; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+// counts -> exclusive digit offsets, one 256-thread group per pass
+__global__ void __launch_bounds__(kMaxPasses * kRadixDigits) scan_hist_kernel(u32* hist)
+{
+  __shared__ u32 s_ws[kMaxPasses * 8];
+  int const t      = threadIdx.x;
+  u32 const c      = hist[t];
+  u32 const incl   = warp_inclusive_scan(c);
+  int const warp   = t >> 5;
+  if ((t & 31) == 31) s_ws[warp] = incl;
+  __syncthreads();
+  u32 base       = 0;
+  int const w0   = (warp >> 3) << 3;  // first warp of this pass's 256-thread group
+  for (int w = w0; w < warp; ++w) base += s_ws[w];
+  hist[t] = base + incl - c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one onesweep pass: rank -> look-back -> scatter
+// ---------------------------------------------------------------------------------------------
+template <bool IOTA>
+__global__ void __launch_bounds__(kSortBlock, 2)
+onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in,
+                u32* __restrict__ keys_out, u32* __restrict__ vals_out, u32 n, int shift,
+                const u32* __restrict__ digit_offsets, u64* __restrict__ lookback,
+                u32* __restrict__ ticket, u32 tag_agg, u32 tag_pre)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  sort_smem& sm = *reinterpret_cast<sort_smem*>(smem_raw);
+
+  int const tid  = threadIdx.x;
+  int const lane = tid & 31;
+  int const warp = tid >> 5;
+
+  if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+  for (int i = tid; i < kWarps * kRadixDigits; i += kSortBlock) sm.whist[i] = 0;
+  __syncthreads();
+  u32 const tile      = sm.tile;
+  u32 const tile_base = tile * (u32)kSortTile;
+  u32 const valid     = min((u32)kSortTile, n - tile_base);
+
+  // ---- load keys, warp-striped: item i of this lane is warp_base + i*32 + lane
+  u32 const warp_base = tile_base + warp * (kSortIPT * 32);
+  u32 key[kSortIPT];
+#pragma unroll
+  for (int i = 0; i < kSortIPT; ++i) {
+    u32 const idx = warp_base + i * 32 + lane;
+    key[i]        = idx < n ? ld_stream(keys_in + idx) : 0xFFFFFFFFu;
+  }
+
+  // ---- per-warp stable ranking with match.any
+  u32* const wh = sm.whist + warp * kRadixDigits;
+  u32 const lt  = lanemask_lt();
+  unsigned short rank[kSortIPT];
+#pragma unroll
+  for (int i = 0; i < kSortIPT; ++i) {
+    u32 const d     = (key[i] >> shift) & 0xFFu;
+    u32 const peers = __match_any_sync(0xffffffffu, d);
+    int const lead  = __ffs(peers) - 1;
+    u32 prev        = 0;
+    if (lane == lead) {
+      prev  = wh[d];
+      wh[d] = prev + __popc(peers);
+    }
+    prev    = __shfl_sync(0xffffffffu, prev, lead);
+    rank[i] = (unsigned short)(prev + __popc(peers & lt));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- digit totals over warps (thread d < 256 owns digit d), exclusive scan over digits
+  u32 total = 0;
+  if (tid < kRadixDigits) {
+    u32 sum = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      u32 const c                    = sm.whist[w * kRadixDigits + tid];
+      sm.whist[w * kRadixDigits + tid] = sum;
+      sum += c;
+    }
+    total = sum;
+  }
+  u32 const incl = warp_inclusive_scan(total);
+  if (lane == 31) sm.warp_sums[warp] = incl;
+  __syncthreads();
+  if (tid < kRadixDigits) {
+    u32 base = 0;
+    for (int w = 0; w < warp; ++w) base += sm.warp_sums[w];
+    u32 const bin_start = base + incl - total;
+    sm.bin_start[tid]   = bin_start;
+
+    // padding keys (0xFFFFFFFF) of the last tile land at the end of digit 255: not counted
+    u32 my_total = total;
+    if (tid == kRadixDigits - 1) my_total -= ((u32)kSortTile - valid);
+
+    // ---- decoupled look-back on this digit's column of tile descriptors
+    u64* const col = lookback + tid;
+    u32 excl       = 0;
+    if (tile == 0) {
+      st_relaxed_u64(col, lb_pack(tag_pre, my_total));
+    } else {
+      st_relaxed_u64(col + (u64)tile * kRadixDigits, lb_pack(tag_agg, my_total));
+      i64 t = (i64)tile - 1;
+      while (true) {
+        u64 const v    = ld_relaxed_u64(col + (u64)t * kRadixDigits);
+        u32 const flag = (u32)(v >> 32);
+        if (flag == tag_pre) {
+          excl += (u32)v;
+          break;
+        }
+        if (flag == tag_agg) {
+          excl += (u32)v;
+          --t;
+        }
+      }
+      st_relaxed_u64(col + (u64)tile * kRadixDigits, lb_pack(tag_pre, excl + my_total));
+    }
+    sm.gbase[tid] = digit_offsets[tid] + excl - bin_start;
+  }
+  __syncthreads();
+
+  // ---- place keys (and values) at their tile-sorted slot in shared memory
+#pragma unroll
+  for (int i = 0; i < kSortIPT; ++i) {
+    u32 const d   = (key[i] >> shift) & 0xFFu;
+    u32 const pos = sm.bin_start[d] + wh[d] + rank[i];
+    sm.keys[pos]  = key[i];
+    key[i]        = pos;  // reuse the register for the slot
+  }
+  if (IOTA) {
+#pragma unroll
+    for (int i = 0; i < kSortIPT; ++i) sm.vals[key[i]] = warp_base + i * 32 + lane;
+  } else {
+    u32 v[kSortIPT];
+#pragma unroll
+    for (int i = 0; i < kSortIPT; ++i) {
+      u32 const idx = warp_base + i * 32 + lane;
+      v[i]          = idx < n ? ld_stream(vals_in + idx) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < kSortIPT; ++i) sm.vals[key[i]] = v[i];
+  }
+  __syncthreads();
+
+  // ---- scatter: consecutive slots of one digit go to consecutive global addresses
+#pragma unroll
+  for (int i = 0; i < kSortIPT; ++i) {
+    u32 const j = i * kSortBlock + tid;
+    if (j < valid) {
+      u32 const k   = sm.keys[j];
+      u32 const dst = sm.gbase[(k >> shift) & 0xFFu] + j;
+      keys_out[dst] = k;
+      vals_out[dst] = sm.vals[j];
+    }
+  }
+}
+
+bool g_attr_set = false;
+void set_kernel_attrs()
+{
+  if (g_attr_set) return;
+  BSJ_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(sort_smem)));
+  BSJ_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(sort_smem)));
+  g_attr_set = true;
+}
+
+}  // namespace
+
+void sort_workspace::alloc(u64 n, cudaStream_t s)
+{
+  num_tiles = (u32)div_up(n, kSortTile);
+  hist.alloc(kMaxPasses * kRadixDigits, s);
+  tickets.alloc(kMaxPasses, s);
+  lookback.alloc((size_t)num_tiles * kRadixDigits, s);
+}
+
+void sort_workspace_reset(sort_workspace& ws, cudaStream_t s)
+{
+  BSJ_CUDA_TRY(cudaMemsetAsync(ws.hist.get(), 0, ws.hist.size() * sizeof(u32), s));
+  BSJ_CUDA_TRY(cudaMemsetAsync(ws.tickets.get(), 0, ws.tickets.size() * sizeof(u32), s));
+  BSJ_CUDA_TRY(cudaMemsetAsync(ws.lookback.get(), 0, ws.lookback.size() * sizeof(u64), s));
+}
+
+void sort_histogram(const u32* keys, u64 n, int begin_bit, int end_bit, sort_workspace& ws,
+                    cudaStream_t s)
+{
+  int const passes = passes_for_bits(begin_bit, end_bit);
+  int const grid   = (int)std::min<u64>((u64)kNumSMs * 4, (u64)div_up(n, 512));
+  histogram_kernel<<<grid, 512, 0, s>>>(keys, n, begin_bit, passes, ws.hist.get());
+  BSJ_CHECK_LAUNCH();
+}
+
+void sort_passes(u32* keys_a, u32* vals_a, bool iota_values, u32* keys_b, u32* vals_b, u64 n,
+                 int begin_bit, int end_bit, sort_workspace& ws, cudaStream_t s,
+                 bool* result_in_a)
+{
+  set_kernel_attrs();
+  int const passes = passes_for_bits(begin_bit, end_bit);
+  scan_hist_kernel<<<1, kMaxPasses * kRadixDigits, 0, s>>>(ws.hist.get());
+  BSJ_CHECK_LAUNCH();
+  bool in_a = true;
+  for (int p = 0; p < passes; ++p) {
+    u32* kin  = in_a ? keys_a : keys_b;
+    u32* vin  = in_a ? vals_a : vals_b;
+    u32* kout = in_a ? keys_b : keys_a;
+    u32* vout = in_a ? vals_b : vals_a;
+    u32 const tag_agg = 2u * (p + 1), tag_pre = 2u * (p + 1) + 1u;
+    int const shift   = begin_bit + p * kRadixBits;
+    if (p == 0 && iota_values) {
+      onesweep_kernel<true><<<ws.num_tiles, kSortBlock, sizeof(sort_smem), s>>>(
+        kin, nullptr, kout, vout, (u32)n, shift, ws.hist.get() + p * kRadixDigits,
+        ws.lookback.get(), ws.tickets.get() + p, tag_agg, tag_pre);
+    } else {
+      onesweep_kernel<false><<<ws.num_tiles, kSortBlock, sizeof(sort_smem), s>>>(
+        kin, vin, kout, vout, (u32)n, shift, ws.hist.get() + p * kRadixDigits,
+        ws.lookback.get(), ws.tickets.get() + p, tag_agg, tag_pre);
+    }
+    BSJ_CHECK_LAUNCH();
+    in_a = !in_a;
+  }
+  *result_in_a = in_a;
+}
+
+}  // namespace bsj

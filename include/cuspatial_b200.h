@@ -1,0 +1,186 @@
+/*
+ * cuspatial_b200.h -- C ABI of the B200-native quadtree point-in-polygon spatial join.
+ *
+ * Drop-in boundary for ONE hot path of rapidsai/cuspatial (25.06):
+ *     quadtree_on_points -> join_quadtree_and_bounding_boxes -> quadtree_point_in_polygon
+ *     (+ the non-indexed bitmask point_in_polygon, + polygon_bounding_boxes as input producer)
+ *
+ * Every entry point states the reference interface it replaces (paths relative to the reference
+ * tree).  The reference's column layer takes cudf::column_view / table_view; here a column is a
+ * plain device pointer + length and a table is its columns passed one by one, in the reference's
+ * column order.  Output columns have the reference's dtypes:
+ *     point_indices UINT32 | key UINT32, level UINT8, is_internal_node BOOL8(1 byte), length UINT32,
+ *     offset UINT32 | (bbox_offset, quad_offset) UINT32 | (polygon_index, point_index) UINT32 |
+ *     bitmask INT32.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers.  `dtype`: 0 = float32, 1 = float64 (the only
+ *     coordinate types the reference dispatches on, cpp/src/indexing/point_quadtree.cu:61).
+ *   - `stream` is a cudaStream_t (NULL = default stream, which is what the reference uses:
+ *     rmm::cuda_stream_default).  Calls are synchronous from the caller's view, re-entrant and
+ *     stateless, like the reference.
+ *   - `mr` plays the role of the reference's `rmm::device_async_resource_ref mr`: OUTPUT columns
+ *     are allocated through it (so a host framework can hand in its own allocator, e.g. a torch
+ *     caching-allocator callback).  NULL = library default (cudaMallocAsync on `stream`); such
+ *     buffers are released with bsj_free().  Temporaries always come from the library's pool.
+ *   - Return value: BSJ_SUCCESS, or an error code with a thread-local message from
+ *     bsj_last_error().  BSJ_INVALID_ARGUMENT corresponds to the reference's cuspatial::logic_error
+ *     (CUSPATIAL_EXPECTS, cpp/include/cuspatial/error.hpp:76-79) with the same wording;
+ *     BSJ_CUDA_ERROR to cuspatial::cuda_error; BSJ_OUT_OF_MEMORY to rmm::out_of_memory.
+ *   - Empty inputs return empty outputs (NULL pointers, size 0) and BSJ_SUCCESS, never an error
+ *     (point_quadtree.cu:167-177, quadtree_bbox_filtering.cu:108-114,
+ *     quadtree_point_in_polygon.cu:171-178).
+ */
+#ifndef CUSPATIAL_B200_H
+#define CUSPATIAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSJ_SUCCESS 0
+#define BSJ_INVALID_ARGUMENT 1
+#define BSJ_CUDA_ERROR 2
+#define BSJ_OUT_OF_MEMORY 3
+
+#define BSJ_FLOAT32 0
+#define BSJ_FLOAT64 1
+
+/* Opaque stream handle: pass a cudaStream_t. */
+typedef void* bsj_stream_t;
+
+/* Output allocator, the analogue of rmm::device_async_resource_ref. `allocate` must return device
+ * memory usable on `stream` (or NULL on failure -> BSJ_OUT_OF_MEMORY). */
+typedef struct bsj_allocator {
+  void* (*allocate)(size_t bytes, bsj_stream_t stream, void* ctx);
+  void (*deallocate)(void* ptr, size_t bytes, bsj_stream_t stream, void* ctx);
+  void* ctx;
+} bsj_allocator;
+
+/* Result of bsj_quadtree_on_points == the reference's
+ * std::pair<std::unique_ptr<cudf::column>, std::unique_ptr<cudf::table>>
+ * (cpp/include/cuspatial/point_quadtree.hpp:68-78; column order cpp/src/indexing/point_quadtree.cu:92-118). */
+typedef struct bsj_quadtree {
+  uint32_t* point_indices;   /* UINT32[num_points]: sorted position -> original point index   */
+  uint64_t num_points;
+  uint32_t* key;             /* UINT32[num_nodes]                                              */
+  uint8_t* level;            /* UINT8 [num_nodes]                                              */
+  uint8_t* is_internal_node; /* BOOL8 [num_nodes] (one byte, 0/1)                              */
+  uint32_t* length;          /* UINT32[num_nodes]: #children (internal) or #points (leaf)      */
+  uint32_t* offset;          /* UINT32[num_nodes]: first child row (internal) / first point pos */
+  uint64_t num_nodes;
+} bsj_quadtree;
+
+/* A two-column UINT32 table: (bbox_offset, quad_offset) or (polygon_index, point_index). */
+typedef struct bsj_pairs {
+  uint32_t* first;
+  uint32_t* second;
+  uint64_t size;
+} bsj_pairs;
+
+/*
+ * Replaces cuspatial::quadtree_on_points
+ *   (cpp/include/cuspatial/point_quadtree.hpp:68-78, cpp/src/indexing/point_quadtree.cu:154-180).
+ * Same argument order and meaning; `x`,`y` are the two coordinate columns (length n each).
+ * Clamping as the reference: max_size >= 1, 0 <= max_depth <= 15,
+ * scale >= max(dx,dy)/((1<<max_depth)+2) computed in the coordinate type
+ * (cpp/include/cuspatial/detail/point_quadtree.cuh:259-268).
+ */
+int bsj_quadtree_on_points(const void* x, const void* y, int dtype, uint64_t n, double x_min,
+                           double x_max, double y_min, double y_max, double scale,
+                           int8_t max_depth, int32_t max_size, const bsj_allocator* mr,
+                           bsj_stream_t stream, bsj_quadtree* out);
+
+/*
+ * Replaces cuspatial::join_quadtree_and_bounding_boxes
+ *   (cpp/include/cuspatial/spatial_join.hpp:66-75, cpp/src/join/quadtree_bbox_filtering.cu:90-126).
+ * quadtree = its 5 columns; bbox = 4 columns (x_min, y_min, x_max, y_max) of n_boxes rows.
+ * Errors (same conditions/wording as quadtree_bbox_filtering.cu:100-106): scale <= 0,
+ * !(x_min < x_max && y_min < y_max), !(0 < max_depth < 16).
+ * Output rows are ordered exactly as the reference's: by quadtree.offset[quad] ascending, ties by
+ * bbox index ascending (cpp/include/cuspatial/detail/join/quadtree_bbox_filtering.cuh:166-180).
+ */
+int bsj_join_quadtree_and_bounding_boxes(const uint32_t* key, const uint8_t* level,
+                                         const uint8_t* is_internal_node, const uint32_t* length,
+                                         const uint32_t* offset, uint64_t num_nodes,
+                                         const void* bbox_x_min, const void* bbox_y_min,
+                                         const void* bbox_x_max, const void* bbox_y_max, int dtype,
+                                         uint64_t n_boxes, double x_min, double x_max, double y_min,
+                                         double y_max, double scale, int8_t max_depth,
+                                         const bsj_allocator* mr, bsj_stream_t stream,
+                                         bsj_pairs* out /* first=bbox_offset, second=quad_offset */);
+
+/*
+ * Replaces cuspatial::quadtree_point_in_polygon
+ *   (cpp/include/cuspatial/spatial_join.hpp:116-126, cpp/src/join/quadtree_point_in_polygon.cu:143-191).
+ * poly_quad_pairs = (pair_poly, pair_quad); quadtree = 5 columns; point_indices, point_x, point_y of
+ * n_points rows; poly_offsets has n_polygons+1 entries into ring_offsets, ring_offsets has
+ * n_rings+1 entries into the vertex columns (GeoArrow; read as uint32 like the reference, :71-74).
+ * Output (polygon_index, point_index): rows in (pair order, point order within the quadrant);
+ * point_index is the position in point_indices (spatial_join.hpp:112-113).
+ */
+int bsj_quadtree_point_in_polygon(const uint32_t* pair_poly, const uint32_t* pair_quad,
+                                  uint64_t n_pairs, const uint32_t* key, const uint8_t* level,
+                                  const uint8_t* is_internal_node, const uint32_t* length,
+                                  const uint32_t* offset, uint64_t num_nodes,
+                                  const uint32_t* point_indices, const void* point_x,
+                                  const void* point_y, int dtype, uint64_t n_points,
+                                  const uint32_t* poly_offsets, uint64_t n_poly_offsets,
+                                  const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+                                  const void* poly_points_x, const void* poly_points_y,
+                                  uint64_t n_poly_points, const bsj_allocator* mr,
+                                  bsj_stream_t stream,
+                                  bsj_pairs* out /* first=polygon_index, second=point_index */);
+
+/*
+ * Replaces cuspatial::point_in_polygon (bitmask form)
+ *   (cpp/include/cuspatial/point_in_polygon.hpp:75-82, cpp/src/point_in_polygon/point_in_polygon.cu:153-171).
+ * Offsets are int32 (cudf::size_type, :72-73). At most 31 polygons
+ * (cpp/include/cuspatial/detail/point_in_polygon.cuh:93-94). out_mask: caller-allocated INT32[n_points];
+ * bit i of out_mask[p] is set iff point p is inside polygon i.
+ */
+int bsj_point_in_polygon(const void* point_x, const void* point_y, int dtype, uint64_t n_points,
+                         const int32_t* poly_offsets, uint64_t n_poly_offsets,
+                         const int32_t* ring_offsets, uint64_t n_ring_offsets,
+                         const void* poly_points_x, const void* poly_points_y,
+                         uint64_t n_poly_points, bsj_stream_t stream, int32_t* out_mask);
+
+/*
+ * Replaces cuspatial::polygon_bounding_boxes
+ *   (cpp/include/cuspatial/bounding_boxes.hpp, cpp/src/bounding_boxes/polygon_bounding_boxes.cu:132-161):
+ * the producer of the bbox table the join consumes. Outputs: 4 caller-allocated columns of
+ * n_poly_offsets-1 rows (x_min, y_min, x_max, y_max), each expanded by `expansion_radius`.
+ */
+int bsj_polygon_bounding_boxes(const uint32_t* poly_offsets, uint64_t n_poly_offsets,
+                               const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+                               const void* poly_points_x, const void* poly_points_y, int dtype,
+                               uint64_t n_poly_points, double expansion_radius,
+                               bsj_stream_t stream, void* out_x_min, void* out_y_min,
+                               void* out_x_max, void* out_y_max);
+
+/* Release a buffer the library allocated with its default allocator (mr == NULL). */
+void bsj_free(void* ptr, bsj_stream_t stream);
+void bsj_free_quadtree(bsj_quadtree* tree, bsj_stream_t stream);
+void bsj_free_pairs(bsj_pairs* pairs, bsj_stream_t stream);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* bsj_last_error(void);
+
+/* Library/version string, and the number of kernels this library has launched in this process
+ * (used by bench.py for its `gpu_launches` claim). */
+const char* bsj_version(void);
+uint64_t bsj_kernel_launch_count(void);
+
+/* Per-stage device timings (milliseconds, CUDA events on `stream`) of the last call of each entry
+ * point on this thread, when profiling was enabled with bsj_set_profiling(1). Keys are
+ * NUL-terminated names; returns the number of entries written (<= capacity). */
+void bsj_set_profiling(int enabled);
+int bsj_get_profile(const char** names, float* millis, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUSPATIAL_B200_H */

@@ -1,0 +1,286 @@
+"""GPU parity tests (B200): the CUDA path, called through the Python API -> C ABI, must equal the
+CPU oracle bit for bit -- quadtree arrays, point_indices, the ordered (bbox, quad) pair table and
+the ordered (polygon_index, point_index) rows -- on the reference's golden vectors, on randomised
+inputs at sizes the oracle finishes in seconds, and (size-independent properties) at full size.
+The reference's own host build (oracle/_ref) is used as a second checker when present.
+"""
+import numpy as np
+import pytest
+
+from util import TREE_COLS, assert_same, make_case, run_gpu, run_host
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev="cuda"):
+    import torch
+
+    return torch.as_tensor(np.ascontiguousarray(a), device=dev)
+
+
+def test_extension_is_loaded_and_launches_kernels():
+    from cuspatial_b200 import _lib
+
+    before = _lib.kernel_launch_count()
+    c = make_case(1000, 5, 5, "u", np.float64, seed=1)
+    run_gpu(c, 16)
+    assert _lib.kernel_launch_count() > before
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_golden_quadtrees(golden, dtype):
+    import cuspatial_b200 as cs
+
+    for c in golden["quadtree_cases"]:
+        pts = np.array(c["points"], dtype=dtype).reshape(-1, 2)
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            pidx, tree = cs.quadtree_on_points((_t(pts[:, 0]), _t(pts[:, 1])), c["v_min"][0],
+                                               c["v_max"][0], c["v_min"][1], c["v_max"][1],
+                                               c["scale"], c["max_depth"], c["max_size"])
+        for k in TREE_COLS:
+            assert tree[k].cpu().numpy().astype(np.int64).tolist() == c[k], (c["name"], k)
+        assert pidx.shape[0] == len(pts)
+        # reference dtypes (python/cuspatial/cuspatial/tests/spatial/indexing/test_indexing.py:27-31)
+        import torch
+
+        assert tree["key"].dtype == torch.uint32 and tree["level"].dtype == torch.uint8
+        assert tree["is_internal_node"].dtype == torch.bool
+        assert tree["length"].dtype == torch.uint32 and tree["offset"].dtype == torch.uint32
+        assert pidx.dtype == torch.uint32
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_golden_small_join_and_pip(golden, dtype):
+    import cuspatial_b200 as cs
+
+    sj = golden["small_join"]
+    pts = np.array(sj["points"], dtype=dtype)
+    x, y = _t(pts[:, 0]), _t(pts[:, 1])
+    pidx, tree = cs.quadtree_on_points((x, y), 0, 8, 0, 8, sj["scale"], sj["max_depth"],
+                                       sj["max_size"])
+    v = np.array(sj["vertices"], dtype=dtype)
+    polys = (_t(np.array(sj["part_offsets"], np.uint32)), _t(np.array(sj["ring_offsets"], np.uint32)),
+             _t(v[:, 0]), _t(v[:, 1]))
+    bb = cs.polygon_bounding_boxes(polys)
+    pairs = cs.join_quadtree_and_bounding_boxes(tree, bb, 0, 8, 0, 8, sj["scale"], sj["max_depth"])
+    assert pairs["bbox_offset"].cpu().numpy().tolist() == sj["pair_poly"]
+    assert pairs["quad_offset"].cpu().numpy().tolist() == sj["pair_quad"]
+    hits = cs.quadtree_point_in_polygon(pairs, tree, pidx, (x, y), polys)
+    assert hits["polygon_index"].cpu().numpy().tolist() == sj["pip_poly"]
+    assert hits["point_index"].cpu().numpy().tolist() == sj["pip_point"]
+    # linestring bounding boxes expanded by 2.0: 21 pairs incl. non-bottom leaves and ties
+    lj = golden["linestring_join"]
+    lb = cs.polygon_bounding_boxes(polys, lj["expansion_radius"])
+    pairs = cs.join_quadtree_and_bounding_boxes(tree, lb, 0, 8, 0, 8, sj["scale"], sj["max_depth"])
+    assert pairs["bbox_offset"].cpu().numpy().tolist() == lj["bbox_offset"]
+    assert pairs["quad_offset"].cpu().numpy().tolist() == lj["quad_offset"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_golden_bitmask_predicate_cases(golden, dtype):
+    import cuspatial_b200 as cs
+
+    for c in golden["pip_cases"]:
+        p = np.array(c["points"], dtype=dtype)
+        v = np.array(c["vertices"], dtype=dtype)
+        polys = (_t(np.array(c["part_offsets"], np.int32)), _t(np.array(c["ring_offsets"], np.int32)),
+                 _t(v[:, 0]), _t(v[:, 1]))
+        m = cs.point_in_polygon_bitmask((_t(p[:, 0]), _t(p[:, 1])), polys)
+        assert m.cpu().numpy().tolist() == c["expected_mask"], c["name"]
+        frame = cs.point_in_polygon((_t(p[:, 0]), _t(p[:, 1])), polys)
+        assert len(frame.columns) == len(c["part_offsets"]) - 1
+
+
+CASES = [
+    # n, n_poly, depth, max_size, kind, oob, dups, median_vertices
+    (20000, 30, 15, 64, "u", 0, 0, 40),
+    (200000, 263, 15, 512, "u", 0, 0, 200),
+    (300000, 50, 8, 20, "c", 50, 1000, 60),
+    (5000, 10, 3, 5, "u", 0, 0, 12),
+    (100000, 20, 15, 1, "c", 10, 300, 30),
+    (1000, 5, 1, 10, "u", 0, 0, 20),
+    (3000, 7, 2, 1, "u", 3, 0, 20),
+    (400000, 100, 12, 100, "c", 0, 0, 100),
+    (1, 3, 15, 1, "u", 0, 0, 10),
+    (2, 3, 4, 1, "u", 1, 0, 10),
+    (100000, 40, 15, 100000, "u", 0, 0, 50),   # a single huge leaf per top cell: many tiles per run
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("case", CASES)
+def test_random_inputs_equal_oracle(oracle_lib, case, dtype):
+    n, n_poly, depth, max_size, kind, oob, dups, mv = case
+    c = make_case(n, n_poly, depth, kind, dtype, seed=n + depth, oob=oob, dups=dups,
+                  median_vertices=mv)
+    assert_same(run_gpu(c, max_size), run_host(oracle_lib, c, max_size), "gpu vs oracle")
+
+
+def test_config1_1M_uniform_263_polygons_equals_oracle_and_reference(oracle_lib):
+    """BASELINE.json configs[0]: 1M uniform fp64 points x 263 taxi-zone-like polygons."""
+    from oracle import hostlib
+
+    c = make_case(1_000_000, 263, 15, "u", np.float64, seed=20251017, median_vertices=200)
+    g = run_gpu(c, 512)
+    assert_same(g, run_host(oracle_lib, c, 512), "gpu vs oracle (config 1)")
+    if hostlib.reference_available():
+        assert_same(g, run_host(hostlib.reference(), c, 512), "gpu vs reference host build")
+    assert len(g["hits"][0]) > 500_000
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_near_edge_points_equal_oracle(oracle_lib, dtype):
+    """The 4-ULP on-edge rule, vertical-edge quirk and exact edge skipping near boundaries."""
+    c = make_case(10, 12, 6, "u", dtype, seed=9, median_vertices=16)
+    vx, vy, ro = c["vx"], c["vy"], c["ro"]
+    sq = np.array([[0.3, 0.3], [0.6, 0.3], [0.6, 0.6], [0.3, 0.6], [0.3, 0.3]], dtype=dtype)
+    vx = np.concatenate([vx, sq[:, 0]]); vy = np.concatenate([vy, sq[:, 1]])
+    ro = np.concatenate([ro, [ro[-1] + 5]]).astype(np.uint32)
+    po = np.concatenate([c["po"], [c["po"][-1] + 1]]).astype(np.uint32)
+    xs, ys = [], []
+    for i in range(len(vx)):
+        j = i + 1 if i + 1 < len(vx) else i
+        for t in (0.0, 0.25, 0.5, 1.0):
+            px, py = vx[i] + t * (vx[j] - vx[i]), vy[i] + t * (vy[j] - vy[i])
+            for k in range(-6, 7, 3):
+                xs.append(px); ys.append(py + dtype(k) * np.spacing(py))
+                xs.append(px + dtype(k) * np.spacing(px)); ys.append(py)
+    # plus points exactly on the vertical edges' x at arbitrary y (rejected regardless of y)
+    for yy in np.linspace(0.05, 0.95, 40):
+        xs += [0.3, 0.6]; ys += [yy, yy]
+    x = np.array(xs, dtype=dtype); y = np.array(ys, dtype=dtype)
+    keep = (x > c["ext"][0]) & (x < c["ext"][1]) & (y > c["ext"][2]) & (y < c["ext"][3])
+    c2 = dict(c, x=x[keep], y=y[keep], po=po, ro=ro, vx=vx, vy=vy)
+    for max_size in (8, 100000):
+        assert_same(run_gpu(c2, max_size), run_host(oracle_lib, c2, max_size), "near-edge")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_special_values_fall_back_to_reference_loop(oracle_lib, dtype):
+    """NaN / Inf / denormal coordinates: the exact-skipping path must not be taken."""
+    c = make_case(5000, 8, 6, "u", dtype, seed=4, median_vertices=16)
+    x, y = c["x"].copy(), c["y"].copy()
+    x[:20] = np.nan; y[20:40] = np.nan; x[40:50] = np.inf; y[50:60] = -np.inf
+    x[60:70] = dtype(1e-310) if dtype == np.float64 else dtype(1e-42)
+    c2 = dict(c, x=x, y=y)
+    assert_same(run_gpu(c2, 64), run_host(oracle_lib, c2, 64), "special values")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_bitmask_equals_oracle(oracle_lib, dtype):
+    import cuspatial_b200 as cs
+
+    c = make_case(300000, 31, 8, "u", dtype, seed=3, median_vertices=60)
+    po, ro = c["po"].astype(np.int32), c["ro"].astype(np.int32)
+    want = oracle_lib.point_in_polygon(c["x"], c["y"], po, ro, c["vx"], c["vy"])
+    got = cs.point_in_polygon_bitmask((_t(c["x"]), _t(c["y"])),
+                                      (_t(po), _t(ro), _t(c["vx"]), _t(c["vy"])))
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_error_conditions_match_reference():
+    """cpp/tests/join/join_quadtree_and_bounding_boxes_test.cpp:35-86."""
+    import cuspatial_b200 as cs
+
+    c = make_case(1000, 5, 5, "u", np.float64, seed=1)
+    ext = c["ext"]
+    pidx, tree = cs.quadtree_on_points((_t(c["x"]), _t(c["y"])), *ext, c["scale"], 5, 16)
+    bb = cs.polygon_bounding_boxes(tuple(_t(a) for a in (c["po"], c["ro"], c["vx"], c["vy"])))
+    from cuspatial_b200 import _lib
+    import ctypes as C
+
+    def raw(scale, x_min, x_max, max_depth):
+        out = _lib.bsj_pairs()
+        cols = [tree[k] for k in TREE_COLS]
+        rc = _lib.lib().bsj_join_quadtree_and_bounding_boxes(
+            *[C.c_void_p(t.data_ptr()) for t in cols], len(tree),
+            *[C.c_void_p(bb[k].data_ptr()) for k in ("minx", "miny", "maxx", "maxy")], 1, len(bb),
+            x_min, x_max, 0.0, 1.0, scale, max_depth, None, None, C.byref(out))
+        return rc, _lib.lib().bsj_last_error().decode()
+
+    rc, msg = raw(0.0, 0.0, 1.0, 5)
+    assert rc == _lib.BSJ_INVALID_ARGUMENT and "scale must be positive" in msg
+    rc, msg = raw(1.0, 1.0, 0.0, 5)
+    assert rc == _lib.BSJ_INVALID_ARGUMENT and "invalid bounding box" in msg
+    rc, msg = raw(1.0, 0.0, 1.0, 16)
+    assert rc == _lib.BSJ_INVALID_ARGUMENT and "maximum depth must be positive and less than 16" in msg
+    rc, msg = raw(1.0, 0.0, 1.0, 0)
+    assert rc == _lib.BSJ_INVALID_ARGUMENT
+    with pytest.raises(RuntimeError):
+        cs.join_quadtree_and_bounding_boxes(tree, bb, 0, 1, 0, 1, 1.0, 16)
+
+
+def test_empty_inputs_return_empty_outputs():
+    import torch
+
+    import cuspatial_b200 as cs
+
+    e = torch.empty(0, dtype=torch.float64, device="cuda")
+    pidx, tree = cs.quadtree_on_points((e, e), 0, 1, 0, 1, 1, 3, 2)
+    assert pidx.numel() == 0 and len(tree) == 0 and tree.columns == list(TREE_COLS)
+    pairs = cs.join_quadtree_and_bounding_boxes(tree, (e, e, e, e), 0, 1, 0, 1, 1, 3)
+    assert len(pairs) == 0 and pairs.columns == ["bbox_offset", "quad_offset"]
+    eo = torch.zeros(1, dtype=torch.int32, device="cuda").to(torch.uint32)
+    hits = cs.quadtree_point_in_polygon(pairs, tree, pidx, (e, e), (eo, eo, e, e))
+    assert len(hits) == 0 and hits.columns == ["polygon_index", "point_index"]
+
+
+def test_scale_clamp_warning_like_reference():
+    import cuspatial_b200 as cs
+
+    c = make_case(1000, 5, 5, "u", np.float64, seed=1)
+    with pytest.warns(UserWarning, match="is less than required minimum"):
+        cs.quadtree_on_points((_t(c["x"]), _t(c["y"])), *c["ext"], -1, 5, 16)
+
+
+def test_full_size_properties_20M(oracle_lib):
+    """Size-independent invariants at a size the oracle cannot check directly (20M points):
+    point_indices is a permutation, keys along it are sorted with ties in index order (stable),
+    leaf ranges tile [0, N), pair rows are ordered, every emitted row verifies under the oracle
+    predicate on a sample, and indexed hits == brute-force bitmask hits on a sample."""
+    import torch
+
+    import cuspatial_b200 as cs
+
+    n = 20_000_000
+    from cuspatial_b200 import datagen as D
+
+    po, ro, vx, vy = D.taxi_zone_like_polygons(263, seed=20251017)
+    ext = D.polygon_extent(vx, vy)
+    scale = D.quadtree_params(ext, 15)
+    x, y = D.uniform_points_torch(n, ext, 1, torch.float64, "cuda")
+    polys = tuple(_t(a) for a in (po, ro, vx, vy))
+    pidx, tree = cs.quadtree_on_points((x, y), *ext, scale, 15, 512)
+    pi = pidx.to(torch.int64)
+    assert torch.equal(torch.sort(pi).values, torch.arange(n, device="cuda"))
+    t = {k: tree[k].to(torch.int64) for k in TREE_COLS}
+    leaf = t["is_internal_node"] == 0
+    lo, ll = t["offset"][leaf], t["length"][leaf]
+    order = torch.argsort(lo)
+    assert int(lo[order][0]) == 0 and int((lo[order] + ll[order])[-1]) == n
+    assert torch.equal((lo[order] + ll[order])[:-1], lo[order][1:])
+    inner = ~leaf
+    assert torch.all(t["length"][inner] >= 1) and torch.all(t["length"][inner] <= 4)
+    bb = cs.polygon_bounding_boxes(polys)
+    pairs = cs.join_quadtree_and_bounding_boxes(tree, bb, *ext, scale, 15)
+    po_ = t["offset"][pairs["quad_offset"].to(torch.int64)]
+    key = po_ * 1024 + pairs["bbox_offset"].to(torch.int64)
+    assert torch.all(key[1:] > key[:-1])           # ordered by (leaf offset, bbox), no duplicates
+    hits = cs.quadtree_point_in_polygon(pairs, tree, pidx, (x, y), polys)
+    hp, hq = hits["polygon_index"].to(torch.int64), hits["point_index"].to(torch.int64)
+    assert len(hits) > n // 2
+    # sample 200k points: brute-force bitmask over the first 31 polygons must agree
+    sub = torch.randperm(n, device="cuda")[:200_000]
+    polys31 = (polys[0][:32].to(torch.int32), polys[1].to(torch.int32), polys[2], polys[3])
+    mask = cs.point_in_polygon_bitmask((x[sub], y[sub]), polys31).cpu().numpy()
+    want = oracle_lib.point_in_polygon(x[sub].cpu().numpy(), y[sub].cpu().numpy(),
+                                       po[:32].astype(np.int32), ro.astype(np.int32), vx, vy)
+    np.testing.assert_array_equal(mask, want)
+    orig = pi[hq]                                   # original point id of every hit row
+    sel = hp < 31
+    got = torch.zeros(n, dtype=torch.int64, device="cuda")
+    got.scatter_add_(0, orig[sel], (1 << hp[sel]))
+    np.testing.assert_array_equal(got[sub].cpu().numpy(), want.astype(np.int64))

@@ -1,0 +1,77 @@
+"""Shared helpers for the parity tests: run the whole path on a host checker or on the GPU."""
+import numpy as np
+
+from cuspatial_b200 import datagen as D
+
+TREE_COLS = ("key", "level", "is_internal_node", "length", "offset")
+
+
+def make_case(n, n_poly, depth, kind="u", dtype=np.float64, seed=0, median_vertices=40,
+              oob=0, dups=0):
+    po, ro, vx, vy = D.taxi_zone_like_polygons(n_poly, seed=seed + 11, dtype=dtype,
+                                               median_vertices=median_vertices)
+    ext = D.polygon_extent(vx, vy)
+    scale = D.quadtree_params(ext, depth)
+    gen = D.uniform_points if kind == "u" else D.clustered_points
+    x, y = gen(n, ext, seed=seed + 5, dtype=dtype)
+    if oob:
+        x[:oob] = dtype(ext[1] + (ext[1] - ext[0]))  # outside the area of interest
+    if dups:
+        x[oob:oob + dups] = x[oob]
+        y[oob:oob + dups] = y[oob]
+    return dict(x=x, y=y, po=po, ro=ro, vx=vx, vy=vy, ext=ext, scale=scale, depth=depth)
+
+
+def run_host(lib, c, max_size):
+    """Full path on a HostLib (oracle or reference host build)."""
+    ext = c["ext"]
+    tree = lib.quadtree_on_points(c["x"], c["y"], ext[0], ext[1], ext[2], ext[3], c["scale"],
+                                  c["depth"], max_size)
+    bb = lib.polygon_bounding_boxes(c["po"], c["ro"], c["vx"], c["vy"])
+    if c["depth"] >= 1:
+        pairs = lib.join_quadtree_and_bounding_boxes(tree, *bb, ext[0], ext[2], c["scale"],
+                                                     c["depth"])
+        hits = lib.quadtree_point_in_polygon(pairs[0], pairs[1], tree, tree["point_indices"],
+                                             c["x"], c["y"], c["po"], c["ro"], c["vx"], c["vy"])
+    else:
+        pairs = hits = (np.empty(0, np.uint32), np.empty(0, np.uint32))
+    return dict(tree=tree, bbox=bb, pairs=pairs, hits=hits)
+
+
+def run_gpu(c, max_size):
+    """Full path through the product's Python API (-> C ABI -> CUDA kernels)."""
+    import torch
+
+    import cuspatial_b200 as cs
+
+    dev = "cuda"
+    ext = c["ext"]
+    x, y = torch.as_tensor(c["x"], device=dev), torch.as_tensor(c["y"], device=dev)
+    polys = tuple(torch.as_tensor(a, device=dev) for a in (c["po"], c["ro"], c["vx"], c["vy"]))
+    pidx, tree = cs.quadtree_on_points((x, y), ext[0], ext[1], ext[2], ext[3], c["scale"],
+                                       c["depth"], max_size)
+    bb = cs.polygon_bounding_boxes(polys)
+    t = {k: tree[k].cpu().numpy().astype(np.uint8 if k in ("level", "is_internal_node")
+                                         else np.uint32) for k in TREE_COLS}
+    t["point_indices"] = pidx.cpu().numpy()
+    out = dict(tree=t, bbox=tuple(bb[k].cpu().numpy() for k in ("minx", "miny", "maxx", "maxy")))
+    if c["depth"] >= 1:
+        pairs = cs.join_quadtree_and_bounding_boxes(tree, bb, ext[0], ext[1], ext[2], ext[3],
+                                                    c["scale"], c["depth"])
+        hits = cs.quadtree_point_in_polygon(pairs, tree, pidx, (x, y), polys)
+        out["pairs"] = (pairs["bbox_offset"].cpu().numpy(), pairs["quad_offset"].cpu().numpy())
+        out["hits"] = (hits["polygon_index"].cpu().numpy(), hits["point_index"].cpu().numpy())
+    else:
+        out["pairs"] = out["hits"] = (np.empty(0, np.uint32), np.empty(0, np.uint32))
+    return out
+
+
+def assert_same(a, b, what=""):
+    for k in TREE_COLS + ("point_indices",):
+        np.testing.assert_array_equal(a["tree"][k], b["tree"][k], err_msg="%s tree.%s" % (what, k))
+    for i in range(4):
+        np.testing.assert_array_equal(a["bbox"][i], b["bbox"][i], err_msg="%s bbox[%d]" % (what, i))
+    for name in ("pairs", "hits"):
+        for i in range(2):
+            np.testing.assert_array_equal(a[name][i], b[name][i],
+                                          err_msg="%s %s[%d]" % (what, name, i))
