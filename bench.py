@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- quadtree point-in-polygon join throughput (BASELINE.json metric) on N B200s.
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+    quadtree_on_points -> join_quadtree_and_bounding_boxes -> quadtree_point_in_polygon
+on BASELINE.json configs[1]: 100 M uniform fp64 points x 263 taxi-zone-like polygons,
+max_depth = 15, max_size = 512 (per GPU; weak scaling over GPUs).
+
+  value : points/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e   : the same through the public Python API with HOST (pinned) buffers: the H2D copy of the
+          point columns and the D2H read of the (polygon_index, point_index) table are inside
+          the timed region
+  roofline     : the dominant kernel (live CUDA-event time inside the timed region) against the
+                 measured HBM peak in MEASURED_PEAKS.json
+  cpu_baseline : the reference's own header-only implementation compiled for the host
+                 (oracle/_ref, Thrust OpenMP; kind "reference") or, if absent, the repo's CPU
+                 restatement (kind "port"), on a bounded sample of the same workload
+
+`--impl reference` times that CPU implementation only (rank 0; other ranks exit).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_POINTS = 100_000_000
+N_POLY = 263
+MAX_DEPTH = 15
+MAX_SIZE = 512
+SEED = 20251017
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json (measured)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def make_polygons():
+    from cuspatial_b200 import datagen as D
+
+    po, ro, vx, vy = D.taxi_zone_like_polygons(N_POLY, seed=SEED)
+    ext = D.polygon_extent(vx, vy)
+    return (po, ro, vx, vy), ext, D.quadtree_params(ext, MAX_DEPTH)
+
+
+def cpu_baseline(sample_points, want_seconds=15.0):
+    """Time the CPU implementation of the whole path on `sample_points` points of the workload."""
+    import numpy as np
+
+    from cuspatial_b200 import datagen as D
+    from oracle import hostlib
+
+    lib = hostlib.reference() if hostlib.reference_available() else hostlib.oracle()
+    (po, ro, vx, vy), ext, scale = make_polygons()
+    x, y = D.uniform_points(sample_points, ext, seed=1)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    tree = lib.quadtree_on_points(x, y, ext[0], ext[1], ext[2], ext[3], scale, MAX_DEPTH, MAX_SIZE)
+    bb = lib.polygon_bounding_boxes(po, ro, vx, vy)
+    pairs = lib.join_quadtree_and_bounding_boxes(tree, *bb, ext[0], ext[2], scale, MAX_DEPTH)
+    hits = lib.quadtree_point_in_polygon(pairs[0], pairs[1], tree, tree["point_indices"], x, y,
+                                         po, ro, vx, vy)
+    dt = time.perf_counter() - t0
+    return {
+        "value": sample_points / dt, "unit": "points/s", "cores": cores, "kind": lib.kind,
+        "sample": "%d uniform fp64 points of the same workload (263 polygons, max_depth 15, "
+                  "max_size 512), whole path, %.2f s, %d hit rows" % (sample_points, dt,
+                                                                      len(hits[0])),
+        "seconds": dt,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 2_000_000
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_baseline(sample)
+        if i >= args.warmup:
+            vals.append(info["seconds"])
+    ms = 1e3 * sum(vals) / max(len(vals), 1)
+    v = sample / (ms / 1e3)
+    info = dict(info, value=v)
+    info.pop("seconds", None)
+    print(json.dumps({
+        "impl": "reference", "metric": "quadtree PIP join points/sec", "value": v,
+        "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 100M uniform fp64 points x 263 polygons, "
+                               "max_depth=15 max_size=512 (each step a %d-point sample)" % sample},
+        "cpu_baseline": info,
+        "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=N_POINTS, help="points per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    import cuspatial_b200 as cs
+    from cuspatial_b200 import _lib
+    from cuspatial_b200 import datagen as D
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.points
+    (po, ro, vx, vy), ext, scale = make_polygons()
+    polys = tuple(torch.as_tensor(a, device=dev) for a in (po, ro, vx, vy))
+    if dist is not None:  # polygon table replicated from rank 0 over NCCL
+        for t in polys:
+            dist.broadcast(t, src=0)
+    x, y = D.uniform_points_torch(n, ext, SEED + rank, torch.float64, dev)
+    bb = cs.polygon_bounding_boxes(polys)
+
+    def step():
+        pidx, tree = cs.quadtree_on_points((x, y), ext[0], ext[1], ext[2], ext[3], scale,
+                                           MAX_DEPTH, MAX_SIZE)
+        pairs = cs.join_quadtree_and_bounding_boxes(tree, bb, ext[0], ext[1], ext[2], ext[3],
+                                                    scale, MAX_DEPTH)
+        hits = cs.quadtree_point_in_polygon(pairs, tree, pidx, (x, y), polys)
+        return pidx, tree, pairs, hits
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        out = step()
+    n_nodes, n_pairs, n_hits = len(out[1]), len(out[2]), len(out[3])
+    lengths = out[1]["length"].to(torch.int64)[out[2]["quad_offset"].to(torch.int64)]
+    n_cand = int(lengths.sum())
+    del out, lengths
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.set_profiling(True)
+    _lib.get_profile()
+    launches0 = _lib.kernel_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+        del out
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.kernel_launch_count() - launches0
+    profile = _lib.get_profile()
+    _lib.set_profiling(False)
+    clocks = sampler.stop()
+
+    tmax = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    value = world * n / (ms_step / 1e3)
+
+    # ---- per-stage / per-kernel device times (CUDA events recorded by the library itself)
+    stage_ms = {}
+    for name, ms in profile:
+        stage_ms.setdefault(name, []).append(ms)
+    stage_avg = {k: sum(v) / len(v) for k, v in stage_ms.items()}          # per launch
+    stage_per_step = {k: sum(v) / args.steps for k, v in stage_ms.items()}  # per step
+
+    peak, peak_src = read_peaks()
+    c, h = n_cand / n, n_hits / n
+    passes = 4
+    # algorithmic bytes per launch of the candidate dominant kernels
+    alg_bytes = {
+        "onesweep_pass": n * (12 + 16 * (passes - 1)) / passes,
+        "encode_hist": n * (2 * 8 + 4),
+        "pip_eval": n * c * (4 + 2 * 8),
+        "pip_emit": n * h * 8,
+    }
+    dom = max(alg_bytes, key=lambda k: stage_per_step.get(k, 0.0))
+    dom_ms = stage_avg.get(dom, float("nan"))
+    achieved = alg_bytes[dom] / (dom_ms / 1e3) / 1e9
+    b_alg = (2 * 8 + 4) + (12 + 16 * (passes - 1)) + 4 + c * (4 + 2 * 8) + 8 * h
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "kernel_ms_per_launch": dom_ms, "kernel_share_of_step": stage_per_step.get(dom, 0) / ms_step,
+        "pipeline": {"alg_bytes_per_point": b_alg, "candidates_per_point": c,
+                     "hits_per_point": h,
+                     "achieved_GBs": n * b_alg / (ms_step / 1e3) / 1e9,
+                     "frac": n * b_alg / (ms_step / 1e3) / 1e9 / peak},
+    }
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty(n, dtype=torch.float64).pin_memory()
+        hy = torch.empty(n, dtype=torch.float64).pin_memory()
+        hx.copy_(x)
+        hy.copy_(y)
+        torch.cuda.synchronize(dev)
+
+        def e2e_step():
+            dx = hx.to(dev, non_blocking=True)
+            dy = hy.to(dev, non_blocking=True)
+            pidx, tree = cs.quadtree_on_points((dx, dy), ext[0], ext[1], ext[2], ext[3], scale,
+                                               MAX_DEPTH, MAX_SIZE)
+            pairs = cs.join_quadtree_and_bounding_boxes(tree, bb, ext[0], ext[1], ext[2], ext[3],
+                                                        scale, MAX_DEPTH)
+            hits = cs.quadtree_point_in_polygon(pairs, tree, pidx, (dx, dy), polys)
+            a = hits["polygon_index"].cpu()
+            b = hits["point_index"].cpu()
+            return a.numel() * 4 + b.numel() * 4
+
+        d2h = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        k = max(1, min(args.steps, 3))
+        for _ in range(k):
+            d2h = e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / k], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n / float(dt.item()), "unit": "points/s",
+               "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * float(dt.item()),
+               "note": "pinned host x,y -> device, 3 API calls, full (polygon_index, point_index) "
+                       "table read back to host"}
+        del hx, hy
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(2_000_000)
+        cpu.pop("seconds", None)
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "quadtree PIP join points/sec", "value": value, "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: %d uniform fp64 points x %d taxi-zone-like "
+                                   "polygons per GPU, quadtree max_depth=%d max_size=%d"
+                                   % (n, N_POLY, MAX_DEPTH, MAX_SIZE),
+                       "l2": "inputs (%.1f GB) and every intermediate exceed the 126 MB L2"
+                             % (2 * n * 8 / 1e9),
+                       "nodes": n_nodes, "pairs": n_pairs, "candidates": n_cand, "hits": n_hits,
+                       "parallelism": "replicated polygons, independent point shards"
+                       if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+            "stage_ms_per_step": {k: round(v, 4) for k, v in stage_per_step.items()},
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

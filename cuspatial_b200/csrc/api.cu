@@ -43,6 +43,7 @@ namespace {
 thread_local std::string t_err;
 thread_local std::vector<std::pair<std::string, float>> t_profile;
 std::atomic<int> g_profiling{0};
+thread_local stage_timer* t_timer = nullptr;
 std::mutex g_pool_mutex;
 bool g_pool_done[64] = {};
 }  // namespace
@@ -64,7 +65,14 @@ void ensure_pool_configured()
 
 stage_timer::stage_timer(cudaStream_t stream) : s(stream), on(g_profiling.load() != 0)
 {
-  if (on) mark("begin");
+  if (on) {
+    mark("begin");
+    t_timer = this;
+  }
+}
+void prof_mark(const char* name)
+{
+  if (t_timer) t_timer->mark(name);
 }
 void stage_timer::mark(const char* name)
 {
@@ -86,6 +94,7 @@ void stage_timer::finish()
 }
 stage_timer::~stage_timer()
 {
+  if (t_timer == this) t_timer = nullptr;
   for (auto& m : marks) cudaEventDestroy(m.second);
 }
 

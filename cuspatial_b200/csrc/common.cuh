@@ -174,6 +174,9 @@ struct stage_timer {
   ~stage_timer();
 };
 
+// mark on the innermost live stage_timer of this thread (no-op when profiling is off)
+void prof_mark(const char* name);
+
 inline int div_up(u64 a, u64 b) { return (int)((a + b - 1) / b); }
 
 #if defined(__CUDACC__)

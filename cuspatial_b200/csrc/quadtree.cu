@@ -356,7 +356,6 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
   sort_passes(keys_a.get(), vals_a, /*iota=*/true, keys_b.get(), vals_b, n, 0, key_bits, ws, s,
               &in_a);
   const u32* sorted_keys = in_a ? keys_a.get() : keys_b.get();
-  tm.mark("sort");
 
   // ---- tree rows. Capacity: every node below level 0 has a parent with > max_size points, so a
   // level holds at most 4*floor(N/(max_size+1)) nodes, and never more than N or (2^(L+1)+3)^2

@@ -242,6 +242,7 @@ void sort_passes(u32* keys_a, u32* vals_a, bool iota_values, u32* keys_b, u32* v
   int const passes = passes_for_bits(begin_bit, end_bit);
   scan_hist_kernel<<<1, kMaxPasses * kRadixDigits, 0, s>>>(ws.hist.get());
   BSJ_CHECK_LAUNCH();
+  prof_mark("scan_hist");
   bool in_a = true;
   for (int p = 0; p < passes; ++p) {
     u32* kin  = in_a ? keys_a : keys_b;
@@ -260,6 +261,7 @@ void sort_passes(u32* keys_a, u32* vals_a, bool iota_values, u32* keys_b, u32* v
         ws.lookback.get(), ws.tickets.get() + p, tag_agg, tag_pre);
     }
     BSJ_CHECK_LAUNCH();
+    prof_mark("onesweep_pass");
     in_a = !in_a;
   }
   *result_in_a = in_a;
