@@ -19,11 +19,20 @@ class bsj_allocator(C.Structure):
     _fields_ = [("allocate", ALLOC_FN), ("deallocate", FREE_FN), ("ctx", C.c_void_p)]
 
 
+class bsj_grid(C.Structure):
+    _fields_ = [
+        ("valid", C.c_int32), ("max_depth", C.c_int32),
+        ("min_x", C.c_double), ("min_y", C.c_double), ("max_x", C.c_double), ("max_y", C.c_double),
+        ("scale", C.c_double), ("has_nan", C.c_int32), ("has_out_of_bbox", C.c_int32),
+    ]
+
+
 class bsj_quadtree(C.Structure):
     _fields_ = [
         ("point_indices", C.c_void_p), ("num_points", C.c_uint64),
         ("key", C.c_void_p), ("level", C.c_void_p), ("is_internal_node", C.c_void_p),
         ("length", C.c_void_p), ("offset", C.c_void_p), ("num_nodes", C.c_uint64),
+        ("grid", bsj_grid),
     ]
 
 
@@ -34,7 +43,7 @@ class bsj_pairs(C.Structure):
 # every symbol include/cuspatial_b200.h declares
 EXPORTED_SYMBOLS = [
     "bsj_quadtree_on_points", "bsj_join_quadtree_and_bounding_boxes",
-    "bsj_quadtree_point_in_polygon", "bsj_point_in_polygon", "bsj_polygon_bounding_boxes",
+    "bsj_quadtree_point_in_polygon", "bsj_quadtree_point_in_polygon_ex", "bsj_point_in_polygon", "bsj_polygon_bounding_boxes",
     "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
     "bsj_kernel_launch_count", "bsj_set_profiling", "bsj_get_profile",
 ]
@@ -63,6 +72,11 @@ def lib():
     L.bsj_quadtree_point_in_polygon.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, u64, vp, vp, vp,
                                                 C.c_int, u64, vp, u64, vp, u64, vp, vp, u64,
                                                 C.POINTER(bsj_allocator), vp, C.POINTER(bsj_pairs)]
+    L.bsj_quadtree_point_in_polygon_ex.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, u64, vp, vp,
+                                                   vp, C.c_int, u64, vp, u64, vp, u64, vp, vp,
+                                                   u64, C.POINTER(bsj_grid),
+                                                   C.POINTER(bsj_allocator), vp,
+                                                   C.POINTER(bsj_pairs)]
     L.bsj_point_in_polygon.argtypes = [vp, vp, C.c_int, u64, vp, u64, vp, u64, vp, vp, u64, vp, vp]
     L.bsj_polygon_bounding_boxes.argtypes = [vp, u64, vp, u64, vp, vp, C.c_int, u64, dbl, vp,
                                              vp, vp, vp, vp]

@@ -151,6 +151,11 @@ def quadtree_on_points(points, x_min, x_max, y_min, y_max, scale, max_depth, max
         ("length", alloc.take(out.length, q, torch.uint32)),
         ("offset", alloc.take(out.offset, q, torch.uint32)),
     ])
+    # cell geometry of this tree: lets quadtree_point_in_polygon settle whole quadrants without
+    # reading their points (include/cuspatial_b200.h, bsj_grid).  Rides along on the Frame only.
+    g = _lib.bsj_grid()
+    C.memmove(C.byref(g), C.byref(out.grid), C.sizeof(_lib.bsj_grid))
+    tree._grid = g
     return point_indices, tree
 
 
@@ -219,10 +224,12 @@ def quadtree_point_in_polygon(poly_quad_pairs, quadtree, point_indices, points, 
     with torch.cuda.device(dev):
         alloc = _TorchAllocator(dev)
         out = _lib.bsj_pairs()
-        rc = _lib.lib().bsj_quadtree_point_in_polygon(
+        grid = getattr(quadtree, "_grid", None)
+        rc = _lib.lib().bsj_quadtree_point_in_polygon_ex(
             _ptr(pp), _ptr(pq), pp.shape[0], *[_ptr(t) for t in tcols], tcols[0].shape[0],
             _ptr(pi), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], _ptr(po), po.shape[0],
-            _ptr(ro), ro.shape[0], _ptr(vx), _ptr(vy), vx.shape[0], C.byref(alloc.struct),
+            _ptr(ro), ro.shape[0], _ptr(vx), _ptr(vy), vx.shape[0],
+            C.byref(grid) if grid is not None else None, C.byref(alloc.struct),
             _stream(dev), C.byref(out))
         _lib.check(rc)
     h = int(out.size)

@@ -2,6 +2,7 @@
 // plumbing.  The reference-side checks are cited next to each condition.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -28,8 +29,8 @@ void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, 
                                     int dtype, u64 n_points, const u32* poly_offsets,
                                     u64 n_poly_offsets, const u32* ring_offsets,
                                     u64 n_ring_offsets, const void* vx, const void* vy,
-                                    u64 n_verts, const bsj_allocator* mr, cudaStream_t s,
-                                    bsj_pairs* out);
+                                    u64 n_verts, const bsj_grid* grid, const bsj_allocator* mr,
+                                    cudaStream_t s, bsj_pairs* out);
 void point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_points,
                            const i32* poly_offsets, u64 n_poly_offsets, const i32* ring_offsets,
                            u64 n_ring_offsets, const void* vx, const void* vy, u64 n_verts,
@@ -59,6 +60,15 @@ void ensure_pool_configured()
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     uint64_t thr = ~0ull;  // keep freed blocks cached in the pool
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  // The refinement gathers 8-byte coordinates at random: ask L2 to fetch 32-byte sectors from
+  // HBM instead of promoting every miss to a larger block (measured: see DESIGN.md section 5).
+  {
+    size_t gran = 32;
+    if (const char* e = std::getenv("BSJ_L2_FETCH_GRANULARITY")) gran = (size_t)std::atoi(e);
+    if (gran == 32 || gran == 64 || gran == 128)
+      cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    cudaGetLastError();
   }
   g_pool_done[dev] = true;
 }
@@ -172,17 +182,17 @@ int bsj_join_quadtree_and_bounding_boxes(const uint32_t* key, const uint8_t* lev
   });
 }
 
-int bsj_quadtree_point_in_polygon(const uint32_t* pair_poly, const uint32_t* pair_quad,
-                                  uint64_t n_pairs, const uint32_t* key, const uint8_t* level,
-                                  const uint8_t* is_internal_node, const uint32_t* length,
-                                  const uint32_t* offset, uint64_t num_nodes,
-                                  const uint32_t* point_indices, const void* point_x,
-                                  const void* point_y, int dtype, uint64_t n_points,
-                                  const uint32_t* poly_offsets, uint64_t n_poly_offsets,
-                                  const uint32_t* ring_offsets, uint64_t n_ring_offsets,
-                                  const void* poly_points_x, const void* poly_points_y,
-                                  uint64_t n_poly_points, const bsj_allocator* mr,
-                                  bsj_stream_t stream, bsj_pairs* out)
+int bsj_quadtree_point_in_polygon_ex(const uint32_t* pair_poly, const uint32_t* pair_quad,
+                                     uint64_t n_pairs, const uint32_t* key, const uint8_t* level,
+                                     const uint8_t* is_internal_node, const uint32_t* length,
+                                     const uint32_t* offset, uint64_t num_nodes,
+                                     const uint32_t* point_indices, const void* point_x,
+                                     const void* point_y, int dtype, uint64_t n_points,
+                                     const uint32_t* poly_offsets, uint64_t n_poly_offsets,
+                                     const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+                                     const void* poly_points_x, const void* poly_points_y,
+                                     uint64_t n_poly_points, const bsj_grid* grid,
+                                     const bsj_allocator* mr, bsj_stream_t stream, bsj_pairs* out)
 {
   return guarded([&] {
     BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
@@ -199,9 +209,29 @@ int bsj_quadtree_point_in_polygon(const uint32_t* pair_poly, const uint32_t* pai
     quadtree_point_in_polygon_impl(pair_poly, pair_quad, n_pairs, key, level, is_internal_node,
                                    length, offset, num_nodes, point_indices, point_x, point_y,
                                    dtype, n_points, poly_offsets, n_poly_offsets, ring_offsets,
-                                   n_ring_offsets, poly_points_x, poly_points_y, n_poly_points, mr,
-                                   (cudaStream_t)stream, out);
+                                   n_ring_offsets, poly_points_x, poly_points_y, n_poly_points,
+                                   grid, mr, (cudaStream_t)stream, out);
   });
+}
+
+int bsj_quadtree_point_in_polygon(const uint32_t* pair_poly, const uint32_t* pair_quad,
+                                  uint64_t n_pairs, const uint32_t* key, const uint8_t* level,
+                                  const uint8_t* is_internal_node, const uint32_t* length,
+                                  const uint32_t* offset, uint64_t num_nodes,
+                                  const uint32_t* point_indices, const void* point_x,
+                                  const void* point_y, int dtype, uint64_t n_points,
+                                  const uint32_t* poly_offsets, uint64_t n_poly_offsets,
+                                  const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+                                  const void* poly_points_x, const void* poly_points_y,
+                                  uint64_t n_poly_points, const bsj_allocator* mr,
+                                  bsj_stream_t stream, bsj_pairs* out)
+{
+  return bsj_quadtree_point_in_polygon_ex(pair_poly, pair_quad, n_pairs, key, level,
+                                          is_internal_node, length, offset, num_nodes,
+                                          point_indices, point_x, point_y, dtype, n_points,
+                                          poly_offsets, n_poly_offsets, ring_offsets,
+                                          n_ring_offsets, poly_points_x, poly_points_y,
+                                          n_poly_points, nullptr, mr, stream, out);
 }
 
 int bsj_point_in_polygon(const void* point_x, const void* point_y, int dtype, uint64_t n_points,

@@ -31,6 +31,7 @@
 //   back to evaluating every edge in the reference's order (pip_reference below).
 #include "scan.cuh"
 
+#include <cmath>
 #include <cstdlib>
 
 namespace bsj {
@@ -190,6 +191,92 @@ poly_meta_kernel(const u32* __restrict__ poly_offsets, u32 n_poly,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Whole-quadrant classification from the cell rectangle (optional bsj_grid hint).
+//
+// A quadrant at (level, key) holds exactly the points whose cell index, floor((x-min)/scale)
+// computed in T, falls in its key range; its points therefore lie in the cell rectangle widened by
+// a rounding margin.  If no polygon edge comes near that rectangle (edge bounding box, widened by
+// the 4-ULP on-edge tolerance, disjoint from it) and no vertical edge has its x inside the
+// rectangle's x-range (the reference rejects such points at ANY y), then every crossing decision
+// is sign-certain and identical for all points of the rectangle: the quadrant is uniformly inside
+// or outside and the answer is the predicate of the rectangle's centre.  No point is read.
+// ---------------------------------------------------------------------------------------------
+struct grid_info {
+  int valid;
+  int max_depth;
+  int has_oob;
+  double min_x, min_y, scale;
+  double margin_x, margin_y;  // rounding margin of the point -> cell assignment
+};
+
+constexpr int kClsOutside = 0, kClsInside = 1, kClsBoundary = 2;
+
+__device__ __forceinline__ u32 undilate16p(u32 v)
+{
+  v &= 0x55555555u;
+  v = (v | (v >> 1)) & 0x33333333u;
+  v = (v | (v >> 2)) & 0x0F0F0F0Fu;
+  v = (v | (v >> 4)) & 0x00FF00FFu;
+  v = (v | (v >> 8)) & 0x0000FFFFu;
+  return v;
+}
+
+// warp-cooperative; all lanes return the same class
+template <typename T>
+__device__ int classify_quadrant(const grid_info& g, u32 key, u32 level, const poly_meta<T>& m,
+                                 const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
+                                 const T* __restrict__ vy)
+{
+  int const sh = g.max_depth - 1 - (int)level;
+  if (!g.valid || !m.safe || sh < 0) return kClsBoundary;
+  // the last cell also receives every out-of-box point, whatever its coordinates
+  if (g.has_oob && level < 16 && key == ((1u << (2 * (level + 1))) - 1u)) return kClsBoundary;
+  double const ls = g.scale * (double)(1u << sh);
+  double const kx = (double)undilate16p(key), ky = (double)undilate16p(key >> 1);
+  double const x0 = g.min_x + kx * ls, x1 = g.min_x + (kx + 1.0) * ls;
+  double const y0 = g.min_y + ky * ls, y1 = g.min_y + (ky + 1.0) * ls;
+  double const ex0 = x0 - g.margin_x, ex1 = x1 + g.margin_x;
+  double const ey0 = y0 - g.margin_y, ey1 = y1 + g.margin_y;
+  double const eps = (double)fpp<T>::eps();
+  {
+    double const dx = eps * fmax(fabs((double)m.xmin), fabs((double)m.xmax));
+    double const dy = eps * fmax(fabs((double)m.ymin), fabs((double)m.ymax));
+    if (ex1 < (double)m.xmin - dx || ex0 > (double)m.xmax + dx || ey1 < (double)m.ymin - dy ||
+        ey0 > (double)m.ymax + dy)
+      return kClsOutside;
+  }
+  T const cx = (T)(0.5 * (x0 + x1)), cy = (T)(0.5 * (y0 + y1));
+  u32 const lane = lane_id();
+  bool near  = false;
+  u32 cross  = 0;
+  for (u32 ring = m.ring_begin; ring < m.ring_end; ++ring) {
+    u32 const v0 = ring_offsets[ring], v1 = ring_offsets[ring + 1];
+    u32 const nv = v1 - v0;
+    for (u32 e = lane; e < nv; e += 32) {
+      u32 const pr = e == 0 ? nv - 1 : e - 1;
+      T const ax = __ldg(vx + v0 + e), ay = __ldg(vy + v0 + e);
+      T const bx = __ldg(vx + v0 + pr), by = __ldg(vy + v0 + pr);
+      if (ax == bx && ay == by) continue;  // degenerate segment: skipped by the reference
+      double const d = eps * fmax(fmax(fabs((double)ax), fabs((double)bx)),
+                                  fmax(fabs((double)ay), fabs((double)by)));
+      double const lx = fmin((double)ax, (double)bx) - d, hx = fmax((double)ax, (double)bx) + d;
+      double const ly = fmin((double)ay, (double)by) - d, hy = fmax((double)ay, (double)by) + d;
+      bool const overlap = !(hx < ex0 || lx > ex1 || hy < ey0 || ly > ey1);
+      bool const vert    = ax == bx && (double)ax >= ex0 && (double)ax <= ex1;
+      near = near || overlap || vert;
+      bool const f1 = ay > cy, f0 = by > cy;
+      if (f1 != f0) {
+        T const u = fpp<T>::mul(fpp<T>::sub(bx, ax), fpp<T>::sub(cy, ay));
+        T const v = fpp<T>::mul(fpp<T>::sub(cx, ax), fpp<T>::sub(by, ay));
+        cross ^= (u32)((v < u) != f1);
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, near)) return kClsBoundary;
+  return (__popc(__ballot_sync(0xffffffffu, cross & 1u)) & 1) ? kClsInside : kClsOutside;
+}
+
+// ---------------------------------------------------------------------------------------------
 // pair bookkeeping
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -231,7 +318,8 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
                 const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
                 const T* __restrict__ vy, const u64* __restrict__ wbase,
                 u32* __restrict__ mask_words, u32* __restrict__ hits, u32* __restrict__ ticket,
-                int force_reference)
+                int force_reference, const u32* __restrict__ node_key,
+                const u8* __restrict__ node_level, grid_info grid, u8* __restrict__ cls)
 {
   u32 const lane   = lane_id();
   u32 const n_runs = (u32)*n_runs_ptr;
@@ -250,9 +338,36 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
     }
     u32 const len = length[quad], off = offset[quad];
     if (len == 0) {
-      for (u32 j = j0 + lane; j < j1; j += 32) hits[j] = 0;
+      for (u32 j = j0 + lane; j < j1; j += 32) {
+        hits[j] = 0;
+        cls[j]  = kClsOutside;
+      }
       continue;
     }
+
+    // ---- whole-quadrant decisions first: pairs settled here never touch the points
+    bool need_points = false;
+    {
+      u32 const nkey = node_key[quad], nlev = node_level[quad];
+      u32 const nvalid = off < n_points ? min(len, n_points - off) : 0u;
+      for (u32 j = j0; j < j1; ++j) {
+        u32 const poly = pair_poly[j];
+        int c          = kClsOutside;
+        if (poly < n_poly) {
+          poly_meta<T> const m = meta[poly];
+          c = (grid.valid && !force_reference)
+                ? classify_quadrant<T>(grid, nkey, nlev, m, ring_offsets, vx, vy)
+                : kClsBoundary;
+        }
+        if (lane == 0) {
+          cls[j] = (u8)c;
+          if (c != kClsBoundary) hits[j] = c == kClsInside ? nvalid : 0u;
+        }
+        need_points = need_points || c == kClsBoundary;
+      }
+    }
+    if (!need_points) continue;
+    __syncwarp();  // cls[] written by lane 0 is read by every lane below
 
     for (u32 base = 0; base < len; base += kPipTile) {
       // ---- gather this tile's points once (quadtree_point_in_polygon.cuh:66,170)
@@ -298,6 +413,7 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
       u32 const tile_words = (min(len - base, (u32)kPipTile) + 31) / 32;  // <= 8
 
       for (u32 j = j0; j < j1; ++j) {
+        if (__ldcg(cls + j) != kClsBoundary) continue;  // settled from the cell rectangle
         u32 const poly = pair_poly[j];
         u32 inside     = 0;  // bit i: point i of this lane is inside
         if (poly < n_poly) {
@@ -381,39 +497,69 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
 }
 
 // ---------------------------------------------------------------------------------------------
-// expansion of ballot words into (polygon_index, point_index) rows; one warp per pair
+// expansion of ballot words into (polygon_index, point_index) rows; one warp per pair.
+// Rows are produced 32 at a time with one lane per OUTPUT row (fully coalesced stores): lane r
+// finds the word holding the r-th hit of the current 32-word group by a shuffle binary search over
+// the lanes' inclusive popcounts and the bit inside it with __fns.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad, u32 n_pairs,
                 const u32* __restrict__ length, const u32* __restrict__ offset, u32 num_nodes,
                 const u64* __restrict__ wbase, const u64* __restrict__ obase,
                 const u32* __restrict__ hits, const u32* __restrict__ mask_words,
-                u32* __restrict__ out_poly, u32* __restrict__ out_point)
+                const u8* __restrict__ cls, u32* __restrict__ out_poly,
+                u32* __restrict__ out_point)
 {
-  u32 const lane    = lane_id();
-  u32 const warps   = (gridDim.x * blockDim.x) >> 5;
+  u32 const lane  = lane_id();
+  u32 const warps = (gridDim.x * blockDim.x) >> 5;
   for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_pairs; j += warps) {
-    if (hits[j] == 0) continue;
+    u32 const nh = hits[j];
+    if (nh == 0) continue;
     u32 const quad = pair_quad[j];
     if (quad >= num_nodes) continue;
     u32 const poly = pair_poly[j], len = length[quad], off = offset[quad];
     u32 const words = len / 32 + ((len & 31) != 0);
     u64 const wb    = wbase[j];
     u64 o           = obase[j];
+    if (cls[j] == kClsInside) {  // whole quadrant inside: rows are (poly, off .. off+nh-1)
+      for (u32 r = lane; r < nh; r += 32) {
+        __stcs(out_poly + o + r, poly);
+        __stcs(out_point + o + r, off + r);
+      }
+      continue;
+    }
     for (u32 w0 = 0; w0 < words; w0 += 32) {
-      u32 w = w0 + lane < words ? __ldcs(mask_words + wb + w0 + lane) : 0u;
+      u32 const w    = w0 + lane < words ? __ldcs(mask_words + wb + w0 + lane) : 0u;
       u32 const c    = __popc(w);
       u32 const incl = warp_inclusive_scan(c);
-      u64 at         = o + incl - c;
-      u32 const pt0  = off + (w0 + lane) * 32;
-      while (w) {
-        int const b = __ffs(w) - 1;
-        w &= w - 1;
-        out_poly[at]  = poly;
-        out_point[at] = pt0 + b;
-        ++at;
+      u32 const tot  = __shfl_sync(0xffffffffu, incl, 31);
+      if (tot == 1024) {  // every candidate of the group is a hit: identity mapping
+        for (u32 r = lane; r < 1024; r += 32) {
+          __stcs(out_poly + o + r, poly);
+          __stcs(out_point + o + r, off + w0 * 32 + r);
+        }
+      } else {
+        for (u32 r0 = 0; r0 < tot; r0 += 32) {
+          u32 const r = r0 + lane;
+          // smallest lane index s with incl[s] > r
+          u32 s = 0;
+#pragma unroll
+          for (int step = 16; step; step >>= 1) {
+            u32 const probe = __shfl_sync(0xffffffffu, incl, s + step - 1);
+            if (probe <= r) s += step;
+          }
+          u32 const ws    = __shfl_sync(0xffffffffu, w, s);
+          u32 const incls = __shfl_sync(0xffffffffu, incl, s);
+          u32 const cs    = __popc(ws);
+          if (r < tot) {
+            u32 const nth = r - (incls - cs);  // 0-based rank inside word s
+            u32 const bit = __fns(ws, 0, nth + 1);
+            __stcs(out_poly + o + r, poly);
+            __stcs(out_point + o + r, off + (w0 + s) * 32 + bit);
+          }
+        }
       }
-      o += __shfl_sync(0xffffffffu, incl, 31);
+      o += tot;
     }
   }
 }
@@ -496,10 +642,35 @@ void qpip_impl_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const 
                  const u32* offset, u64 num_nodes, const u32* point_indices, const void* px,
                  const void* py, u64 n_points, const u32* poly_offsets, u64 n_poly_offsets,
                  const u32* ring_offsets, u64 n_ring_offsets, const void* vx, const void* vy,
-                 u64 n_verts, const bsj_allocator* mr, cudaStream_t s, bsj_pairs* out)
+                 u64 n_verts, const u32* node_key, const u8* node_level, const bsj_grid* grid,
+                 const bsj_allocator* mr, cudaStream_t s, bsj_pairs* out)
 {
   stage_timer tm(s);
   u32 const n_poly = (u32)(n_poly_offsets - 1);
+  grid_info gi{};
+  {
+    static int no_grid = -1;
+    if (no_grid < 0) {
+      const char* e = std::getenv("BSJ_PIP_NO_GRID");
+      no_grid       = (e && e[0] == '1') ? 1 : 0;
+    }
+    // NaN coordinates pass the reference's box test and key into row/column 0, so with NaNs
+    // present a cell rectangle no longer bounds its points: the hint is dropped.
+    if (grid && grid->valid && !grid->has_nan && !no_grid && node_key && node_level &&
+        grid->scale > 0 && grid->max_depth >= 1 && grid->max_depth <= 15) {
+      gi.valid     = 1;
+      gi.max_depth = grid->max_depth;
+      gi.has_oob   = grid->has_out_of_bbox;
+      gi.min_x = grid->min_x; gi.min_y = grid->min_y; gi.scale = grid->scale;
+      // |x - min| / scale is computed with two roundings of relative size 2^-53 (2^-24): a point
+      // lies at most ~3 ulp(extent) outside its cell; take 2^-40 (2^-18) of the coordinate range
+      double const c  = sizeof(T) == 8 ? 9.094947017729282e-13 : 3.814697265625e-06;
+      gi.margin_x = c * (std::fabs(grid->min_x) + std::fabs(grid->max_x) +
+                         std::fabs(grid->max_x - grid->min_x));
+      gi.margin_y = c * (std::fabs(grid->min_y) + std::fabs(grid->max_y) +
+                         std::fabs(grid->max_y - grid->min_y));
+    }
+  }
   dev_buf<poly_meta<T>> meta(std::max<u32>(n_poly, 1), s);
   if (n_poly) {
     poly_meta_kernel<T><<<div_up((u64)n_poly * 32, 128), 128, 0, s>>>(
@@ -510,6 +681,7 @@ void qpip_impl_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const 
   dev_buf<u32> words(n_pairs, s), heads(n_pairs, s), hits(n_pairs, s), run_start(n_pairs + 1, s);
   dev_buf<u64> wbase(n_pairs, s), run_idx(n_pairs, s), obase(n_pairs, s), totals(4, s);
   dev_buf<u32> ticket(1, s);
+  dev_buf<u8> cls(n_pairs, s);
   BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
   pair_prep_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(pair_quad, (u32)n_pairs, length,
                                                         (u32)num_nodes, words.get(), heads.get());
@@ -532,7 +704,7 @@ void qpip_impl_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const 
       pair_poly, pair_quad, run_start.get(), totals.get() + 1, length, offset, (u32)num_nodes,
       point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly, ring_offsets,
       (const T*)vx, (const T*)vy, wbase.get(), mask_words.get(), hits.get(), ticket.get(),
-      force_reference_mode());
+      force_reference_mode(), node_key, node_level, gi, cls.get());
     BSJ_CHECK_LAUNCH();
   }
   tm.mark("pip_eval");
@@ -548,7 +720,7 @@ void qpip_impl_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const 
     int const grid = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_pairs * 32, 256));
     pip_emit_kernel<<<std::max(grid, 1), 256, 0, s>>>(
       pair_poly, pair_quad, (u32)n_pairs, length, offset, (u32)num_nodes, wbase.get(),
-      obase.get(), hits.get(), mask_words.get(), out->first, out->second);
+      obase.get(), hits.get(), mask_words.get(), cls.get(), out->first, out->second);
     BSJ_CHECK_LAUNCH();
   }
   tm.mark("pip_emit");
@@ -590,10 +762,10 @@ void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, 
                                     int dtype, u64 n_points, const u32* poly_offsets,
                                     u64 n_poly_offsets, const u32* ring_offsets,
                                     u64 n_ring_offsets, const void* vx, const void* vy,
-                                    u64 n_verts, const bsj_allocator* mr, cudaStream_t s,
-                                    bsj_pairs* out)
+                                    u64 n_verts, const bsj_grid* grid, const bsj_allocator* mr,
+                                    cudaStream_t s, bsj_pairs* out)
 {
-  (void)key; (void)level; (void)internal;
+  (void)internal;
   *out = bsj_pairs{};
   // empty inputs: cpp/src/join/quadtree_point_in_polygon.cu:171-178
   if (n_pairs == 0 || num_nodes == 0 || n_points == 0 || n_poly_offsets == 0) return;
@@ -603,11 +775,11 @@ void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, 
   if (dtype == BSJ_FLOAT32)
     qpip_impl_t<float>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes, point_indices, px,
                        py, n_points, poly_offsets, n_poly_offsets, ring_offsets, n_ring_offsets,
-                       vx, vy, n_verts, mr, s, out);
+                       vx, vy, n_verts, key, level, grid, mr, s, out);
   else
     qpip_impl_t<double>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes, point_indices,
                         px, py, n_points, poly_offsets, n_poly_offsets, ring_offsets,
-                        n_ring_offsets, vx, vy, n_verts, mr, s, out);
+                        n_ring_offsets, vx, vy, n_verts, key, level, grid, mr, s, out);
 }
 
 void point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_points,

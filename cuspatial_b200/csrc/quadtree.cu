@@ -49,9 +49,13 @@ struct fp<double> {
 // -prec-div=true), no reciprocal multiply.
 template <typename T>
 __device__ __forceinline__ u32 point_key(T x, T y, T min_x, T min_y, T max_x, T max_y, T scale,
-                                         u32 oob_key)
+                                         u32 oob_key, u32& flags)
 {
-  if (x < min_x || x > max_x || y < min_y || y > max_y) return oob_key;
+  if (x < min_x || x > max_x || y < min_y || y > max_y) {
+    flags |= 1u;
+    return oob_key;
+  }
+  if (x != x || y != y) flags |= 2u;
   u32 const ix = fp<T>::to_u32(fp<T>::div(fp<T>::sub(x, min_x), scale)) & 0xFFFFu;
   u32 const iy = fp<T>::to_u32(fp<T>::div(fp<T>::sub(y, min_y), scale)) & 0xFFFFu;
   return (dilate16(iy) << 1) | dilate16(ix);
@@ -66,8 +70,9 @@ template <typename T>
 __global__ void __launch_bounds__(512)
 encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T min_x, T min_y,
                    T max_x, T max_y, T scale, u32 oob_key, int passes, u32* __restrict__ keys,
-                   u32* __restrict__ hist)
+                   u32* __restrict__ hist, u32* __restrict__ point_flags)
 {
+  u32 flags = 0;  // bit 0: a point outside the box, bit 1: a NaN coordinate
   constexpr int V = 16 / sizeof(T);  // points per 128-bit load
   __shared__ u32 s_hist[kMaxPasses * kRadixDigits];
   for (int i = threadIdx.x; i < kMaxPasses * kRadixDigits; i += blockDim.x) s_hist[i] = 0;
@@ -92,7 +97,7 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
       u32 ks[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        ks[j] = point_key<T>(xs[j], ys[j], min_x, min_y, max_x, max_y, scale, oob_key);
+        ks[j] = point_key<T>(xs[j], ys[j], min_x, min_y, max_x, max_y, scale, oob_key, flags);
         tally(ks[j]);
       }
       if constexpr (V == 2)
@@ -102,13 +107,13 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
     }
     // tail
     for (u64 i = nvec * V + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, oob_key);
+      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, oob_key, flags);
       tally(k);
       keys[i] = k;
     }
   } else {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, oob_key);
+      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, oob_key, flags);
       tally(k);
       keys[i] = k;
     }
@@ -116,6 +121,7 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
   __syncthreads();
   for (int i = threadIdx.x; i < passes * kRadixDigits; i += blockDim.x)
     if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+  if (flags) atomicOr(point_flags, flags);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -125,7 +131,7 @@ struct tree_state {
   u32 level_begin[17];
   u32 level_end[17];
   u32 overflow;
-  u32 pad;
+  u32 point_flags;  // written by the encode kernel
 };
 
 // first index in [lo, hi) whose key is >= target (target is 64-bit: wide keys cannot overflow it)
@@ -293,7 +299,7 @@ expand_level_kernel(const u32* __restrict__ keys, int L, int max_depth, u32 max_
 template <typename T>
 void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_max, double y_min,
                    double y_max, double scale_d, int max_depth, int passes, u32* keys, u32* hist,
-                   cudaStream_t s)
+                   u32* point_flags, bsj_grid* grid, cudaStream_t s)
 {
   // the column API casts to T (cpp/src/indexing/point_quadtree.cu:82-84), the header API then
   // orders the corners and clamps scale in T (detail/point_quadtree.cuh:259-268)
@@ -304,10 +310,15 @@ void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_m
                                          (T)((1 << max_depth) + 2));
   u32 const oob_key = (u32)((1 << (2 * max_depth)) - 1);
   int const V       = 16 / sizeof(T);
-  int const grid    = (int)std::min<u64>((u64)kNumSMs * 4, (u64)div_up(div_up(n, V), 512));
-  encode_hist_kernel<T><<<std::max(grid, 1), 512, 0, s>>>(
-    (const T*)x, (const T*)y, n, min_x, min_y, max_x, max_y, scale, oob_key, passes, keys, hist);
+  int const nblk    = (int)std::min<u64>((u64)kNumSMs * 4, (u64)div_up(div_up(n, V), 512));
+  encode_hist_kernel<T><<<std::max(nblk, 1), 512, 0, s>>>(
+    (const T*)x, (const T*)y, n, min_x, min_y, max_x, max_y, scale, oob_key, passes, keys, hist,
+    point_flags);
   BSJ_CHECK_LAUNCH();
+  grid->valid     = 1;
+  grid->max_depth = max_depth;
+  grid->min_x = min_x; grid->min_y = min_y; grid->max_x = max_x; grid->max_y = max_y;
+  grid->scale = scale;
 }
 
 }  // namespace
@@ -339,12 +350,15 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
   ws.alloc(n, s);
   sort_workspace_reset(ws, s);
 
+  dev_buf<tree_state> st(1, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(st.get(), 0, sizeof(tree_state), s));
+  bsj_grid grid{};
   if (dtype == BSJ_FLOAT32)
     launch_encode<float>(x, y, n, x_min, x_max, y_min, y_max, scale, d, passes, keys_a.get(),
-                         ws.hist.get(), s);
+                         ws.hist.get(), &st.get()->point_flags, &grid, s);
   else
     launch_encode<double>(x, y, n, x_min, x_max, y_min, y_max, scale, d, passes, keys_a.get(),
-                          ws.hist.get(), s);
+                          ws.hist.get(), &st.get()->point_flags, &grid, s);
   tm.mark("encode_hist");
 
   // ping-pong so that the last pass writes into out_idx: with P passes the result lands in
@@ -370,11 +384,9 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
   }
   dev_buf<u32> tkey(cap, s), tlen(cap, s), toff(cap, s);
   dev_buf<u8> tlevel(cap, s), tint(cap, s);
-  dev_buf<tree_state> st(1, s);
   u32 const max_tiles = (u32)div_up(cap, kExpandBlock) + 1;
   dev_buf<u64> lb(max_tiles, s);
   dev_buf<u32> tickets(16, s);
-  BSJ_CUDA_TRY(cudaMemsetAsync(st.get(), 0, sizeof(tree_state), s));
   BSJ_CUDA_TRY(cudaMemsetAsync(lb.get(), 0, max_tiles * sizeof(u64), s));
   BSJ_CUDA_TRY(cudaMemsetAsync(tickets.get(), 0, 16 * sizeof(u32), s));
 
@@ -401,6 +413,9 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
   int const last = d >= 2 ? d - 1 : 0;
   u64 const q    = h.level_end[last];
 
+  grid.has_out_of_bbox  = (h.point_flags & 1u) ? 1 : 0;
+  grid.has_nan          = (h.point_flags & 2u) ? 1 : 0;
+  out->grid             = grid;
   out->point_indices    = out_idx;
   out->num_points       = n;
   out->num_nodes        = q;

@@ -88,16 +88,24 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
     key[i]        = idx < n ? ld_stream(keys_in + idx) : 0xFFFFFFFFu;
   }
 
-  // ---- per-warp stable ranking with match.any
+  // ---- per-warp stable ranking.  Peer masks come from 8 ballots (one per digit bit) instead of
+  // match.any: MATCH.ANY was the top stall of this kernel on B200 (ncu, profiles/), the ballots
+  // are independent of each other and of the counter chain.
   u32* const wh = sm.whist + warp * kRadixDigits;
   u32 const lt  = lanemask_lt();
   unsigned short rank[kSortIPT];
 #pragma unroll
   for (int i = 0; i < kSortIPT; ++i) {
-    u32 const d     = (key[i] >> shift) & 0xFFu;
-    u32 const peers = __match_any_sync(0xffffffffu, d);
-    int const lead  = __ffs(peers) - 1;
-    u32 prev        = 0;
+    u32 const d = (key[i] >> shift) & 0xFFu;
+    u32 peers   = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < kRadixBits; ++b) {
+      bool const bit = (d >> b) & 1u;
+      u32 const m    = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? m : ~m;
+    }
+    int const lead = __ffs(peers) - 1;
+    u32 prev       = 0;
     if (lane == lead) {
       prev  = wh[d];
       wh[d] = prev + __popc(peers);

@@ -60,6 +60,20 @@ typedef struct bsj_allocator {
   void* ctx;
 } bsj_allocator;
 
+/* How the quadtree's cells map to coordinates: filled by bsj_quadtree_on_points, optionally handed
+ * back to bsj_quadtree_point_in_polygon_ex so that quadrants lying entirely inside or outside a
+ * polygon are decided from their cell rectangle without gathering their points.  Purely an
+ * acceleration hint: results are identical with or without it. */
+typedef struct bsj_grid {
+  int32_t valid;           /* 0 = unknown (hint ignored)                                        */
+  int32_t max_depth;       /* clamped depth the keys were built with                            */
+  double min_x, min_y;     /* area-of-interest corners and scale exactly as used for the keys   */
+  double max_x, max_y;     /* (values of the coordinate type, widened to double)                */
+  double scale;
+  int32_t has_nan;         /* some coordinate was NaN (such points key into row/column 0)       */
+  int32_t has_out_of_bbox; /* some point lay outside the box (all keyed to the last cell)       */
+} bsj_grid;
+
 /* Result of bsj_quadtree_on_points == the reference's
  * std::pair<std::unique_ptr<cudf::column>, std::unique_ptr<cudf::table>>
  * (cpp/include/cuspatial/point_quadtree.hpp:68-78; column order cpp/src/indexing/point_quadtree.cu:92-118). */
@@ -72,6 +86,7 @@ typedef struct bsj_quadtree {
   uint32_t* length;          /* UINT32[num_nodes]: #children (internal) or #points (leaf)      */
   uint32_t* offset;          /* UINT32[num_nodes]: first child row (internal) / first point pos */
   uint64_t num_nodes;
+  bsj_grid grid;             /* not part of the reference's result: optional hint, see bsj_grid */
 } bsj_quadtree;
 
 /* A two-column UINT32 table: (bbox_offset, quad_offset) or (polygon_index, point_index). */
@@ -134,6 +149,21 @@ int bsj_quadtree_point_in_polygon(const uint32_t* pair_poly, const uint32_t* pai
                                   uint64_t n_poly_points, const bsj_allocator* mr,
                                   bsj_stream_t stream,
                                   bsj_pairs* out /* first=polygon_index, second=point_index */);
+
+/* Same as bsj_quadtree_point_in_polygon plus the optional cell-geometry hint (`grid` may be NULL or
+ * have valid == 0).  The hint must describe the quadtree passed in, and `point_x/point_y` must be
+ * the points that quadtree was built from -- which the reference's contract requires anyway. */
+int bsj_quadtree_point_in_polygon_ex(const uint32_t* pair_poly, const uint32_t* pair_quad,
+                                     uint64_t n_pairs, const uint32_t* key, const uint8_t* level,
+                                     const uint8_t* is_internal_node, const uint32_t* length,
+                                     const uint32_t* offset, uint64_t num_nodes,
+                                     const uint32_t* point_indices, const void* point_x,
+                                     const void* point_y, int dtype, uint64_t n_points,
+                                     const uint32_t* poly_offsets, uint64_t n_poly_offsets,
+                                     const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+                                     const void* poly_points_x, const void* poly_points_y,
+                                     uint64_t n_poly_points, const bsj_grid* grid,
+                                     const bsj_allocator* mr, bsj_stream_t stream, bsj_pairs* out);
 
 /*
  * Replaces cuspatial::point_in_polygon (bitmask form)

@@ -116,7 +116,9 @@ def test_random_inputs_equal_oracle(oracle_lib, case, dtype):
     n, n_poly, depth, max_size, kind, oob, dups, mv = case
     c = make_case(n, n_poly, depth, kind, dtype, seed=n + depth, oob=oob, dups=dups,
                   median_vertices=mv)
-    assert_same(run_gpu(c, max_size), run_host(oracle_lib, c, max_size), "gpu vs oracle")
+    want = run_host(oracle_lib, c, max_size)
+    assert_same(run_gpu(c, max_size), want, "gpu vs oracle")
+    assert_same(run_gpu(c, max_size, use_grid_hint=False), want, "gpu (no grid hint) vs oracle")
 
 
 def test_config1_1M_uniform_263_polygons_equals_oracle_and_reference(oracle_lib):
@@ -155,7 +157,39 @@ def test_near_edge_points_equal_oracle(oracle_lib, dtype):
     keep = (x > c["ext"][0]) & (x < c["ext"][1]) & (y > c["ext"][2]) & (y < c["ext"][3])
     c2 = dict(c, x=x[keep], y=y[keep], po=po, ro=ro, vx=vx, vy=vy)
     for max_size in (8, 100000):
-        assert_same(run_gpu(c2, max_size), run_host(oracle_lib, c2, max_size), "near-edge")
+        want = run_host(oracle_lib, c2, max_size)
+        assert_same(run_gpu(c2, max_size), want, "near-edge")
+        assert_same(run_gpu(c2, max_size, use_grid_hint=False), want, "near-edge (no hint)")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("depth,max_size", [(6, 4), (4, 50), (8, 1)])
+def test_grid_aligned_polygons_and_lattice_points(oracle_lib, dtype, depth, max_size):
+    """Polygon edges lying exactly on quadtree cell boundaries and points on a lattice that hits
+    cell borders, polygon vertices and vertical edges: the whole-quadrant shortcut must classify
+    every such quadrant as 'boundary' (vertical-edge rule, on-edge rule)."""
+    ext = (0.0, 64.0, 0.0, 64.0)
+    scale = 64.0 / (1 << depth)
+    rings = [
+        [(8, 8), (24, 8), (24, 24), (8, 24), (8, 8)],                       # cell-aligned square
+        [(32, 4), (60, 4), (60, 30), (46, 30), (46, 18), (32, 18), (32, 4)],  # L-shape
+        [(4, 40), (28, 40), (16, 60), (4, 40)],                              # triangle
+        [(36, 36), (60, 36), (60, 60), (36, 60), (36, 36)],                  # square with a hole
+        [(44, 44), (44, 52), (52, 52), (52, 44), (44, 44)],
+    ]
+    po = np.array([0, 1, 2, 3, 5], dtype=np.uint32)
+    ro = np.cumsum([0] + [len(r) for r in rings]).astype(np.uint32)
+    v = np.array([p for r in rings for p in r], dtype=dtype)
+    g = np.arange(0, 64, 0.5, dtype=dtype)
+    gx, gy = np.meshgrid(g, g)
+    rng = np.random.default_rng(5)
+    x = np.concatenate([gx.ravel(), rng.uniform(0, 64, 20000).astype(dtype)])
+    y = np.concatenate([gy.ravel(), rng.uniform(0, 64, 20000).astype(dtype)])
+    c = dict(x=x, y=y, po=po, ro=ro, vx=v[:, 0].copy(), vy=v[:, 1].copy(), ext=ext, scale=scale,
+             depth=depth)
+    want = run_host(oracle_lib, c, max_size)
+    assert_same(run_gpu(c, max_size), want, "lattice")
+    assert_same(run_gpu(c, max_size, use_grid_hint=False), want, "lattice (no hint)")
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

@@ -38,8 +38,10 @@ def run_host(lib, c, max_size):
     return dict(tree=tree, bbox=bb, pairs=pairs, hits=hits)
 
 
-def run_gpu(c, max_size):
-    """Full path through the product's Python API (-> C ABI -> CUDA kernels)."""
+def run_gpu(c, max_size, use_grid_hint=True):
+    """Full path through the product's Python API (-> C ABI -> CUDA kernels).
+    use_grid_hint=False drops the cell-geometry hint so that every quadrant goes through the
+    per-point refinement (the two must give identical rows)."""
     import torch
 
     import cuspatial_b200 as cs
@@ -58,6 +60,8 @@ def run_gpu(c, max_size):
     if c["depth"] >= 1:
         pairs = cs.join_quadtree_and_bounding_boxes(tree, bb, ext[0], ext[1], ext[2], ext[3],
                                                     c["scale"], c["depth"])
+        if not use_grid_hint:
+            tree._grid = None
         hits = cs.quadtree_point_in_polygon(pairs, tree, pidx, (x, y), polys)
         out["pairs"] = (pairs["bbox_offset"].cpu().numpy(), pairs["quad_offset"].cpu().numpy())
         out["hits"] = (hits["polygon_index"].cpu().numpy(), hits["point_index"].cpu().numpy())
