@@ -201,7 +201,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 1)):
         out = step()
     n_nodes, n_pairs, n_hits = len(out[1]), len(out[2]), len(out[3])
     lengths = out[1]["length"].to(torch.int64)[out[2]["quad_offset"].to(torch.int64)]

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcuspatial_b200.so")
+LIB_PATH = os.environ.get("BSJ_LIBRARY_PATH") or os.path.join(_HERE, "libcuspatial_b200.so")
 
 BSJ_SUCCESS, BSJ_INVALID_ARGUMENT, BSJ_CUDA_ERROR, BSJ_OUT_OF_MEMORY = 0, 1, 2, 3
 

@@ -34,30 +34,55 @@ struct fp;
 template <>
 struct fp<float> {
   static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
   static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
   static __device__ __forceinline__ u32 to_u32(float v) { return __float2uint_rz(v); }
+  static __device__ __forceinline__ float trunc_(float v) { return truncf(v); }
+  // |a*inv - a/s| < 2^-22 * 65536 = 2^-6 for quotients below 2^16
+  static __host__ __device__ constexpr float guard() { return 0.03125f; }
 };
 template <>
 struct fp<double> {
   static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
   static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
   static __device__ __forceinline__ u32 to_u32(double v) { return __double2uint_rz(v); }
+  static __device__ __forceinline__ double trunc_(double v) { return trunc(v); }
+  // |a*inv - a/s| < 2^-51 * 65536 = 2^-35 for quotients below 2^16
+  static __host__ __device__ constexpr double guard() { return 9.313225746154785e-10; }  // 2^-30
 };
+
+// uint16 cell index == static_cast<uint16_t>(a / scale) of the reference (phase_1.cuh:83-84), bit
+// for bit.  The IEEE quotient is only needed when it could land on the other side of an integer
+// than the cheap product a * (1/scale): both are within `guard` of the exact quotient, so when the
+// product's fractional part is farther than `guard` from 0 and 1 (and the quotient is in range)
+// the truncations agree.  Otherwise (probability ~2^-29 for fp64, ~6 % for fp32; NaN; huge
+// values) the true division is evaluated.
+template <typename T>
+__device__ __forceinline__ u32 cell_index(T a, T scale, T inv_scale)
+{
+  T const q = fp<T>::mul(a, inv_scale);
+  T const t = fp<T>::trunc_(q);
+  T const f = q - t;
+  if (q >= (T)0 && q < (T)65536 && f > fp<T>::guard() && f < (T)1 - fp<T>::guard())
+    return (u32)(int)t;
+  return fp<T>::to_u32(fp<T>::div(a, scale)) & 0xFFFFu;
+}
 
 // phase_1.cuh:78-85.  static_cast<uint16_t>(T) compiles to cvt.rzi.u32 (saturating, NaN -> 0)
 // followed by & 0xFFFF, restated explicitly.  IEEE division (the reference builds with the default
 // -prec-div=true), no reciprocal multiply.
 template <typename T>
 __device__ __forceinline__ u32 point_key(T x, T y, T min_x, T min_y, T max_x, T max_y, T scale,
-                                         u32 oob_key, u32& flags)
+                                         T inv_scale, u32 oob_key, u32& flags)
 {
   if (x < min_x || x > max_x || y < min_y || y > max_y) {
     flags |= 1u;
     return oob_key;
   }
   if (x != x || y != y) flags |= 2u;
-  u32 const ix = fp<T>::to_u32(fp<T>::div(fp<T>::sub(x, min_x), scale)) & 0xFFFFu;
-  u32 const iy = fp<T>::to_u32(fp<T>::div(fp<T>::sub(y, min_y), scale)) & 0xFFFFu;
+  u32 const ix = cell_index<T>(fp<T>::sub(x, min_x), scale, inv_scale);
+  u32 const iy = cell_index<T>(fp<T>::sub(y, min_y), scale, inv_scale);
   return (dilate16(iy) << 1) | dilate16(ix);
 }
 
@@ -73,6 +98,7 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
                    u32* __restrict__ hist, u32* __restrict__ point_flags)
 {
   u32 flags = 0;  // bit 0: a point outside the box, bit 1: a NaN coordinate
+  T const inv_scale = (T)1 / scale;
   constexpr int V = 16 / sizeof(T);  // points per 128-bit load
   __shared__ u32 s_hist[kMaxPasses * kRadixDigits];
   for (int i = threadIdx.x; i < kMaxPasses * kRadixDigits; i += blockDim.x) s_hist[i] = 0;
@@ -97,7 +123,7 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
       u32 ks[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        ks[j] = point_key<T>(xs[j], ys[j], min_x, min_y, max_x, max_y, scale, oob_key, flags);
+        ks[j] = point_key<T>(xs[j], ys[j], min_x, min_y, max_x, max_y, scale, inv_scale, oob_key, flags);
         tally(ks[j]);
       }
       if constexpr (V == 2)
@@ -107,13 +133,13 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
     }
     // tail
     for (u64 i = nvec * V + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, oob_key, flags);
+      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, inv_scale, oob_key, flags);
       tally(k);
       keys[i] = k;
     }
   } else {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, oob_key, flags);
+      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, inv_scale, oob_key, flags);
       tally(k);
       keys[i] = k;
     }
@@ -239,9 +265,22 @@ expand_level_kernel(const u32* __restrict__ keys, int L, int max_depth, u32 max_
       if (cnt > max_size) {
         b[0] = start;
         b[4] = start + cnt;
-#pragma unroll
-        for (int c = 1; c < 4; ++c)
-          b[c] = lower_bound_key(keys, b[c - 1], b[4], (((u64)k << 2) + c) << shift);
+        // three independent binary searches advanced in lock step: three loads in flight per
+        // round instead of three dependent searches one after the other
+        u32 lo1 = start, lo2 = start, lo3 = start, hi1 = b[4], hi2 = b[4], hi3 = b[4];
+        u64 const t1 = (((u64)k << 2) + 1) << shift, t2 = (((u64)k << 2) + 2) << shift,
+                  t3 = (((u64)k << 2) + 3) << shift;
+        while (lo1 < hi1 || lo2 < hi2 || lo3 < hi3) {
+          u32 const m1 = lo1 + ((hi1 - lo1) >> 1), m2 = lo2 + ((hi2 - lo2) >> 1),
+                    m3 = lo3 + ((hi3 - lo3) >> 1);
+          u64 const k1 = lo1 < hi1 ? (u64)__ldg(keys + m1) : 0;
+          u64 const k2 = lo2 < hi2 ? (u64)__ldg(keys + m2) : 0;
+          u64 const k3 = lo3 < hi3 ? (u64)__ldg(keys + m3) : 0;
+          if (lo1 < hi1) { if (k1 < t1) lo1 = m1 + 1; else hi1 = m1; }
+          if (lo2 < hi2) { if (k2 < t2) lo2 = m2 + 1; else hi2 = m2; }
+          if (lo3 < hi3) { if (k3 < t3) lo3 = m3 + 1; else hi3 = m3; }
+        }
+        b[1] = lo1; b[2] = lo2; b[3] = lo3;
 #pragma unroll
         for (int c = 0; c < 4; ++c) nchild += (b[c + 1] > b[c]);
       }

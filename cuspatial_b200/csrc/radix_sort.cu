@@ -11,7 +11,9 @@ constexpr int kWarps = kSortBlock / 32;
 struct sort_smem {
   u32 keys[kSortTile];
   u32 vals[kSortTile];
-  u32 whist[kWarps * kRadixDigits];  // per-warp digit counters -> per-warp exclusive offsets
+  // per-warp, per-digit {x: running count -> exclusive warp offset, y: match mask of the
+  // current round}
+  uint2 whist[kWarps * kRadixDigits];
   u32 bin_start[kRadixDigits];       // exclusive scan of the tile's digit totals
   u32 gbase[kRadixDigits];           // global destination of (digit, slot j): gbase[d] + j
   u32 warp_sums[kWarps];
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(kMaxPasses * kRadixDigits) scan_hist_kernel(u3
 // one onesweep pass: rank -> look-back -> scatter
 // ---------------------------------------------------------------------------------------------
 template <bool IOTA>
-__global__ void __launch_bounds__(kSortBlock, 2)
+__global__ void __launch_bounds__(kSortBlock, BSJ_SORT_MINBLOCKS)
 onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in,
                 u32* __restrict__ keys_out, u32* __restrict__ vals_out, u32 n, int shift,
                 const u32* __restrict__ digit_offsets, u64* __restrict__ lookback,
@@ -73,7 +75,7 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
   int const warp = tid >> 5;
 
   if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < kWarps * kRadixDigits; i += kSortBlock) sm.whist[i] = 0;
+  for (int i = tid; i < kWarps * kRadixDigits; i += kSortBlock) sm.whist[i] = make_uint2(0u, 0u);
   __syncthreads();
   u32 const tile      = sm.tile;
   u32 const tile_base = tile * (u32)kSortTile;
@@ -88,30 +90,25 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
     key[i]        = idx < n ? ld_stream(keys_in + idx) : 0xFFFFFFFFu;
   }
 
-  // ---- per-warp stable ranking.  Peer masks come from 8 ballots (one per digit bit) instead of
-  // match.any: MATCH.ANY was the top stall of this kernel on B200 (ncu, profiles/), the ballots
-  // are independent of each other and of the counter chain.
-  u32* const wh = sm.whist + warp * kRadixDigits;
-  u32 const lt  = lanemask_lt();
+  // ---- per-warp stable ranking.  Lanes holding the same digit find each other through a
+  // shared-memory match word (atomicOr of the lane bit), which took the place of match.any (the
+  // top stall on B200) and of an 8-ballot vote (3x the instructions): the word sits next to the
+  // digit's running count, so ONE 64-bit load gives a lane both its peer mask and the count of
+  // earlier items; the lowest peer then bumps the count and clears the mask for the next round.
+  uint2* const wh = sm.whist + warp * kRadixDigits;
+  u32 const lt    = lanemask_lt();
+  u32 const mybit = 1u << lane;
   unsigned short rank[kSortIPT];
 #pragma unroll
   for (int i = 0; i < kSortIPT; ++i) {
     u32 const d = (key[i] >> shift) & 0xFFu;
-    u32 peers   = 0xffffffffu;
-#pragma unroll
-    for (int b = 0; b < kRadixBits; ++b) {
-      bool const bit = (d >> b) & 1u;
-      u32 const m    = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? m : ~m;
-    }
-    int const lead = __ffs(peers) - 1;
-    u32 prev       = 0;
-    if (lane == lead) {
-      prev  = wh[d];
-      wh[d] = prev + __popc(peers);
-    }
-    prev    = __shfl_sync(0xffffffffu, prev, lead);
-    rank[i] = (unsigned short)(prev + __popc(peers & lt));
+    atomicOr(&wh[d].y, mybit);
+    __syncwarp();
+    uint2 const cm = wh[d];  // {count before this round, peers of this round}
+    __syncwarp();
+    u32 const below = cm.y & lt;
+    if (below == 0) wh[d] = make_uint2(cm.x + __popc(cm.y), 0u);
+    rank[i] = (unsigned short)(cm.x + __popc(below));
     __syncwarp();
   }
   __syncthreads();
@@ -122,8 +119,8 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
     u32 sum = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
-      u32 const c                    = sm.whist[w * kRadixDigits + tid];
-      sm.whist[w * kRadixDigits + tid] = sum;
+      u32 const c                        = sm.whist[w * kRadixDigits + tid].x;
+      sm.whist[w * kRadixDigits + tid].x = sum;
       sum += c;
     }
     total = sum;
@@ -171,7 +168,7 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
 #pragma unroll
   for (int i = 0; i < kSortIPT; ++i) {
     u32 const d   = (key[i] >> shift) & 0xFFu;
-    u32 const pos = sm.bin_start[d] + wh[d] + rank[i];
+    u32 const pos = sm.bin_start[d] + wh[d].x + rank[i];
     sm.keys[pos]  = key[i];
     key[i]        = pos;  // reuse the register for the slot
   }

@@ -16,8 +16,17 @@ constexpr int kRadixBits   = 8;
 constexpr int kRadixDigits = 1 << kRadixBits;
 constexpr int kMaxPasses   = 4;
 
-constexpr int kSortBlock = 512;  // threads per CTA
-constexpr int kSortIPT   = 16;   // keys per thread
+#ifndef BSJ_SORT_BLOCK
+#define BSJ_SORT_BLOCK 512
+#endif
+#ifndef BSJ_SORT_IPT
+#define BSJ_SORT_IPT 16
+#endif
+#ifndef BSJ_SORT_MINBLOCKS
+#define BSJ_SORT_MINBLOCKS 2
+#endif
+constexpr int kSortBlock = BSJ_SORT_BLOCK;  // threads per CTA
+constexpr int kSortIPT   = BSJ_SORT_IPT;    // keys per thread
 constexpr int kSortTile  = kSortBlock * kSortIPT;
 
 // Temporary storage for one sort of n elements.
