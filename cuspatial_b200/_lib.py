@@ -44,7 +44,7 @@ class bsj_pairs(C.Structure):
 EXPORTED_SYMBOLS = [
     "bsj_quadtree_on_points", "bsj_join_quadtree_and_bounding_boxes",
     "bsj_quadtree_point_in_polygon", "bsj_quadtree_point_in_polygon_ex", "bsj_point_in_polygon", "bsj_polygon_bounding_boxes",
-    "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
+    "bsj_point_keys_histogram", "bsj_partition_points", "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
     "bsj_kernel_launch_count", "bsj_set_profiling", "bsj_get_profile",
 ]
 
@@ -80,6 +80,10 @@ def lib():
     L.bsj_point_in_polygon.argtypes = [vp, vp, C.c_int, u64, vp, u64, vp, u64, vp, vp, u64, vp, vp]
     L.bsj_polygon_bounding_boxes.argtypes = [vp, u64, vp, u64, vp, vp, C.c_int, u64, dbl, vp,
                                              vp, vp, vp, vp]
+    L.bsj_point_keys_histogram.argtypes = [vp, vp, C.c_int, u64, dbl, dbl, dbl, dbl, dbl, C.c_int8,
+                                           C.c_int, vp, vp, u64, vp]
+    L.bsj_partition_points.argtypes = [vp, vp, vp, C.c_int, u64, C.c_uint32, vp, C.c_int, vp, vp,
+                                       vp, vp, vp]
     L.bsj_free.argtypes = [vp, vp]
     L.bsj_last_error.restype = C.c_char_p
     L.bsj_version.restype = C.c_char_p

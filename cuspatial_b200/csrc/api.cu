@@ -40,6 +40,15 @@ void polygon_bounding_boxes_impl(const u32* poly_offsets, u64 n_poly_offsets,
                                  const void* vy, int dtype, u64 n_verts, double r, cudaStream_t s,
                                  void* x0, void* y0, void* x1, void* y1);
 
+void point_keys_histogram_impl(const void* x, const void* y, int dtype, u64 n, double x_min,
+                               double x_max, double y_min, double y_max, double scale,
+                               int max_depth, int hist_shift, u32* keys, u32* bins, u64 n_bins,
+                               cudaStream_t s);
+void partition_points_impl(const u32* keys, const void* x, const void* y, int dtype, u64 n,
+                           u32 gid_base, const u32* h_splitters, int n_ranks,
+                           const u32* d_bucket_base, void* out_x, void* out_y, u32* out_gid,
+                           cudaStream_t s);
+
 namespace {
 thread_local std::string t_err;
 thread_local std::vector<std::pair<std::string, float>> t_profile;
@@ -266,6 +275,31 @@ int bsj_polygon_bounding_boxes(const uint32_t* poly_offsets, uint64_t n_poly_off
                                 poly_points_x, poly_points_y, dtype, n_poly_points,
                                 expansion_radius, (cudaStream_t)stream, out_x_min, out_y_min,
                                 out_x_max, out_y_max);
+  });
+}
+
+int bsj_point_keys_histogram(const void* x, const void* y, int dtype, uint64_t n, double x_min,
+                             double x_max, double y_min, double y_max, double scale,
+                             int8_t max_depth, int hist_shift, uint32_t* keys, uint32_t* bins,
+                             uint64_t n_bins, bsj_stream_t stream)
+{
+  return guarded([&] {
+    check_dtype(dtype);
+    BSJ_EXPECTS(n == 0 || (x && y && keys), "x and y columns must have the same length");
+    point_keys_histogram_impl(x, y, dtype, n, x_min, x_max, y_min, y_max, scale, max_depth,
+                              hist_shift, keys, bins, n_bins, (cudaStream_t)stream);
+  });
+}
+
+int bsj_partition_points(const uint32_t* keys, const void* x, const void* y, int dtype, uint64_t n,
+                         uint32_t gid_base, const uint32_t* host_splitters, int n_ranks,
+                         const uint32_t* bucket_base, void* out_x, void* out_y, uint32_t* out_gid,
+                         bsj_stream_t stream)
+{
+  return guarded([&] {
+    check_dtype(dtype);
+    partition_points_impl(keys, x, y, dtype, n, gid_base, host_splitters, n_ranks, bucket_base,
+                          out_x, out_y, out_gid, (cudaStream_t)stream);
   });
 }
 

@@ -1,0 +1,198 @@
+// partition.cu -- Morton-range sharding of a point set across GPUs (new work: the reference is
+// single-GPU).
+//
+// Each rank (1) computes the reference's Morton key of every local point
+// (detail/index/construction/phase_1.cuh:78-85, same arithmetic as quadtree.cu) together with a
+// histogram of the keys' leading bits, (2) after the ranks agreed on key-range splitters (an
+// all-reduce of the histograms, done by the host layer over NCCL), STABLY partitions its points by
+// destination rank: one pass, tile by tile -- per-destination ballots give the in-tile rank, a
+// decoupled look-back over tile descriptors gives the tile's offset inside each destination
+// bucket -- writing x, y and the global point id into contiguous per-destination send buffers.
+// Stability (ascending global id inside a bucket) is what keeps the tie order of the reference's
+// stable sort after the exchange.
+#include "common.cuh"
+
+namespace bsj {
+
+// implemented in quadtree.cu
+template <typename T>
+void launch_point_keys(const void* x, const void* y, u64 n, double x_min, double x_max,
+                       double y_min, double y_max, double scale, int max_depth, u32* keys,
+                       cudaStream_t s);
+
+namespace {
+
+constexpr int kMaxRanks  = 32;
+constexpr int kPartBlock = 256;
+constexpr int kPartIPT   = 8;
+constexpr int kPartTile  = kPartBlock * kPartIPT;
+
+struct splitters_t {
+  u32 key[kMaxRanks];  // rank r owns keys in [key[r-1], key[r]); key[R-1] unused
+  int n_ranks;
+};
+
+__global__ void __launch_bounds__(256)
+key_histogram_kernel(const u32* __restrict__ keys, u64 n, int shift, u32* __restrict__ bins)
+{
+  u64 const stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    // warp-aggregate equal neighbours (spatially coherent inputs) before the global reduction
+    u32 const b     = __ldcs(keys + i) >> shift;
+    u32 const peers = __match_any_sync(__activemask(), b);
+    if ((peers & lanemask_lt()) == 0) atomicAdd(&bins[b], (u32)__popc(peers));
+  }
+}
+
+__device__ __forceinline__ int dest_of(u32 key, const splitters_t& sp)
+{
+  int d = 0;
+  for (int r = 0; r + 1 < sp.n_ranks; ++r) d += key >= sp.key[r];
+  return d;
+}
+
+// descriptors: [tile][kMaxRanks] u64 {tag, value}
+template <typename T>
+__global__ void __launch_bounds__(kPartBlock)
+partition_kernel(const u32* __restrict__ keys, const T* __restrict__ x, const T* __restrict__ y,
+                 u32 n, u32 gid_base, splitters_t sp, const u32* __restrict__ bucket_base,
+                 T* __restrict__ out_x, T* __restrict__ out_y, u32* __restrict__ out_gid,
+                 u64* __restrict__ desc, u32* __restrict__ ticket)
+{
+  __shared__ u32 s_tile;
+  __shared__ u32 s_warp_cnt[kPartBlock / 32][kMaxRanks];
+  __shared__ u32 s_warp_off[kPartBlock / 32][kMaxRanks];
+  __shared__ u32 s_base[kMaxRanks];
+  int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int const R   = sp.n_ranks;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  u32 const tile = s_tile;
+  // blocked-by-warp layout keeps the original order: warp w owns items [w*IPT*32, (w+1)*IPT*32)
+  u32 const warp_base = tile * kPartTile + warp * (kPartIPT * 32);
+  u32 const lt        = lanemask_lt();
+
+  int dest[kPartIPT];
+  u32 rank[kPartIPT];
+  u32 cnt = 0;  // lane r < R accumulates this warp's count for destination r
+#pragma unroll
+  for (int i = 0; i < kPartIPT; ++i) {
+    u32 const idx = warp_base + i * 32 + lane;
+    dest[i]       = idx < n ? dest_of(__ldcs(keys + idx), sp) : -1;
+    rank[i]       = 0;
+    for (int r = 0; r < R; ++r) {
+      u32 const m = __ballot_sync(0xffffffffu, dest[i] == r);
+      u32 const before = __shfl_sync(0xffffffffu, cnt, r);
+      if (dest[i] == r) rank[i] = before + __popc(m & lt);
+      if (lane == r) cnt += __popc(m);
+    }
+  }
+  if (lane < R) s_warp_cnt[warp][lane] = cnt;
+  __syncthreads();
+  if (tid < R) {
+    u32 sum = 0;
+    for (int w = 0; w < kPartBlock / 32; ++w) {
+      s_warp_off[w][tid] = sum;
+      sum += s_warp_cnt[w][tid];
+    }
+  }
+  // per-destination chained scan over tiles (descriptor column = destination)
+  if (tid < R) {
+    u32 total = 0;
+    for (int w = 0; w < kPartBlock / 32; ++w) total += s_warp_cnt[w][tid];
+    u64* const col = desc + tid;
+    u32 excl       = 0;
+    if (tile == 0) {
+      st_relaxed_u64(col, lb_pack(3u, total));
+    } else {
+      st_relaxed_u64(col + (u64)tile * kMaxRanks, lb_pack(2u, total));
+      i64 t = (i64)tile - 1;
+      while (true) {
+        u64 const v    = ld_relaxed_u64(col + (u64)t * kMaxRanks);
+        u32 const flag = (u32)(v >> 32);
+        if (flag == 3u) {
+          excl += (u32)v;
+          break;
+        }
+        if (flag == 2u) {
+          excl += (u32)v;
+          --t;
+        }
+      }
+      st_relaxed_u64(col + (u64)tile * kMaxRanks, lb_pack(3u, excl + total));
+    }
+    s_base[tid] = bucket_base[tid] + excl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kPartIPT; ++i) {
+    if (dest[i] >= 0) {
+      u32 const idx = warp_base + i * 32 + lane;
+      u32 const o   = s_base[dest[i]] + s_warp_off[warp][dest[i]] + rank[i];
+      out_x[o]      = __ldcs(x + idx);
+      out_y[o]      = __ldcs(y + idx);
+      out_gid[o]    = gid_base + idx;
+    }
+  }
+}
+
+template <typename T>
+void partition_t(const u32* keys, const void* x, const void* y, u64 n, u32 gid_base,
+                 const u32* h_splitters, int n_ranks, const u32* d_bucket_base, void* out_x,
+                 void* out_y, u32* out_gid, cudaStream_t s)
+{
+  splitters_t sp{};
+  sp.n_ranks = n_ranks;
+  for (int r = 0; r + 1 < n_ranks; ++r) sp.key[r] = h_splitters[r];
+  u32 const tiles = (u32)div_up(n, kPartTile);
+  dev_buf<u64> desc((size_t)tiles * kMaxRanks, s);
+  dev_buf<u32> ticket(1, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(desc.get(), 0, desc.size() * sizeof(u64), s));
+  BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
+  partition_kernel<T><<<tiles, kPartBlock, 0, s>>>(keys, (const T*)x, (const T*)y, (u32)n,
+                                                   gid_base, sp, d_bucket_base, (T*)out_x,
+                                                   (T*)out_y, out_gid, desc.get(), ticket.get());
+  BSJ_CHECK_LAUNCH();
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+}
+
+}  // namespace
+
+void point_keys_histogram_impl(const void* x, const void* y, int dtype, u64 n, double x_min,
+                               double x_max, double y_min, double y_max, double scale,
+                               int max_depth, int hist_shift, u32* keys, u32* bins, u64 n_bins,
+                               cudaStream_t s)
+{
+  if (n == 0) return;
+  int const d = std::max(0, std::min(15, max_depth));
+  if (dtype == BSJ_FLOAT32)
+    launch_point_keys<float>(x, y, n, x_min, x_max, y_min, y_max, scale, d, keys, s);
+  else
+    launch_point_keys<double>(x, y, n, x_min, x_max, y_min, y_max, scale, d, keys, s);
+  if (bins) {
+    BSJ_EXPECTS(hist_shift >= 0 && hist_shift < 32 && (0xFFFFFFFFull >> hist_shift) < n_bins,
+                "histogram does not cover the key range");
+    int const grid = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n, 256));
+    key_histogram_kernel<<<grid, 256, 0, s>>>(keys, n, hist_shift, bins);
+    BSJ_CHECK_LAUNCH();
+  }
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+}
+
+void partition_points_impl(const u32* keys, const void* x, const void* y, int dtype, u64 n,
+                           u32 gid_base, const u32* h_splitters, int n_ranks,
+                           const u32* d_bucket_base, void* out_x, void* out_y, u32* out_gid,
+                           cudaStream_t s)
+{
+  BSJ_EXPECTS(n_ranks >= 1 && n_ranks <= kMaxRanks, "unsupported number of ranks");
+  BSJ_EXPECTS(n < 0xFFFFFFFFull, "number of points must fit uint32 indices");
+  if (n == 0) return;
+  if (dtype == BSJ_FLOAT32)
+    partition_t<float>(keys, x, y, n, gid_base, h_splitters, n_ranks, d_bucket_base, out_x, out_y,
+                       out_gid, s);
+  else
+    partition_t<double>(keys, x, y, n, gid_base, h_splitters, n_ranks, d_bucket_base, out_x,
+                        out_y, out_gid, s);
+}
+
+}  // namespace bsj

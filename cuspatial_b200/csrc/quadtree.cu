@@ -362,6 +362,23 @@ void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_m
 
 }  // namespace
 
+// Keys only (no histograms): used by the multi-GPU partitioner (partition.cu).
+template <typename T>
+void launch_point_keys(const void* x, const void* y, u64 n, double x_min, double x_max,
+                       double y_min, double y_max, double scale, int max_depth, u32* keys,
+                       cudaStream_t s)
+{
+  dev_buf<u32> flags(1, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(flags.get(), 0, sizeof(u32), s));
+  bsj_grid g{};
+  launch_encode<T>(x, y, n, x_min, x_max, y_min, y_max, scale, max_depth, /*passes=*/0, keys,
+                   nullptr, flags.get(), &g, s);
+}
+template void launch_point_keys<float>(const void*, const void*, u64, double, double, double,
+                                       double, double, int, u32*, cudaStream_t);
+template void launch_point_keys<double>(const void*, const void*, u64, double, double, double,
+                                        double, double, int, u32*, cudaStream_t);
+
 // Host orchestration.  One stream synchronisation at the end (to learn the node count).
 void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, double x_min,
                              double x_max, double y_min, double y_max, double scale,

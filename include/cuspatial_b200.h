@@ -191,6 +191,27 @@ int bsj_polygon_bounding_boxes(const uint32_t* poly_offsets, uint64_t n_poly_off
                                bsj_stream_t stream, void* out_x_min, void* out_y_min,
                                void* out_x_max, void* out_y_max);
 
+/*
+ * Multi-GPU sharding helpers (no reference analogue: the reference is single-GPU).  Points are
+ * sharded across ranks by contiguous Morton-key range; the host layer (one process per GPU,
+ * NCCL) all-reduces the histograms, agrees on splitters and exchanges the partitioned buffers.
+ *
+ * bsj_point_keys_histogram: keys[i] = the reference's Morton key of point i
+ *   (cpp/include/cuspatial/detail/index/construction/phase_1.cuh:78-85) and, if bins != NULL,
+ *   bins[keys[i] >> hist_shift] += 1 (bins are accumulated into, n_bins > max key >> hist_shift).
+ * bsj_partition_points: stable partition by destination rank, destination of key k =
+ *   #{r : k >= host_splitters[r]}, r < n_ranks-1.  bucket_base[r] (device) is the first slot of
+ *   destination r in the output buffers; out_gid[o] = gid_base + original index.
+ */
+int bsj_point_keys_histogram(const void* x, const void* y, int dtype, uint64_t n, double x_min,
+                             double x_max, double y_min, double y_max, double scale,
+                             int8_t max_depth, int hist_shift, uint32_t* keys, uint32_t* bins,
+                             uint64_t n_bins, bsj_stream_t stream);
+int bsj_partition_points(const uint32_t* keys, const void* x, const void* y, int dtype, uint64_t n,
+                         uint32_t gid_base, const uint32_t* host_splitters, int n_ranks,
+                         const uint32_t* bucket_base, void* out_x, void* out_y, uint32_t* out_gid,
+                         bsj_stream_t stream);
+
 /* Release a buffer the library allocated with its default allocator (mr == NULL). */
 void bsj_free(void* ptr, bsj_stream_t stream);
 void bsj_free_quadtree(bsj_quadtree* tree, bsj_stream_t stream);

@@ -1,0 +1,147 @@
+"""CPU test (gloo, world_size 2) of the multi-GPU host logic: splitters, stable exchange, global
+index fix-up and merge.  The three device steps are replaced by host callables (numpy + the CPU
+oracle); the merged result must equal a single-process oracle run on all points."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _dilate(v):
+    v = v.astype(np.uint32) & 0xFFFF
+    v = (v | (v << 8)) & 0x00FF00FF
+    v = (v | (v << 4)) & 0x0F0F0F0F
+    v = (v | (v << 2)) & 0x33333333
+    v = (v | (v << 1)) & 0x55555555
+    return v
+
+
+def _host_steps(oracle):
+    import torch
+
+    def keys_hist(x, y, bbox, scale, max_depth, shift, n_bins):
+        xn, yn = x.numpy(), y.numpy()
+        T = xn.dtype.type
+        mnx, mxx, mny, mxy = (T(b) for b in bbox)
+        sc = max(T(scale), max(mxx - mnx, mxy - mny) / T((1 << max_depth) + 2))
+        oob = (xn < mnx) | (xn > mxx) | (yn < mny) | (yn > mxy)
+        ix = ((xn - mnx) / sc).astype(np.uint32) & 0xFFFF
+        iy = ((yn - mny) / sc).astype(np.uint32) & 0xFFFF
+        k = (_dilate(iy) << 1) | _dilate(ix)
+        k[oob] = (1 << (2 * max_depth)) - 1
+        hist = np.bincount(k >> shift, minlength=n_bins).astype(np.int64)
+        return torch.from_numpy(k.astype(np.int32)), torch.from_numpy(hist)
+
+    def partition(keys, x, y, gid_base, splitters, counts):
+        k = keys.numpy().view(np.uint32).astype(np.int64)
+        dest = np.searchsorted(splitters.astype(np.int64), k, side="right")
+        order = np.argsort(dest, kind="stable")
+        gid = (gid_base + np.arange(len(k))).astype(np.int32)
+        assert np.bincount(dest, minlength=len(counts)).tolist() == list(counts)
+        return (torch.from_numpy(x.numpy()[order]), torch.from_numpy(y.numpy()[order]),
+                torch.from_numpy(gid[order]))
+
+    def local_join(x, y, polys, bbox, scale, max_depth, max_size):
+        po, ro, vx, vy = (p.numpy() for p in polys)
+        po, ro = po.view(np.uint32), ro.view(np.uint32)
+        xn, yn = x.numpy(), y.numpy()
+        t = oracle.quadtree_on_points(xn, yn, bbox[0], bbox[1], bbox[2], bbox[3], scale,
+                                      max_depth, max_size)
+        bb = oracle.polygon_bounding_boxes(po, ro, vx, vy)
+        pairs = oracle.join_quadtree_and_bounding_boxes(t, *bb, bbox[0], bbox[2], scale, max_depth)
+        hp, hq = oracle.quadtree_point_in_polygon(pairs[0], pairs[1], t, t["point_indices"], xn,
+                                                  yn, po, ro, vx, vy)
+        return (torch.from_numpy(t["point_indices"].view(np.int32).copy()),
+                torch.from_numpy(hp.view(np.int32).copy()),
+                torch.from_numpy(hq.view(np.int32).copy()))
+
+    return {"keys_hist": keys_hist, "partition": partition, "local_join": local_join}
+
+
+def _worker(rank, world, port, kind, dtype_name, q):
+    import torch
+    import torch.distributed as dist
+
+    from cuspatial_b200 import multi_gpu as mg
+    from oracle import hostlib
+    from util import make_case
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dtype = np.dtype(dtype_name).type
+        c = make_case(30000, 25, 10, kind, dtype, seed=77, oob=20, dups=200, median_vertices=24)
+        n = len(c["x"])
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        x, y = torch.from_numpy(c["x"][lo:hi].copy()), torch.from_numpy(c["y"][lo:hi].copy())
+        polys = tuple(torch.from_numpy(a.view(np.int32).copy() if a.dtype == np.uint32 else a)
+                      for a in (c["po"], c["ro"], c["vx"], c["vy"]))
+        if rank != 0:  # only rank 0's polygon content may be used
+            polys = tuple(torch.zeros_like(p) for p in polys)
+        ext = c["ext"]
+        out = mg.sharded_quadtree_point_in_polygon(
+            (x, y), polys, ext[0], ext[1], ext[2], ext[3], c["scale"], c["depth"], 32,
+            gather_pairs=True, gather_point_indices=True, steps=_host_steps(hostlib.oracle()))
+        q.put((rank, out["polygon_index"].numpy(), out["point_index"].numpy(),
+               out["point_indices"].numpy(), out["counts"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("kind,dtype_name", [("u", "float64"), ("c", "float64"), ("c", "float32")])
+def test_sharded_join_world2_equals_single_process_oracle(oracle_lib, kind, dtype_name):
+    import torch.multiprocessing as mp
+
+    from util import make_case, run_host
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, dtype_name, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    dtype = np.dtype(dtype_name).type
+    c = make_case(30000, 25, 10, kind, dtype, seed=77, oob=20, dups=200, median_vertices=24)
+    ref = run_host(oracle_lib, c, 32)
+    want = np.stack([ref["hits"][0].astype(np.int64), ref["hits"][1].astype(np.int64)], 1)
+    want = want[np.lexsort((want[:, 1], want[:, 0]))]
+    for rank, hp, hq, pidx, counts in results:
+        got = np.stack([hp.view(np.uint32).astype(np.int64), hq.view(np.uint32).astype(np.int64)], 1)
+        got = got[np.lexsort((got[:, 1], got[:, 0]))]
+        np.testing.assert_array_equal(got, want)               # same pair set on every rank
+        np.testing.assert_array_equal(pidx.view(np.uint32), ref["tree"]["point_indices"])
+        assert sum(counts) == len(c["x"]) and min(counts) > 0.3 * len(c["x"]) / world
+
+
+def test_choose_splitters_balances_and_stays_on_bin_boundaries():
+    from cuspatial_b200.multi_gpu import choose_splitters
+
+    rng = np.random.default_rng(0)
+    hist = rng.integers(0, 1000, size=1 << 16)
+    for R in (2, 4, 8):
+        sp = choose_splitters(hist, R, 14).astype(np.int64)
+        assert len(sp) == R - 1 and np.all(np.diff(sp) >= 0) and np.all(sp % (1 << 14) == 0)
+        owner = np.searchsorted(sp >> 14, np.arange(1 << 16), side="right")
+        loads = np.bincount(owner, weights=hist, minlength=R)
+        assert loads.max() < 1.05 * hist.sum() / R
