@@ -208,6 +208,7 @@ def run_sharded(args, dist, dev, rank, world, x, y, polys, ext, scale):
                     "d2h_bytes_per_step": 0,
                     "note": "device-resident shards; see the N=1 line for the host-buffer e2e"},
             "gpu_launches": int(launches), "clocks": clocks,
+            "phase_ms_last_step": {k: round(v, 3) for k, v in mg.LAST_PROFILE.items()} or None,
         }))
     dist.destroy_process_group()
 
@@ -247,9 +248,8 @@ def main():
     n = args.points
     (po, ro, vx, vy), ext, scale = make_polygons()
     polys = tuple(torch.as_tensor(a, device=dev) for a in (po, ro, vx, vy))
-    if dist is not None:  # polygon table replicated from rank 0 over NCCL
-        for t in polys:
-            dist.broadcast(t, src=0)
+    # (for N > 1 the polygon table is replicated from rank 0 by an NCCL broadcast inside the
+    #  sharded join itself, every step)
     x, y = D.uniform_points_torch(n, ext, SEED + rank, torch.float64, dev)
     bb = cs.polygon_bounding_boxes(polys)
 

@@ -36,6 +36,15 @@ class bsj_quadtree(C.Structure):
     ]
 
 
+class bsj_pip_compact(C.Structure):
+    _fields_ = [
+        ("pair_offset", C.c_void_p), ("pair_length", C.c_void_p), ("pair_hits", C.c_void_p),
+        ("pair_class", C.c_void_p), ("pair_word_base", C.c_void_p), ("pair_row_base", C.c_void_p),
+        ("mask_words", C.c_void_p), ("n_pairs", C.c_uint64), ("n_words", C.c_uint64),
+        ("n_hits", C.c_uint64),
+    ]
+
+
 class bsj_pairs(C.Structure):
     _fields_ = [("first", C.c_void_p), ("second", C.c_void_p), ("size", C.c_uint64)]
 
@@ -43,7 +52,8 @@ class bsj_pairs(C.Structure):
 # every symbol include/cuspatial_b200.h declares
 EXPORTED_SYMBOLS = [
     "bsj_quadtree_on_points", "bsj_join_quadtree_and_bounding_boxes",
-    "bsj_quadtree_point_in_polygon", "bsj_quadtree_point_in_polygon_ex", "bsj_point_in_polygon", "bsj_polygon_bounding_boxes",
+    "bsj_quadtree_point_in_polygon", "bsj_quadtree_point_in_polygon_ex", "bsj_quadtree_point_in_polygon_compact",
+    "bsj_expand_pip_compact", "bsj_point_in_polygon", "bsj_polygon_bounding_boxes",
     "bsj_point_keys_histogram", "bsj_partition_points", "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
     "bsj_kernel_launch_count", "bsj_set_profiling", "bsj_get_profile",
 ]
@@ -77,6 +87,10 @@ def lib():
                                                    u64, C.POINTER(bsj_grid),
                                                    C.POINTER(bsj_allocator), vp,
                                                    C.POINTER(bsj_pairs)]
+    L.bsj_quadtree_point_in_polygon_compact.argtypes = [
+        vp, vp, u64, vp, vp, vp, vp, vp, u64, vp, vp, vp, C.c_int, u64, vp, u64, vp, u64, vp, vp,
+        u64, C.POINTER(bsj_grid), C.POINTER(bsj_allocator), vp, C.POINTER(bsj_pip_compact)]
+    L.bsj_expand_pip_compact.argtypes = [vp, C.POINTER(bsj_pip_compact), C.c_uint32, vp, vp, vp]
     L.bsj_point_in_polygon.argtypes = [vp, vp, C.c_int, u64, vp, u64, vp, u64, vp, vp, u64, vp, vp]
     L.bsj_polygon_bounding_boxes.argtypes = [vp, u64, vp, u64, vp, vp, C.c_int, u64, dbl, vp,
                                              vp, vp, vp, vp]

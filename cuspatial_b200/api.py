@@ -237,6 +237,69 @@ def quadtree_point_in_polygon(poly_quad_pairs, quadtree, point_indices, points, 
                   ("point_index", alloc.take(out.second, h, torch.uint32))])
 
 
+_COMPACT_FIELDS = (("pair_offset", torch.uint32, "n_pairs"), ("pair_length", torch.uint32, "n_pairs"),
+                   ("pair_hits", torch.uint32, "n_pairs"), ("pair_class", torch.uint8, "n_pairs"),
+                   ("pair_word_base", torch.int64, "n_pairs"),
+                   ("pair_row_base", torch.int64, "n_pairs"), ("mask_words", torch.uint32, "n_words"))
+
+
+def quadtree_point_in_polygon_compact(poly_quad_pairs, quadtree, point_indices, points, polygons):
+    """quadtree_point_in_polygon stopped before the rows are written: returns the compact result
+    (dict of device tensors + 'n_hits', see bsj_pip_compact) for `expand_pip_compact`.  Used by
+    the multi-GPU merge, which all-gathers this form instead of the expanded table."""
+    x, y = _split_points(points)
+    po, ro, vx, vy = _split_polygons(polygons)
+    po = _as_cuda(po, torch.uint32 if getattr(po, "dtype", None) != torch.int32 else None)
+    ro = _as_cuda(ro, torch.uint32 if getattr(ro, "dtype", None) != torch.int32 else None)
+    names = list(poly_quad_pairs.columns)
+    pp = _as_cuda(poly_quad_pairs[names[0]], torch.uint32)
+    pq = _as_cuda(poly_quad_pairs[names[1]], torch.uint32)
+    pi = _as_cuda(point_indices, torch.uint32)
+    tcols = _quadtree_columns(quadtree)
+    dev = x.device
+    with torch.cuda.device(dev):
+        alloc = _TorchAllocator(dev)
+        out = _lib.bsj_pip_compact()
+        grid = getattr(quadtree, "_grid", None)
+        rc = _lib.lib().bsj_quadtree_point_in_polygon_compact(
+            _ptr(pp), _ptr(pq), pp.shape[0], *[_ptr(t) for t in tcols], tcols[0].shape[0],
+            _ptr(pi), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], _ptr(po), po.shape[0],
+            _ptr(ro), ro.shape[0], _ptr(vx), _ptr(vy), vx.shape[0],
+            C.byref(grid) if grid is not None else None, C.byref(alloc.struct), _stream(dev),
+            C.byref(out))
+        _lib.check(rc)
+    res = {"pair_poly": pp, "n_hits": int(out.n_hits)}
+    for name, dt, cnt in _COMPACT_FIELDS:
+        n = int(getattr(out, cnt))
+        if name == "mask_words":
+            n = max(n, 1) if getattr(out, name) else 0
+        res[name] = alloc.take(getattr(out, name), n, dt)
+    return res
+
+
+def expand_pip_compact(compact, position_base, out_polygon_index, out_point_index):
+    """Write the rows of a compact result into caller-provided uint32/int32 tensors
+    (point_index = sorted position + position_base)."""
+    c = _lib.bsj_pip_compact()
+    keep = []
+    for name, dt, _ in _COMPACT_FIELDS:
+        t = compact[name]
+        if t.dtype != dt:
+            t = t.view(dt) if t.element_size() == torch.empty(0, dtype=dt).element_size() else t.to(dt)
+        t = t.contiguous()
+        keep.append(t)
+        setattr(c, name, t.data_ptr() if t.numel() else None)
+    c.n_pairs = compact["pair_hits"].shape[0]
+    c.n_words = compact["mask_words"].shape[0]
+    c.n_hits = int(compact["n_hits"])
+    pp = compact["pair_poly"].contiguous()
+    dev = pp.device
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().bsj_expand_pip_compact(
+            _ptr(pp), C.byref(c), int(position_base) & 0xFFFFFFFF, _stream(dev),
+            _ptr(out_polygon_index), _ptr(out_point_index)))
+
+
 def point_in_polygon_bitmask(points, polygons):
     """The libcuspatial result of point_in_polygon: one INT32 per point, bit i = inside polygon i
     (cpp/include/cuspatial/point_in_polygon.hpp:75-82)."""

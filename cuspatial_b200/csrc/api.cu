@@ -31,6 +31,15 @@ void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, 
                                     u64 n_ring_offsets, const void* vx, const void* vy,
                                     u64 n_verts, const bsj_grid* grid, const bsj_allocator* mr,
                                     cudaStream_t s, bsj_pairs* out);
+void quadtree_point_in_polygon_compact_impl(
+  const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const u32* key, const u8* level,
+  const u8* internal, const u32* length, const u32* offset, u64 num_nodes,
+  const u32* point_indices, const void* px, const void* py, int dtype, u64 n_points,
+  const u32* poly_offsets, u64 n_poly_offsets, const u32* ring_offsets, u64 n_ring_offsets,
+  const void* vx, const void* vy, u64 n_verts, const bsj_grid* grid, const bsj_allocator* mr,
+  cudaStream_t s, bsj_pip_compact* c);
+void expand_pip_compact_impl(const u32* pair_poly, const bsj_pip_compact* c, u32 position_base,
+                             u32* out_poly, u32* out_point, cudaStream_t s);
 void point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_points,
                            const i32* poly_offsets, u64 n_poly_offsets, const i32* ring_offsets,
                            u64 n_ring_offsets, const void* vx, const void* vy, u64 n_verts,
@@ -241,6 +250,45 @@ int bsj_quadtree_point_in_polygon(const uint32_t* pair_poly, const uint32_t* pai
                                           poly_offsets, n_poly_offsets, ring_offsets,
                                           n_ring_offsets, poly_points_x, poly_points_y,
                                           n_poly_points, nullptr, mr, stream, out);
+}
+
+int bsj_quadtree_point_in_polygon_compact(
+  const uint32_t* pair_poly, const uint32_t* pair_quad, uint64_t n_pairs, const uint32_t* key,
+  const uint8_t* level, const uint8_t* is_internal_node, const uint32_t* length,
+  const uint32_t* offset, uint64_t num_nodes, const uint32_t* point_indices, const void* point_x,
+  const void* point_y, int dtype, uint64_t n_points, const uint32_t* poly_offsets,
+  uint64_t n_poly_offsets, const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+  const void* poly_points_x, const void* poly_points_y, uint64_t n_poly_points,
+  const bsj_grid* grid, const bsj_allocator* mr, bsj_stream_t stream, bsj_pip_compact* out)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
+    *out = bsj_pip_compact{};
+    check_dtype(dtype);
+    BSJ_EXPECTS(n_pairs == 0 || (pair_poly && pair_quad),
+                "a quadrant-polygon table must have 2 columns");
+    BSJ_EXPECTS(num_nodes == 0 || (length && offset), "a quadtree table must have 5 columns");
+    BSJ_EXPECTS(n_points == 0 || (point_indices && point_x && point_y),
+                "number of points must be the same for both x and y columns");
+    quadtree_point_in_polygon_compact_impl(
+      pair_poly, pair_quad, n_pairs, key, level, is_internal_node, length, offset, num_nodes,
+      point_indices, point_x, point_y, dtype, n_points, poly_offsets, n_poly_offsets,
+      ring_offsets, n_ring_offsets, poly_points_x, poly_points_y, n_poly_points, grid, mr,
+      (cudaStream_t)stream, out);
+  });
+}
+
+int bsj_expand_pip_compact(const uint32_t* pair_poly, const bsj_pip_compact* c,
+                           uint32_t position_base, bsj_stream_t stream,
+                           uint32_t* out_polygon_index, uint32_t* out_point_index)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(c != nullptr, "compact result must not be NULL");
+    BSJ_EXPECTS(c->n_hits == 0 || (pair_poly && out_polygon_index && out_point_index),
+                "output columns must not be NULL");
+    expand_pip_compact_impl(pair_poly, c, position_base, out_polygon_index, out_point_index,
+                            (cudaStream_t)stream);
+  });
 }
 
 int bsj_point_in_polygon(const void* point_x, const void* point_y, int dtype, uint64_t n_points,

@@ -32,15 +32,38 @@ struct splitters_t {
   int n_ranks;
 };
 
-__global__ void __launch_bounds__(256)
-key_histogram_kernel(const u32* __restrict__ keys, u64 n, int shift, u32* __restrict__ bins)
+// histogram of the keys' leading bits; bins are privatised in shared memory when they fit
+constexpr int kHistSmemBins = 8192;
+__global__ void __launch_bounds__(512)
+key_histogram_kernel(const u32* __restrict__ keys, u64 n, int shift, u32 n_bins,
+                     u32* __restrict__ bins)
 {
+  __shared__ u32 s_bins[kHistSmemBins];
+  bool const use_smem = n_bins <= (u32)kHistSmemBins;
+  if (use_smem) {
+    for (u32 i = threadIdx.x; i < n_bins; i += blockDim.x) s_bins[i] = 0;
+    __syncthreads();
+  }
   u64 const stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    // warp-aggregate equal neighbours (spatially coherent inputs) before the global reduction
-    u32 const b     = __ldcs(keys + i) >> shift;
-    u32 const peers = __match_any_sync(__activemask(), b);
-    if ((peers & lanemask_lt()) == 0) atomicAdd(&bins[b], (u32)__popc(peers));
+  u64 const nvec   = (reinterpret_cast<uintptr_t>(keys) & 15) == 0 ? n / 4 : 0;
+  for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    uint4 const k = __ldcs(reinterpret_cast<const uint4*>(keys) + v);
+    if (use_smem) {
+      atomicAdd(&s_bins[k.x >> shift], 1u); atomicAdd(&s_bins[k.y >> shift], 1u);
+      atomicAdd(&s_bins[k.z >> shift], 1u); atomicAdd(&s_bins[k.w >> shift], 1u);
+    } else {
+      atomicAdd(&bins[k.x >> shift], 1u); atomicAdd(&bins[k.y >> shift], 1u);
+      atomicAdd(&bins[k.z >> shift], 1u); atomicAdd(&bins[k.w >> shift], 1u);
+    }
+  }
+  for (u64 i = nvec * 4 + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u32 const b = keys[i] >> shift;
+    if (use_smem) atomicAdd(&s_bins[b], 1u); else atomicAdd(&bins[b], 1u);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < n_bins; i += blockDim.x)
+      if (s_bins[i]) atomicAdd(&bins[i], s_bins[i]);
   }
 }
 
@@ -172,8 +195,8 @@ void point_keys_histogram_impl(const void* x, const void* y, int dtype, u64 n, d
   if (bins) {
     BSJ_EXPECTS(hist_shift >= 0 && hist_shift < 32 && (0xFFFFFFFFull >> hist_shift) < n_bins,
                 "histogram does not cover the key range");
-    int const grid = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n, 256));
-    key_histogram_kernel<<<grid, 256, 0, s>>>(keys, n, hist_shift, bins);
+    int const grid = (int)std::min<u64>((u64)kNumSMs * 2, (u64)div_up(n, 2048));
+    key_histogram_kernel<<<std::max(grid, 1), 512, 0, s>>>(keys, n, hist_shift, (u32)n_bins, bins);
     BSJ_CHECK_LAUNCH();
   }
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));

@@ -281,12 +281,15 @@ __device__ int classify_quadrant(const grid_info& g, u32 key, u32 level, const p
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pair_prep_kernel(const u32* __restrict__ pair_quad, u32 n_pairs, const u32* __restrict__ length,
-                 u32 num_nodes, u32* __restrict__ words, u32* __restrict__ heads)
+                 const u32* __restrict__ offset, u32 num_nodes, u32* __restrict__ words,
+                 u32* __restrict__ heads, u32* __restrict__ pair_len, u32* __restrict__ pair_off)
 {
   u32 const j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_pairs) return;
   u32 const q   = pair_quad[j];
   u32 const len = q < num_nodes ? length[q] : 0u;
+  pair_len[j]   = len;
+  pair_off[j]   = q < num_nodes ? offset[q] : 0u;
   words[j]      = len / 32 + ((len & 31) != 0);
   heads[j]      = (j == 0 || pair_quad[j - 1] != q) ? 1u : 0u;
 }
@@ -503,21 +506,18 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
 // the lanes' inclusive popcounts and the bit inside it with __fns.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad, u32 n_pairs,
-                const u32* __restrict__ length, const u32* __restrict__ offset, u32 num_nodes,
-                const u64* __restrict__ wbase, const u64* __restrict__ obase,
-                const u32* __restrict__ hits, const u32* __restrict__ mask_words,
-                const u8* __restrict__ cls, u32* __restrict__ out_poly,
-                u32* __restrict__ out_point)
+pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_off,
+                const u32* __restrict__ pair_len, u32 n_pairs, const u64* __restrict__ wbase,
+                const u64* __restrict__ obase, const u32* __restrict__ hits,
+                const u32* __restrict__ mask_words, const u8* __restrict__ cls, u32 position_base,
+                u32* __restrict__ out_poly, u32* __restrict__ out_point)
 {
   u32 const lane  = lane_id();
   u32 const warps = (gridDim.x * blockDim.x) >> 5;
   for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_pairs; j += warps) {
     u32 const nh = hits[j];
     if (nh == 0) continue;
-    u32 const quad = pair_quad[j];
-    if (quad >= num_nodes) continue;
-    u32 const poly = pair_poly[j], len = length[quad], off = offset[quad];
+    u32 const poly = pair_poly[j], len = pair_len[j], off = pair_off[j] + position_base;
     u32 const words = len / 32 + ((len & 31) != 0);
     u64 const wb    = wbase[j];
     u64 o           = obase[j];
@@ -637,15 +637,18 @@ int force_reference_mode()
   return v;
 }
 
+// Everything up to (and including) the evaluation: per-pair hit counts, classes, ballot words and
+// output row offsets -- the COMPACT form of the result (include/cuspatial_b200.h,
+// bsj_pip_compact).  Expanding it into (polygon_index, point_index) rows is a separate step so
+// that a multi-GPU caller can all-gather the compact form (tens of MB) instead of the rows (GBs).
 template <typename T>
-void qpip_impl_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const u32* length,
-                 const u32* offset, u64 num_nodes, const u32* point_indices, const void* px,
-                 const void* py, u64 n_points, const u32* poly_offsets, u64 n_poly_offsets,
-                 const u32* ring_offsets, u64 n_ring_offsets, const void* vx, const void* vy,
-                 u64 n_verts, const u32* node_key, const u8* node_level, const bsj_grid* grid,
-                 const bsj_allocator* mr, cudaStream_t s, bsj_pairs* out)
+void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const u32* length,
+                    const u32* offset, u64 num_nodes, const u32* point_indices, const void* px,
+                    const void* py, u64 n_points, const u32* poly_offsets, u64 n_poly_offsets,
+                    const u32* ring_offsets, u64 n_ring_offsets, const void* vx, const void* vy,
+                    u64 n_verts, const u32* node_key, const u8* node_level, const bsj_grid* grid,
+                    out_alloc& oa, cudaStream_t s, bsj_pip_compact* c)
 {
-  stage_timer tm(s);
   u32 const n_poly = (u32)(n_poly_offsets - 1);
   grid_info gi{};
   {
@@ -664,11 +667,11 @@ void qpip_impl_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const 
       gi.min_x = grid->min_x; gi.min_y = grid->min_y; gi.scale = grid->scale;
       // |x - min| / scale is computed with two roundings of relative size 2^-53 (2^-24): a point
       // lies at most ~3 ulp(extent) outside its cell; take 2^-40 (2^-18) of the coordinate range
-      double const c  = sizeof(T) == 8 ? 9.094947017729282e-13 : 3.814697265625e-06;
-      gi.margin_x = c * (std::fabs(grid->min_x) + std::fabs(grid->max_x) +
-                         std::fabs(grid->max_x - grid->min_x));
-      gi.margin_y = c * (std::fabs(grid->min_y) + std::fabs(grid->max_y) +
-                         std::fabs(grid->max_y - grid->min_y));
+      double const cm = sizeof(T) == 8 ? 9.094947017729282e-13 : 3.814697265625e-06;
+      gi.margin_x = cm * (std::fabs(grid->min_x) + std::fabs(grid->max_x) +
+                          std::fabs(grid->max_x - grid->min_x));
+      gi.margin_y = cm * (std::fabs(grid->min_y) + std::fabs(grid->max_y) +
+                          std::fabs(grid->max_y - grid->min_y));
     }
   }
   dev_buf<poly_meta<T>> meta(std::max<u32>(n_poly, 1), s);
@@ -678,15 +681,22 @@ void qpip_impl_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const 
       (const T*)vx, (const T*)vy, (u32)n_verts, meta.get());
     BSJ_CHECK_LAUNCH();
   }
-  dev_buf<u32> words(n_pairs, s), heads(n_pairs, s), hits(n_pairs, s), run_start(n_pairs + 1, s);
-  dev_buf<u64> wbase(n_pairs, s), run_idx(n_pairs, s), obase(n_pairs, s), totals(4, s);
+  c->n_pairs        = n_pairs;
+  c->pair_offset    = oa.get<u32>(n_pairs);
+  c->pair_length    = oa.get<u32>(n_pairs);
+  c->pair_hits      = oa.get<u32>(n_pairs);
+  c->pair_class     = oa.get<u8>(n_pairs);
+  c->pair_word_base = oa.get<u64>(n_pairs);
+  c->pair_row_base  = oa.get<u64>(n_pairs);
+  dev_buf<u32> words(n_pairs, s), heads(n_pairs, s), run_start(n_pairs + 1, s);
+  dev_buf<u64> run_idx(n_pairs, s), totals(4, s);
   dev_buf<u32> ticket(1, s);
-  dev_buf<u8> cls(n_pairs, s);
   BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
-  pair_prep_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(pair_quad, (u32)n_pairs, length,
-                                                        (u32)num_nodes, words.get(), heads.get());
+  pair_prep_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(pair_quad, (u32)n_pairs, length, offset,
+                                                        (u32)num_nodes, words.get(), heads.get(),
+                                                        c->pair_length, c->pair_offset);
   BSJ_CHECK_LAUNCH();
-  exclusive_scan_u32_to_u64(words.get(), wbase.get(), n_pairs, totals.get() + 0, s);
+  exclusive_scan_u32_to_u64(words.get(), c->pair_word_base, n_pairs, totals.get() + 0, s);
   exclusive_scan_u32_to_u64(heads.get(), run_idx.get(), n_pairs, totals.get() + 1, s);
   run_start_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(heads.get(), run_idx.get(), (u32)n_pairs,
                                                         totals.get() + 1, run_start.get());
@@ -695,38 +705,38 @@ void qpip_impl_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const 
   BSJ_CUDA_TRY(cudaMemcpyAsync(h_tot, totals.get(), 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
   u64 const total_words = h_tot[0], n_runs = h_tot[1];
-  tm.mark("pair_prep");
+  prof_mark("pair_prep");
 
-  dev_buf<u32> mask_words(std::max<u64>(total_words, 1), s);
+  c->n_words    = total_words;
+  c->mask_words = oa.get<u32>(std::max<u64>(total_words, 1));
   {
-    int const grid = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_runs, kPipWarps));
-    pip_eval_kernel<T><<<std::max(grid, 1), kPipWarps * 32, 0, s>>>(
+    int const grid_dim = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_runs, kPipWarps));
+    pip_eval_kernel<T><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
       pair_poly, pair_quad, run_start.get(), totals.get() + 1, length, offset, (u32)num_nodes,
       point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly, ring_offsets,
-      (const T*)vx, (const T*)vy, wbase.get(), mask_words.get(), hits.get(), ticket.get(),
-      force_reference_mode(), node_key, node_level, gi, cls.get());
+      (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words, c->pair_hits, ticket.get(),
+      force_reference_mode(), node_key, node_level, gi, c->pair_class);
     BSJ_CHECK_LAUNCH();
   }
-  tm.mark("pip_eval");
-  exclusive_scan_u32_to_u64(hits.get(), obase.get(), n_pairs, totals.get() + 2, s);
+  prof_mark("pip_eval");
+  exclusive_scan_u32_to_u64(c->pair_hits, c->pair_row_base, n_pairs, totals.get() + 2, s);
   u64 h_hits = 0;
   BSJ_CUDA_TRY(cudaMemcpyAsync(&h_hits, totals.get() + 2, sizeof(u64), cudaMemcpyDeviceToHost, s));
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
-  out_alloc oa(mr, s);
-  out->size = h_hits;
-  if (h_hits) {
-    out->first  = oa.get<u32>(h_hits);
-    out->second = oa.get<u32>(h_hits);
-    int const grid = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_pairs * 32, 256));
-    pip_emit_kernel<<<std::max(grid, 1), 256, 0, s>>>(
-      pair_poly, pair_quad, (u32)n_pairs, length, offset, (u32)num_nodes, wbase.get(),
-      obase.get(), hits.get(), mask_words.get(), cls.get(), out->first, out->second);
-    BSJ_CHECK_LAUNCH();
-  }
-  tm.mark("pip_emit");
-  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
-  tm.finish();
-  oa.commit();
+  c->n_hits = h_hits;
+}
+
+void expand_compact(const u32* pair_poly, const bsj_pip_compact* c, u32 position_base,
+                    u32* out_poly, u32* out_point, cudaStream_t s)
+{
+  if (c->n_hits == 0 || c->n_pairs == 0) return;
+  int const grid_dim = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(c->n_pairs * 32, 256));
+  pip_emit_kernel<<<std::max(grid_dim, 1), 256, 0, s>>>(
+    pair_poly, c->pair_offset, c->pair_length, (u32)c->n_pairs, c->pair_word_base,
+    c->pair_row_base, c->pair_hits, c->mask_words, c->pair_class, position_base, out_poly,
+    out_point);
+  BSJ_CHECK_LAUNCH();
+  prof_mark("pip_emit");
 }
 
 template <typename T>
@@ -755,6 +765,60 @@ void pip_bitmask_t(const void* px, const void* py, u64 n_points, const u32* poly
 
 }  // namespace
 
+namespace {
+struct temp_allocator {  // compact buffers that live only for the duration of one call
+  bsj_allocator a;
+  cudaStream_t s;
+  static void* alloc(size_t bytes, bsj_stream_t st, void*)
+  {
+    void* p = nullptr;
+    ensure_pool_configured();
+    return cudaMallocAsync(&p, bytes, (cudaStream_t)st) == cudaSuccess ? p : nullptr;
+  }
+  static void dealloc(void* p, size_t, bsj_stream_t st, void*) { cudaFreeAsync(p, (cudaStream_t)st); }
+  explicit temp_allocator(cudaStream_t st) : a{&alloc, &dealloc, nullptr}, s(st) {}
+};
+}  // namespace
+
+void quadtree_point_in_polygon_compact_impl(
+  const u32* pair_poly, const u32* pair_quad, u64 n_pairs, const u32* key, const u8* level,
+  const u8* internal, const u32* length, const u32* offset, u64 num_nodes,
+  const u32* point_indices, const void* px, const void* py, int dtype, u64 n_points,
+  const u32* poly_offsets, u64 n_poly_offsets, const u32* ring_offsets, u64 n_ring_offsets,
+  const void* vx, const void* vy, u64 n_verts, const bsj_grid* grid, const bsj_allocator* mr,
+  cudaStream_t s, bsj_pip_compact* c)
+{
+  (void)internal;
+  *c = bsj_pip_compact{};
+  // empty inputs: cpp/src/join/quadtree_point_in_polygon.cu:171-178
+  if (n_pairs == 0 || num_nodes == 0 || n_points == 0 || n_poly_offsets == 0) return;
+  BSJ_EXPECTS(n_pairs < 0xFFFFFFFFull && num_nodes < 0xFFFFFFFFull && n_points <= 0xFFFFFFFFull,
+              "table too large");
+  BSJ_EXPECTS(n_ring_offsets >= 1 || n_poly_offsets <= 1, "ring offsets must not be empty");
+  stage_timer tm(s);
+  out_alloc oa(mr, s);
+  if (dtype == BSJ_FLOAT32)
+    qpip_compact_t<float>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes, point_indices,
+                          px, py, n_points, poly_offsets, n_poly_offsets, ring_offsets,
+                          n_ring_offsets, vx, vy, n_verts, key, level, grid, oa, s, c);
+  else
+    qpip_compact_t<double>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes,
+                           point_indices, px, py, n_points, poly_offsets, n_poly_offsets,
+                           ring_offsets, n_ring_offsets, vx, vy, n_verts, key, level, grid, oa, s,
+                           c);
+  tm.finish();
+  oa.commit();
+}
+
+void expand_pip_compact_impl(const u32* pair_poly, const bsj_pip_compact* c, u32 position_base,
+                             u32* out_poly, u32* out_point, cudaStream_t s)
+{
+  stage_timer tm(s);
+  expand_compact(pair_poly, c, position_base, out_poly, out_point, s);
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+  tm.finish();
+}
+
 void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, u64 n_pairs,
                                     const u32* key, const u8* level, const u8* internal,
                                     const u32* length, const u32* offset, u64 num_nodes,
@@ -767,19 +831,34 @@ void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, 
 {
   (void)internal;
   *out = bsj_pairs{};
-  // empty inputs: cpp/src/join/quadtree_point_in_polygon.cu:171-178
   if (n_pairs == 0 || num_nodes == 0 || n_points == 0 || n_poly_offsets == 0) return;
   BSJ_EXPECTS(n_pairs < 0xFFFFFFFFull && num_nodes < 0xFFFFFFFFull && n_points <= 0xFFFFFFFFull,
               "table too large");
   BSJ_EXPECTS(n_ring_offsets >= 1 || n_poly_offsets <= 1, "ring offsets must not be empty");
+  stage_timer tm(s);
+  temp_allocator tmp(s);
+  out_alloc scratch(&tmp.a, s);  // the compact form is a temporary here: freed on return
+  bsj_pip_compact c{};
   if (dtype == BSJ_FLOAT32)
-    qpip_impl_t<float>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes, point_indices, px,
-                       py, n_points, poly_offsets, n_poly_offsets, ring_offsets, n_ring_offsets,
-                       vx, vy, n_verts, key, level, grid, mr, s, out);
+    qpip_compact_t<float>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes, point_indices,
+                          px, py, n_points, poly_offsets, n_poly_offsets, ring_offsets,
+                          n_ring_offsets, vx, vy, n_verts, key, level, grid, scratch, s, &c);
   else
-    qpip_impl_t<double>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes, point_indices,
-                        px, py, n_points, poly_offsets, n_poly_offsets, ring_offsets,
-                        n_ring_offsets, vx, vy, n_verts, key, level, grid, mr, s, out);
+    qpip_compact_t<double>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes,
+                           point_indices, px, py, n_points, poly_offsets, n_poly_offsets,
+                           ring_offsets, n_ring_offsets, vx, vy, n_verts, key, level, grid,
+                           scratch, s, &c);
+  out_alloc oa(mr, s);
+  out->size = c.n_hits;
+  if (c.n_hits) {
+    out->first  = oa.get<u32>(c.n_hits);
+    out->second = oa.get<u32>(c.n_hits);
+    expand_compact(pair_poly, &c, 0u, out->first, out->second, s);
+  }
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+  tm.finish();
+  oa.commit();
+  // `scratch` is not committed: its destructor releases the compact buffers
 }
 
 void point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_points,

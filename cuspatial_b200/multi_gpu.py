@@ -22,10 +22,32 @@ global quadtree, so row order inside the table differs; compare sorted rows).
 The three device steps are injected as callables so that the host-side logic (splitters, index
 fix-up, merge) is testable on CPU with the gloo backend (tests/test_multi_gpu_cpu.py).
 """
+import os
+import time
+
 import numpy as np
 import torch
 
-HIST_BITS = 16
+HIST_BITS = 13   # 8192 bins: privatised in shared memory by the histogram kernel
+LAST_PROFILE = {}
+
+
+class _Prof:
+    """Optional wall-clock phase timing (BSJ_MG_PROFILE=1): synchronises, so never on by default."""
+
+    def __init__(self, dev):
+        self.on = os.environ.get("BSJ_MG_PROFILE") == "1" and dev.type == "cuda"
+        self.dev, self.t, self.out = dev, None, {}
+        if self.on:
+            torch.cuda.synchronize(dev)
+            self.t = time.perf_counter()
+
+    def mark(self, name):
+        if self.on:
+            torch.cuda.synchronize(self.dev)
+            now = time.perf_counter()
+            self.out[name] = self.out.get(name, 0.0) + 1e3 * (now - self.t)
+            self.t = now
 
 
 def choose_splitters(global_hist, n_ranks, shift):
@@ -88,7 +110,8 @@ def cuda_partition(keys, x, y, gid_base, splitters, counts):
     return ox, oy, ogid
 
 
-def cuda_local_join(x, y, polygons, bbox, scale, max_depth, max_size):
+def cuda_local_compact(x, y, polygons, bbox, scale, max_depth, max_size):
+    """The single-GPU path on this rank's points, stopped at the COMPACT PIP result."""
     from . import api
 
     pidx, tree = api.quadtree_on_points((x, y), bbox[0], bbox[1], bbox[2], bbox[3], scale,
@@ -96,25 +119,43 @@ def cuda_local_join(x, y, polygons, bbox, scale, max_depth, max_size):
     bb = api.polygon_bounding_boxes(polygons)
     pairs = api.join_quadtree_and_bounding_boxes(tree, bb, bbox[0], bbox[1], bbox[2], bbox[3],
                                                  scale, max_depth)
-    hits = api.quadtree_point_in_polygon(pairs, tree, pidx, (x, y), polygons)
-    return (pidx.view(torch.int32), hits["polygon_index"].view(torch.int32),
-            hits["point_index"].view(torch.int32))
+    comp = api.quadtree_point_in_polygon_compact(pairs, tree, pidx, (x, y), polygons)
+    n_hits = comp.pop("n_hits")
+    comp = {k: (v.view(torch.int32) if v.dtype == torch.uint32 else v) for k, v in comp.items()}
+    return pidx.view(torch.int32), comp, n_hits
+
+
+def cuda_expand(comp, n_hits, position_base, out_poly, out_point):
+    from . import api
+
+    api.expand_pip_compact(dict(comp, n_hits=n_hits), position_base, out_poly, out_point)
 
 
 # ------------------------------------------------------------------------------------------------
-def _all_gather_varlen(t, dist, group):
-    """all-gather of 1-D tensors of different lengths (padded all_gather_into_tensor)."""
+def _all_gather_varlen(t, dist, group, sizes=None):
+    """all-gather of 1-D tensors of different lengths straight into the merged buffer: one
+    broadcast per source rank into its slice (no padding, no concatenation copy)."""
     world = dist.get_world_size(group)
-    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    m = max(sizes) if sizes else 0
-    pad = torch.zeros(m, dtype=t.dtype, device=t.device)
-    pad[: t.shape[0]] = t
-    out = torch.empty(m * world, dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(out, pad, group=group)
-    return torch.cat([out[r * m: r * m + sizes[r]] for r in range(world)]), sizes
+    rank = dist.get_rank(group)
+    if sizes is None:
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        sz = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sz, n, group=group)
+        sizes = [int(s.item()) for s in sz]
+    out = torch.empty(sum(sizes), dtype=t.dtype, device=t.device)
+    works, o = [], 0
+    for r in range(world):
+        sl = out[o: o + sizes[r]]
+        o += sizes[r]
+        if sizes[r] == 0:
+            continue
+        if r == rank:
+            sl.copy_(t)
+        src = dist.get_global_rank(group, r) if group is not None else r
+        works.append(dist.broadcast(sl, src=src, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    return out, sizes
 
 
 def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_max, scale,
@@ -136,7 +177,8 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     steps = steps or {}
     keys_hist = steps.get("keys_hist", cuda_keys_and_histogram)
     partition = steps.get("partition", cuda_partition)
-    local_join = steps.get("local_join", cuda_local_join)
+    local_compact = steps.get("local_compact", cuda_local_compact)
+    expand = steps.get("expand", cuda_expand)
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -146,6 +188,7 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     min_scale = max(bbox[1] - bbox[0], bbox[3] - bbox[2]) / ((1 << max_depth) + 2)
     scale = max(scale, min_scale)
 
+    prof = _Prof(dev)
     # 1. replicate the polygon table (sizes first, then payload) -- NCCL broadcast
     meta = torch.tensor([t.shape[0] for t in polygons], dtype=torch.int64, device=dev)
     dist.broadcast(meta, src=dist.get_global_rank(group, 0) if group else 0, group=group)
@@ -159,6 +202,7 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
         polys.append(t)
     polys = tuple(polys)
 
+    prof.mark("broadcast_polygons")
     # global ids are rank-major
     n_local = torch.tensor([x.shape[0]], dtype=torch.int64, device=dev)
     all_n = [torch.zeros_like(n_local) for _ in range(world)]
@@ -169,17 +213,21 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     # 2. keys + leading-bit histogram, one all-reduce, identical splitters everywhere
     shift = hist_shift_for(max_depth)
     n_bins = 1 << min(HIST_BITS, 32 - shift) if shift < 32 else 1
+    prof.mark("gid_bases")
     keys, hist = keys_hist(x, y, bbox, scale, max_depth, shift, n_bins)
+    prof.mark("keys_hist")
     local_hist = hist.detach().clone().cpu().numpy()
     dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     hist_h = hist.cpu().numpy()
     splitters = choose_splitters(hist_h, world, shift)
 
+    prof.mark("allreduce_splitters")
     # 3. stable partition by destination + all-to-all
     bin_owner = np.searchsorted(splitters.astype(np.int64) >> shift,
                                 np.arange(n_bins, dtype=np.int64), side="right")
     send_counts = np.bincount(bin_owner, weights=local_hist, minlength=world).astype(np.int64)
     sx, sy, sgid = partition(keys, x, y, gid_base, splitters, send_counts.tolist())
+    prof.mark("partition")
     sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
     rc = torch.empty_like(sc)
     dist.all_to_all_single(rc, sc, group=group)
@@ -192,25 +240,57 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
         dist.all_to_all_single(dst, src, output_split_sizes=recv_counts,
                                input_split_sizes=send_counts.tolist(), group=group)
 
-    # 4. the unchanged single-GPU path on this rank's key range
-    pidx_local, poly_idx, pos_local = local_join(rx, ry, polys, bbox, scale, max_depth, max_size)
+    prof.mark("all_to_all")
+    # 4. the unchanged single-GPU path on this rank's key range, stopped at the compact result
+    pidx_local, comp, n_hits = local_compact(rx, ry, polys, bbox, scale, max_depth, max_size)
+    prof.mark("local_join")
 
-    # 5. global indices and merge
-    cnt = torch.tensor([n_recv], dtype=torch.int64, device=dev)
-    cnts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(cnts, cnt, group=group)
-    counts = [int(c.item()) for c in cnts]
+    # 5. global indices and merge.  What crosses NVLink is the COMPACT result (per-pair records +
+    # ballot words, tens of MB); every rank then expands every rank's rows itself, at HBM speed,
+    # with point_index = rank base + local sorted position.
+    names = sorted(comp)
+    stat = torch.tensor([n_recv, n_hits] + [comp[k].shape[0] for k in names], dtype=torch.int64,
+                        device=dev)
+    stats = [torch.zeros_like(stat) for _ in range(world)]
+    dist.all_gather(stats, stat, group=group)
+    stats = [s_.tolist() for s_ in stats]
+    counts = [s_[0] for s_ in stats]
+    hits = [s_[1] for s_ in stats]
     base = sum(counts[:rank])
-    point_indices = rgid[pidx_local.to(torch.int64)] if n_recv else rgid
-    pos_global = (pos_local.to(torch.int64) + base).to(torch.int32)
-    out = {"base": base, "counts": counts}
+    out = {"base": base, "counts": counts, "rows_per_rank": hits}
+    prof.mark("global_indices")
     if gather_pairs:
-        out["polygon_index"], _ = _all_gather_varlen(poly_idx, dist, group)
-        out["point_index"], _ = _all_gather_varlen(pos_global, dist, group)
+        gathered = {}
+        for i, k in enumerate(names):
+            gathered[k], _ = _all_gather_varlen(comp[k], dist, group, [s_[2 + i] for s_ in stats])
+        total = sum(hits)
+        out_poly = torch.empty(total, dtype=torch.int32, device=dev)
+        out_point = torch.empty(total, dtype=torch.int32, device=dev)
+        row = 0
+        for r in range(world):
+            part = {}
+            for i, k in enumerate(names):
+                o = sum(s_[2 + i] for s_ in stats[:r])
+                part[k] = gathered[k][o: o + stats[r][2 + i]]
+            if hits[r]:
+                expand(part, hits[r], sum(counts[:r]), out_poly[row: row + hits[r]],
+                       out_point[row: row + hits[r]])
+            row += hits[r]
+        out["polygon_index"], out["point_index"] = out_poly, out_point
     else:
-        out["polygon_index"], out["point_index"] = poly_idx, pos_global
+        out_poly = torch.empty(n_hits, dtype=torch.int32, device=dev)
+        out_point = torch.empty(n_hits, dtype=torch.int32, device=dev)
+        if n_hits:
+            expand(comp, n_hits, base, out_poly, out_point)
+        out["polygon_index"], out["point_index"] = out_poly, out_point
+    # global sorted position -> global point id, for this rank's key range (lazy: a 100M-element
+    # gather that most callers of a join do not need)
+    out["local_point_indices"], out["received_global_ids"] = pidx_local, rgid
     if gather_point_indices:
-        out["point_indices"], _ = _all_gather_varlen(point_indices, dist, group)
-    else:
-        out["point_indices"] = point_indices
+        point_indices = rgid[pidx_local.to(torch.int64)] if n_recv else rgid
+        out["point_indices"], _ = _all_gather_varlen(point_indices, dist, group, counts)
+    prof.mark("all_gather")
+    if prof.on:
+        LAST_PROFILE.clear()
+        LAST_PROFILE.update(prof.out)
     return out

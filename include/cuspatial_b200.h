@@ -166,6 +166,42 @@ int bsj_quadtree_point_in_polygon_ex(const uint32_t* pair_poly, const uint32_t* 
                                      const bsj_allocator* mr, bsj_stream_t stream, bsj_pairs* out);
 
 /*
+ * Compact form of a quadtree_point_in_polygon result (no reference analogue; used by the
+ * multi-GPU merge, which all-gathers this instead of the expanded rows).  For pair j:
+ * quadrant points are sorted positions pair_offset[j] .. +pair_length[j]-1; pair_class[j] is
+ * 0 (no point inside), 1 (every point inside) or 2 (bit l of the ballot words starting at
+ * mask_words[pair_word_base[j]] tells whether point l is inside); pair_hits[j] rows start at row
+ * pair_row_base[j] of the expanded table.
+ */
+typedef struct bsj_pip_compact {
+  uint32_t* pair_offset;
+  uint32_t* pair_length;
+  uint32_t* pair_hits;
+  uint8_t* pair_class;
+  uint64_t* pair_word_base;
+  uint64_t* pair_row_base;
+  uint32_t* mask_words;
+  uint64_t n_pairs, n_words, n_hits;
+} bsj_pip_compact;
+
+/* Same inputs as bsj_quadtree_point_in_polygon_ex; buffers of `out` come from `mr`. */
+int bsj_quadtree_point_in_polygon_compact(
+  const uint32_t* pair_poly, const uint32_t* pair_quad, uint64_t n_pairs, const uint32_t* key,
+  const uint8_t* level, const uint8_t* is_internal_node, const uint32_t* length,
+  const uint32_t* offset, uint64_t num_nodes, const uint32_t* point_indices, const void* point_x,
+  const void* point_y, int dtype, uint64_t n_points, const uint32_t* poly_offsets,
+  uint64_t n_poly_offsets, const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+  const void* poly_points_x, const void* poly_points_y, uint64_t n_poly_points,
+  const bsj_grid* grid, const bsj_allocator* mr, bsj_stream_t stream, bsj_pip_compact* out);
+
+/* Expand a compact result into rows: out_polygon_index/out_point_index must hold c->n_hits rows;
+ * point_index = sorted position + position_base (the first global position of the producing
+ * rank's key range; 0 on a single GPU). */
+int bsj_expand_pip_compact(const uint32_t* pair_poly, const bsj_pip_compact* c,
+                           uint32_t position_base, bsj_stream_t stream,
+                           uint32_t* out_polygon_index, uint32_t* out_point_index);
+
+/*
  * Replaces cuspatial::point_in_polygon (bitmask form)
  *   (cpp/include/cuspatial/point_in_polygon.hpp:75-82, cpp/src/point_in_polygon/point_in_polygon.cu:153-171).
  * Offsets are int32 (cudf::size_type, :72-73). At most 31 polygons

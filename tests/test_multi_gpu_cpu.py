@@ -57,11 +57,16 @@ def _host_steps(oracle):
         pairs = oracle.join_quadtree_and_bounding_boxes(t, *bb, bbox[0], bbox[2], scale, max_depth)
         hp, hq = oracle.quadtree_point_in_polygon(pairs[0], pairs[1], t, t["point_indices"], xn,
                                                   yn, po, ro, vx, vy)
-        return (torch.from_numpy(t["point_indices"].view(np.int32).copy()),
-                torch.from_numpy(hp.view(np.int32).copy()),
-                torch.from_numpy(hq.view(np.int32).copy()))
+        comp = {"poly": torch.from_numpy(hp.view(np.int32).copy()),
+                "pos": torch.from_numpy(hq.view(np.int32).copy())}
+        return torch.from_numpy(t["point_indices"].view(np.int32).copy()), comp, len(hp)
 
-    return {"keys_hist": keys_hist, "partition": partition, "local_join": local_join}
+    def expand(comp, n_hits, position_base, out_poly, out_point):
+        out_poly.copy_(comp["poly"])
+        out_point.copy_((comp["pos"].to(torch.int64) + position_base).to(torch.int32))
+
+    return {"keys_hist": keys_hist, "partition": partition, "local_compact": local_join,
+            "expand": expand}
 
 
 def _worker(rank, world, port, kind, dtype_name, q):
