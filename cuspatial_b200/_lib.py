@@ -97,7 +97,7 @@ def lib():
     L.bsj_point_keys_histogram.argtypes = [vp, vp, C.c_int, u64, dbl, dbl, dbl, dbl, dbl, C.c_int8,
                                            C.c_int, vp, vp, u64, vp]
     L.bsj_partition_points.argtypes = [vp, vp, vp, C.c_int, u64, C.c_uint32, vp, C.c_int, vp, vp,
-                                       vp, vp, vp]
+                                       vp, vp]
     L.bsj_free.argtypes = [vp, vp]
     L.bsj_last_error.restype = C.c_char_p
     L.bsj_version.restype = C.c_char_p

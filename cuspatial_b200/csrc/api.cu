@@ -55,7 +55,7 @@ void point_keys_histogram_impl(const void* x, const void* y, int dtype, u64 n, d
                                cudaStream_t s);
 void partition_points_impl(const u32* keys, const void* x, const void* y, int dtype, u64 n,
                            u32 gid_base, const u32* h_splitters, int n_ranks,
-                           const u32* d_bucket_base, void* out_x, void* out_y, u32* out_gid,
+                           void* const* dst_x, void* const* dst_y, u32* const* dst_gid,
                            cudaStream_t s);
 
 namespace {
@@ -341,13 +341,14 @@ int bsj_point_keys_histogram(const void* x, const void* y, int dtype, uint64_t n
 
 int bsj_partition_points(const uint32_t* keys, const void* x, const void* y, int dtype, uint64_t n,
                          uint32_t gid_base, const uint32_t* host_splitters, int n_ranks,
-                         const uint32_t* bucket_base, void* out_x, void* out_y, uint32_t* out_gid,
+                         void* const* dst_x, void* const* dst_y, uint32_t* const* dst_gid,
                          bsj_stream_t stream)
 {
   return guarded([&] {
     check_dtype(dtype);
-    partition_points_impl(keys, x, y, dtype, n, gid_base, host_splitters, n_ranks, bucket_base,
-                          out_x, out_y, out_gid, (cudaStream_t)stream);
+    BSJ_EXPECTS(dst_x && dst_y && dst_gid, "destination pointer tables must not be NULL");
+    partition_points_impl(keys, x, y, dtype, n, gid_base, host_splitters, n_ranks, dst_x, dst_y,
+                          dst_gid, (cudaStream_t)stream);
   });
 }
 

@@ -31,6 +31,14 @@ struct splitters_t {
   u32 key[kMaxRanks];  // rank r owns keys in [key[r-1], key[r]); key[R-1] unused
   int n_ranks;
 };
+// Per-destination output bases.  On the multi-GPU path these are PEER pointers (symmetric memory
+// mapped over NVLink): the partition kernel's stores ARE the all-to-all exchange.
+template <typename T>
+struct dests_t {
+  T* x[kMaxRanks];
+  T* y[kMaxRanks];
+  u32* gid[kMaxRanks];
+};
 
 // histogram of the keys' leading bits; bins are privatised in shared memory when they fit
 constexpr int kHistSmemBins = 8192;
@@ -78,9 +86,8 @@ __device__ __forceinline__ int dest_of(u32 key, const splitters_t& sp)
 template <typename T>
 __global__ void __launch_bounds__(kPartBlock)
 partition_kernel(const u32* __restrict__ keys, const T* __restrict__ x, const T* __restrict__ y,
-                 u32 n, u32 gid_base, splitters_t sp, const u32* __restrict__ bucket_base,
-                 T* __restrict__ out_x, T* __restrict__ out_y, u32* __restrict__ out_gid,
-                 u64* __restrict__ desc, u32* __restrict__ ticket)
+                 u32 n, u32 gid_base, splitters_t sp, dests_t<T> dst, u64* __restrict__ desc,
+                 u32* __restrict__ ticket)
 {
   __shared__ u32 s_tile;
   __shared__ u32 s_warp_cnt[kPartBlock / 32][kMaxRanks];
@@ -144,37 +151,43 @@ partition_kernel(const u32* __restrict__ keys, const T* __restrict__ x, const T*
       }
       st_relaxed_u64(col + (u64)tile * kMaxRanks, lb_pack(3u, excl + total));
     }
-    s_base[tid] = bucket_base[tid] + excl;
+    s_base[tid] = excl;
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < kPartIPT; ++i) {
     if (dest[i] >= 0) {
       u32 const idx = warp_base + i * 32 + lane;
-      u32 const o   = s_base[dest[i]] + s_warp_off[warp][dest[i]] + rank[i];
-      out_x[o]      = __ldcs(x + idx);
-      out_y[o]      = __ldcs(y + idx);
-      out_gid[o]    = gid_base + idx;
+      int const d   = dest[i];
+      u32 const o   = s_base[d] + s_warp_off[warp][d] + rank[i];
+      dst.x[d][o]   = __ldcs(x + idx);
+      dst.y[d][o]   = __ldcs(y + idx);
+      dst.gid[d][o] = gid_base + idx;
     }
   }
 }
 
 template <typename T>
 void partition_t(const u32* keys, const void* x, const void* y, u64 n, u32 gid_base,
-                 const u32* h_splitters, int n_ranks, const u32* d_bucket_base, void* out_x,
-                 void* out_y, u32* out_gid, cudaStream_t s)
+                 const u32* h_splitters, int n_ranks, void* const* dst_x, void* const* dst_y,
+                 u32* const* dst_gid, cudaStream_t s)
 {
   splitters_t sp{};
   sp.n_ranks = n_ranks;
   for (int r = 0; r + 1 < n_ranks; ++r) sp.key[r] = h_splitters[r];
+  dests_t<T> dst{};
+  for (int r = 0; r < n_ranks; ++r) {
+    dst.x[r]   = (T*)dst_x[r];
+    dst.y[r]   = (T*)dst_y[r];
+    dst.gid[r] = dst_gid[r];
+  }
   u32 const tiles = (u32)div_up(n, kPartTile);
   dev_buf<u64> desc((size_t)tiles * kMaxRanks, s);
   dev_buf<u32> ticket(1, s);
   BSJ_CUDA_TRY(cudaMemsetAsync(desc.get(), 0, desc.size() * sizeof(u64), s));
   BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
   partition_kernel<T><<<tiles, kPartBlock, 0, s>>>(keys, (const T*)x, (const T*)y, (u32)n,
-                                                   gid_base, sp, d_bucket_base, (T*)out_x,
-                                                   (T*)out_y, out_gid, desc.get(), ticket.get());
+                                                   gid_base, sp, dst, desc.get(), ticket.get());
   BSJ_CHECK_LAUNCH();
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
 }
@@ -204,18 +217,16 @@ void point_keys_histogram_impl(const void* x, const void* y, int dtype, u64 n, d
 
 void partition_points_impl(const u32* keys, const void* x, const void* y, int dtype, u64 n,
                            u32 gid_base, const u32* h_splitters, int n_ranks,
-                           const u32* d_bucket_base, void* out_x, void* out_y, u32* out_gid,
+                           void* const* dst_x, void* const* dst_y, u32* const* dst_gid,
                            cudaStream_t s)
 {
   BSJ_EXPECTS(n_ranks >= 1 && n_ranks <= kMaxRanks, "unsupported number of ranks");
   BSJ_EXPECTS(n < 0xFFFFFFFFull, "number of points must fit uint32 indices");
   if (n == 0) return;
   if (dtype == BSJ_FLOAT32)
-    partition_t<float>(keys, x, y, n, gid_base, h_splitters, n_ranks, d_bucket_base, out_x, out_y,
-                       out_gid, s);
+    partition_t<float>(keys, x, y, n, gid_base, h_splitters, n_ranks, dst_x, dst_y, dst_gid, s);
   else
-    partition_t<double>(keys, x, y, n, gid_base, h_splitters, n_ranks, d_bucket_base, out_x,
-                        out_y, out_gid, s);
+    partition_t<double>(keys, x, y, n, gid_base, h_splitters, n_ranks, dst_x, dst_y, dst_gid, s);
 }
 
 }  // namespace bsj

@@ -89,25 +89,66 @@ def cuda_keys_and_histogram(x, y, bbox, scale, max_depth, shift, n_bins):
     return keys, bins.to(torch.int64)
 
 
-def cuda_partition(keys, x, y, gid_base, splitters, counts):
+_SYMM = {}
+
+
+def _symmetric_buffers(dev, dtype, capacity, group):
+    """Receive buffers (x, y, gid) in symmetric memory, mapped into every peer: grown
+    collectively (all ranks see the same `capacity`), cached across calls."""
+    import torch.distributed._symmetric_memory as symm
+
+    key = (dev.index, dtype)
+    ent = _SYMM.get(key)
+    if ent is None or ent["cap"] < capacity:
+        cap = int(capacity * 1.25) + 4096
+        bufs, hdls = [], []
+        for dt in (dtype, dtype, torch.int32):
+            t = symm.empty(cap, dtype=dt, device=dev)
+            hdls.append(symm.rendezvous(t, group if group is not None else
+                                        torch.distributed.group.WORLD))
+            bufs.append(t)
+        ent = {"cap": cap, "bufs": bufs, "hdls": hdls}
+        _SYMM[key] = ent
+    return ent
+
+
+def cuda_partition_exchange(keys, x, y, gid_base, splitters, counts_matrix, rank, group):
+    """Stable partition by destination rank whose stores go straight into the destination GPUs'
+    receive buffers (peer memory over NVLink): partition and all-to-all in ONE kernel.
+    counts_matrix[src][dst] = points rank src sends to rank dst (identical on every rank)."""
     import ctypes as C
+
+    import torch.distributed as dist
 
     from . import _lib
     from .api import _DTYPE_CODE, _ptr, _stream
 
-    n, R = x.shape[0], len(counts)
-    base = torch.zeros(R, dtype=torch.int64)
-    base[1:] = torch.cumsum(torch.as_tensor(counts[:-1], dtype=torch.int64), 0)
-    d_base = base.to(torch.int32).to(x.device)
-    ox, oy = torch.empty_like(x), torch.empty_like(y)
-    ogid = torch.empty(n, dtype=torch.int32, device=x.device)
+    R = len(counts_matrix)
+    dev = x.device
+    recv_tot = [sum(counts_matrix[s][d] for s in range(R)) for d in range(R)]
+    ent = _symmetric_buffers(dev, x.dtype, max(recv_tot), group)
+    cap = ent["cap"]
+    esz = x.element_size()
+    ptr_x, ptr_y, ptr_g = (C.c_void_p * R)(), (C.c_void_p * R)(), (C.c_void_p * R)()
+    for d in range(R):
+        off = sum(counts_matrix[s][d] for s in range(rank))  # where my bucket starts in rank d
+        bx = ent["hdls"][0].get_buffer(d, (cap,), x.dtype)
+        by = ent["hdls"][1].get_buffer(d, (cap,), x.dtype)
+        bg = ent["hdls"][2].get_buffer(d, (cap,), torch.int32)
+        ptr_x[d] = bx.data_ptr() + off * esz
+        ptr_y[d] = by.data_ptr() + off * esz
+        ptr_g[d] = bg.data_ptr() + off * 4
     sp = np.ascontiguousarray(splitters, dtype=np.uint32)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(dev):
         _lib.check(_lib.lib().bsj_partition_points(
-            _ptr(keys), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], n, int(gid_base),
-            sp.ctypes.data_as(C.c_void_p), R, _ptr(d_base), _ptr(ox), _ptr(oy), _ptr(ogid),
-            _stream(x.device)))
-    return ox, oy, ogid
+            _ptr(keys), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], int(gid_base),
+            sp.ctypes.data_as(C.c_void_p), R, ptr_x, ptr_y, ptr_g, _stream(dev)))
+    # every rank's stores must have landed before anyone reads its receive buffers
+    torch.cuda.synchronize(dev)
+    dist.barrier(group=group)
+    n_recv = recv_tot[rank]
+    rx, ry, rg = (b[:n_recv] for b in ent["bufs"])
+    return rx, ry, rg
 
 
 def cuda_local_compact(x, y, polygons, bbox, scale, max_depth, max_size):
@@ -176,7 +217,7 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
 
     steps = steps or {}
     keys_hist = steps.get("keys_hist", cuda_keys_and_histogram)
-    partition = steps.get("partition", cuda_partition)
+    partition = steps.get("partition")  # host stand-in for the CPU tests
     local_compact = steps.get("local_compact", cuda_local_compact)
     expand = steps.get("expand", cuda_expand)
 
@@ -226,21 +267,27 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     bin_owner = np.searchsorted(splitters.astype(np.int64) >> shift,
                                 np.arange(n_bins, dtype=np.int64), side="right")
     send_counts = np.bincount(bin_owner, weights=local_hist, minlength=world).astype(np.int64)
-    sx, sy, sgid = partition(keys, x, y, gid_base, splitters, send_counts.tolist())
-    prof.mark("partition")
     sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
-    rc = torch.empty_like(sc)
-    dist.all_to_all_single(rc, sc, group=group)
-    recv_counts = rc.tolist()
+    rows = [torch.zeros_like(sc) for _ in range(world)]
+    dist.all_gather(rows, sc, group=group)       # also orders this step after every rank's
+    counts_matrix = [r_.tolist() for r_ in rows]  # previous step (receive buffers are reused)
+    recv_counts = [counts_matrix[s_][rank] for s_ in range(world)]
     n_recv = int(sum(recv_counts))
-    rx = torch.empty(n_recv, dtype=x.dtype, device=dev)
-    ry = torch.empty(n_recv, dtype=y.dtype, device=dev)
-    rgid = torch.empty(n_recv, dtype=torch.int32, device=dev)
-    for dst, src in ((rx, sx), (ry, sy), (rgid, sgid)):
-        dist.all_to_all_single(dst, src, output_split_sizes=recv_counts,
-                               input_split_sizes=send_counts.tolist(), group=group)
-
-    prof.mark("all_to_all")
+    if partition is None:
+        # fused partition + exchange: the kernel writes into the peers' receive buffers
+        rx, ry, rgid = cuda_partition_exchange(keys, x, y, gid_base, splitters, counts_matrix,
+                                               rank, group)
+        prof.mark("partition_exchange")
+    else:
+        sx, sy, sgid = partition(keys, x, y, gid_base, splitters, send_counts.tolist())
+        prof.mark("partition")
+        rx = torch.empty(n_recv, dtype=x.dtype, device=dev)
+        ry = torch.empty(n_recv, dtype=y.dtype, device=dev)
+        rgid = torch.empty(n_recv, dtype=torch.int32, device=dev)
+        for dst, src in ((rx, sx), (ry, sy), (rgid, sgid)):
+            dist.all_to_all_single(dst, src, output_split_sizes=recv_counts,
+                                   input_split_sizes=send_counts.tolist(), group=group)
+        prof.mark("all_to_all")
     # 4. the unchanged single-GPU path on this rank's key range, stopped at the compact result
     pidx_local, comp, n_hits = local_compact(rx, ry, polys, bbox, scale, max_depth, max_size)
     prof.mark("local_join")

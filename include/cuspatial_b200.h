@@ -236,8 +236,10 @@ int bsj_polygon_bounding_boxes(const uint32_t* poly_offsets, uint64_t n_poly_off
  *   (cpp/include/cuspatial/detail/index/construction/phase_1.cuh:78-85) and, if bins != NULL,
  *   bins[keys[i] >> hist_shift] += 1 (bins are accumulated into, n_bins > max key >> hist_shift).
  * bsj_partition_points: stable partition by destination rank, destination of key k =
- *   #{r : k >= host_splitters[r]}, r < n_ranks-1.  bucket_base[r] (device) is the first slot of
- *   destination r in the output buffers; out_gid[o] = gid_base + original index.
+ *   #{r : k >= host_splitters[r]}, r < n_ranks-1.  dst_x/dst_y/dst_gid are HOST arrays of n_ranks
+ *   DEVICE pointers: where this rank's bucket for destination r starts.  They may point into peer
+ *   GPUs' memory (CUDA IPC / symmetric memory over NVLink): the kernel's stores then ARE the
+ *   all-to-all exchange -- no staging buffer, no separate collective.  gid = gid_base + index.
  */
 int bsj_point_keys_histogram(const void* x, const void* y, int dtype, uint64_t n, double x_min,
                              double x_max, double y_min, double y_max, double scale,
@@ -245,7 +247,7 @@ int bsj_point_keys_histogram(const void* x, const void* y, int dtype, uint64_t n
                              uint64_t n_bins, bsj_stream_t stream);
 int bsj_partition_points(const uint32_t* keys, const void* x, const void* y, int dtype, uint64_t n,
                          uint32_t gid_base, const uint32_t* host_splitters, int n_ranks,
-                         const uint32_t* bucket_base, void* out_x, void* out_y, uint32_t* out_gid,
+                         void* const* dst_x, void* const* dst_y, uint32_t* const* dst_gid,
                          bsj_stream_t stream);
 
 /* Release a buffer the library allocated with its default allocator (mr == NULL). */
