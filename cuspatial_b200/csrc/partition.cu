@@ -83,23 +83,37 @@ __device__ __forceinline__ int dest_of(u32 key, const splitters_t& sp)
 }
 
 // descriptors: [tile][kMaxRanks] u64 {tag, value}
+// The tile is first re-ordered by destination in shared memory so that what leaves the SM (over
+// NVLink for remote destinations) are contiguous per-destination runs, not 8-byte scatters.
+template <typename T>
+struct part_smem {
+  T x[kPartTile];
+  T y[kPartTile];
+  u32 gid[kPartTile];
+  u32 warp_cnt[kPartBlock / 32][kMaxRanks];
+  u32 warp_off[kPartBlock / 32][kMaxRanks];
+  u32 bin_start[kMaxRanks + 1];  // exclusive scan of the tile's per-destination counts
+  u32 base[kMaxRanks];           // tile's first slot inside each destination bucket
+  u32 tile;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kPartBlock)
 partition_kernel(const u32* __restrict__ keys, const T* __restrict__ x, const T* __restrict__ y,
                  u32 n, u32 gid_base, splitters_t sp, dests_t<T> dst, u64* __restrict__ desc,
                  u32* __restrict__ ticket)
 {
-  __shared__ u32 s_tile;
-  __shared__ u32 s_warp_cnt[kPartBlock / 32][kMaxRanks];
-  __shared__ u32 s_warp_off[kPartBlock / 32][kMaxRanks];
-  __shared__ u32 s_base[kMaxRanks];
+  extern __shared__ __align__(16) unsigned char part_smem_raw[];
+  part_smem<T>& sm = *reinterpret_cast<part_smem<T>*>(part_smem_raw);
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int const R   = sp.n_ranks;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
   __syncthreads();
-  u32 const tile = s_tile;
+  u32 const tile = sm.tile;
   // blocked-by-warp layout keeps the original order: warp w owns items [w*IPT*32, (w+1)*IPT*32)
-  u32 const warp_base = tile * kPartTile + warp * (kPartIPT * 32);
+  u32 const tile_base = tile * kPartTile;
+  u32 const warp_base = tile_base + warp * (kPartIPT * 32);
+  u32 const valid     = min((u32)kPartTile, n - tile_base);
   u32 const lt        = lanemask_lt();
 
   int dest[kPartIPT];
@@ -111,25 +125,22 @@ partition_kernel(const u32* __restrict__ keys, const T* __restrict__ x, const T*
     dest[i]       = idx < n ? dest_of(__ldcs(keys + idx), sp) : -1;
     rank[i]       = 0;
     for (int r = 0; r < R; ++r) {
-      u32 const m = __ballot_sync(0xffffffffu, dest[i] == r);
+      u32 const m      = __ballot_sync(0xffffffffu, dest[i] == r);
       u32 const before = __shfl_sync(0xffffffffu, cnt, r);
       if (dest[i] == r) rank[i] = before + __popc(m & lt);
       if (lane == r) cnt += __popc(m);
     }
   }
-  if (lane < R) s_warp_cnt[warp][lane] = cnt;
+  if (lane < R) sm.warp_cnt[warp][lane] = cnt;
   __syncthreads();
-  if (tid < R) {
-    u32 sum = 0;
-    for (int w = 0; w < kPartBlock / 32; ++w) {
-      s_warp_off[w][tid] = sum;
-      sum += s_warp_cnt[w][tid];
-    }
-  }
-  // per-destination chained scan over tiles (descriptor column = destination)
+  // per-destination totals, warp offsets and the chained scan over tiles (column = destination)
   if (tid < R) {
     u32 total = 0;
-    for (int w = 0; w < kPartBlock / 32; ++w) total += s_warp_cnt[w][tid];
+    for (int w = 0; w < kPartBlock / 32; ++w) {
+      sm.warp_off[w][tid] = total;
+      total += sm.warp_cnt[w][tid];
+    }
+    sm.bin_start[tid + 1] = total;  // turned into a prefix below
     u64* const col = desc + tid;
     u32 excl       = 0;
     if (tile == 0) {
@@ -151,19 +162,35 @@ partition_kernel(const u32* __restrict__ keys, const T* __restrict__ x, const T*
       }
       st_relaxed_u64(col + (u64)tile * kMaxRanks, lb_pack(3u, excl + total));
     }
-    s_base[tid] = excl;
+    sm.base[tid] = excl;
   }
   __syncthreads();
+  if (tid == 0) {
+    sm.bin_start[0] = 0;
+    for (int r = 0; r < R; ++r) sm.bin_start[r + 1] += sm.bin_start[r];
+  }
+  __syncthreads();
+  // stage the tile ordered by (destination, original order)
 #pragma unroll
   for (int i = 0; i < kPartIPT; ++i) {
     if (dest[i] >= 0) {
-      u32 const idx = warp_base + i * 32 + lane;
-      int const d   = dest[i];
-      u32 const o   = s_base[d] + s_warp_off[warp][d] + rank[i];
-      dst.x[d][o]   = __ldcs(x + idx);
-      dst.y[d][o]   = __ldcs(y + idx);
-      dst.gid[d][o] = gid_base + idx;
+      u32 const idx  = warp_base + i * 32 + lane;
+      int const d    = dest[i];
+      u32 const slot = sm.bin_start[d] + sm.warp_off[warp][d] + rank[i];
+      sm.x[slot]     = __ldcs(x + idx);
+      sm.y[slot]     = __ldcs(y + idx);
+      sm.gid[slot]   = gid_base + idx;
     }
+  }
+  __syncthreads();
+  // coalesced per-destination runs out of shared memory
+  for (u32 j = tid; j < valid; j += kPartBlock) {
+    int d = 0;
+    while (d + 1 < R && j >= sm.bin_start[d + 1]) ++d;
+    u32 const o   = sm.base[d] + (j - sm.bin_start[d]);
+    dst.x[d][o]   = sm.x[j];
+    dst.y[d][o]   = sm.y[j];
+    dst.gid[d][o] = sm.gid[j];
   }
 }
 
@@ -186,8 +213,18 @@ void partition_t(const u32* keys, const void* x, const void* y, u64 n, u32 gid_b
   dev_buf<u32> ticket(1, s);
   BSJ_CUDA_TRY(cudaMemsetAsync(desc.get(), 0, desc.size() * sizeof(u64), s));
   BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
-  partition_kernel<T><<<tiles, kPartBlock, 0, s>>>(keys, (const T*)x, (const T*)y, (u32)n,
-                                                   gid_base, sp, dst, desc.get(), ticket.get());
+  static bool attr_set = false;
+  if (!attr_set) {
+    BSJ_CUDA_TRY(cudaFuncSetAttribute(partition_kernel<float>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(part_smem<float>)));
+    BSJ_CUDA_TRY(cudaFuncSetAttribute(partition_kernel<double>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(part_smem<double>)));
+    attr_set = true;
+  }
+  partition_kernel<T><<<tiles, kPartBlock, sizeof(part_smem<T>), s>>>(
+    keys, (const T*)x, (const T*)y, (u32)n, gid_base, sp, dst, desc.get(), ticket.get());
   BSJ_CHECK_LAUNCH();
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
 }

@@ -307,18 +307,30 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     out = {"base": base, "counts": counts, "rows_per_rank": hits}
     prof.mark("global_indices")
     if gather_pairs:
-        gathered = {}
-        for i, k in enumerate(names):
-            gathered[k], _ = _all_gather_varlen(comp[k], dist, group, [s_[2 + i] for s_ in stats])
+        # one packed byte buffer per rank -> R broadcasts in total (not R per array)
+        def _bytes(t):
+            return t.contiguous().view(torch.uint8)
+
+        sizes_b = [[s_[2 + i] * comp[k].element_size() for i, k in enumerate(names)]
+                   for s_ in stats]
+        pad = [[(-b) % 16 for b in row] for row in sizes_b]  # keep every array 16-byte aligned
+        packed = torch.cat([torch.cat([_bytes(comp[k]),
+                                       torch.zeros(pad[rank][i], dtype=torch.uint8, device=dev)])
+                            for i, k in enumerate(names)]) if names else \
+            torch.empty(0, dtype=torch.uint8, device=dev)
+        tot_b = [sum(b + p_ for b, p_ in zip(sizes_b[r], pad[r])) for r in range(world)]
+        allb, _ = _all_gather_varlen(packed, dist, group, tot_b)
         total = sum(hits)
         out_poly = torch.empty(total, dtype=torch.int32, device=dev)
         out_point = torch.empty(total, dtype=torch.int32, device=dev)
-        row = 0
+        row, boff = 0, 0
         for r in range(world):
-            part = {}
+            part, o = {}, boff
             for i, k in enumerate(names):
-                o = sum(s_[2 + i] for s_ in stats[:r])
-                part[k] = gathered[k][o: o + stats[r][2 + i]]
+                nb = sizes_b[r][i]
+                part[k] = allb[o: o + nb].view(comp[k].dtype)
+                o += nb + pad[r][i]
+            boff += tot_b[r]
             if hits[r]:
                 expand(part, hits[r], sum(counts[:r]), out_poly[row: row + hits[r]],
                        out_point[row: row + hits[r]])
