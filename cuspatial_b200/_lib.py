@@ -130,7 +130,8 @@ def set_profiling(on):
 
 
 def get_profile():
-    names = (C.c_char_p * 64)()
-    ms = (C.c_float * 64)()
-    n = lib().bsj_get_profile(names, ms, 64)
+    cap = 8192
+    names = (C.c_char_p * cap)()
+    ms = (C.c_float * cap)()
+    n = lib().bsj_get_profile(names, ms, cap)
     return [(names[i].decode(), float(ms[i])) for i in range(n)]

@@ -256,7 +256,8 @@ void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32*
     int const bits = bits_for(n_boxes ? n_boxes - 1 : 0);
     sort_workspace_reset(ws, s);
     sort_histogram(hit_box.get(), p, 0, bits, ws, s);
-    sort_passes(hit_box.get(), hit_node.get(), false, k2.get(), v2.get(), p, 0, bits, ws, s, &in_a);
+    sort_passes(hit_box.get(), hit_node.get(), false, k2.get(), v2.get(), p, 0, bits, ws, s, &in_a,
+                "pair_sort_pass");
   }
   u32* box_sorted  = in_a ? hit_box.get() : k2.get();
   u32* node_sorted = in_a ? hit_node.get() : v2.get();
@@ -270,7 +271,8 @@ void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32*
     sort_workspace_reset(ws, s);
     sort_histogram(okeys.get(), p, 0, 32, ws, s);
     // values = iota; spare_v / perm_b are the value ping-pong buffers
-    sort_passes(okeys.get(), spare_v, true, spare_k, perm_b.get(), p, 0, 32, ws, s, &in_a);
+    sort_passes(okeys.get(), spare_v, true, spare_k, perm_b.get(), p, 0, 32, ws, s, &in_a,
+                "pair_sort_pass");
   }
   u32* perm = in_a ? spare_v : perm_b.get();
   gather_pairs_kernel<<<div_up(p, 256), 256, 0, s>>>(perm, box_sorted, node_sorted, (u32)p,

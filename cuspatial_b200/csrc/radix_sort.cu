@@ -241,7 +241,7 @@ void sort_histogram(const u32* keys, u64 n, int begin_bit, int end_bit, sort_wor
 
 void sort_passes(u32* keys_a, u32* vals_a, bool iota_values, u32* keys_b, u32* vals_b, u64 n,
                  int begin_bit, int end_bit, sort_workspace& ws, cudaStream_t s,
-                 bool* result_in_a)
+                 bool* result_in_a, const char* profile_label)
 {
   set_kernel_attrs();
   int const passes = passes_for_bits(begin_bit, end_bit);
@@ -266,7 +266,7 @@ void sort_passes(u32* keys_a, u32* vals_a, bool iota_values, u32* keys_b, u32* v
         ws.lookback.get(), ws.tickets.get() + p, tag_agg, tag_pre);
     }
     BSJ_CHECK_LAUNCH();
-    prof_mark("onesweep_pass");
+    prof_mark(profile_label);
     in_a = !in_a;
   }
   *result_in_a = in_a;

@@ -58,6 +58,6 @@ void sort_histogram(const u32* keys, u64 n, int begin_bit, int end_bit, sort_wor
 // pass runs (it becomes a ping-pong target).
 void sort_passes(u32* keys_a, u32* vals_a, bool iota_values, u32* keys_b, u32* vals_b, u64 n,
                  int begin_bit, int end_bit, sort_workspace& ws, cudaStream_t s,
-                 bool* result_in_a);
+                 bool* result_in_a, const char* profile_label = "onesweep_pass");
 
 }  // namespace bsj
