@@ -139,10 +139,33 @@ __device__ bool pip_reference(T px, T py, const u32* __restrict__ ring_offsets, 
 template <typename T>
 struct poly_meta {
   T xmin, ymin, xmax, ymax;
+  T inv_h;  // n_slabs / (ymax - ymin)
   u32 ring_begin, ring_end;
-  u32 safe;  // every coordinate / edge delta "comfy": exact edge skipping is allowed
-  u32 pad;
+  u32 safe;      // every coordinate / edge delta "comfy": exact edge skipping is allowed
+  u32 n_verts;   // vertices over all rings
+  u32 n_slabs;   // y-slab edge index (0 = none: unsafe polygon)
+  u32 slab_base; // first slab of this polygon in the global slab arrays
+  u32 n_vertical, vert_begin;  // vertical edges (x-only rule of the reference) and their list
 };
+
+template <typename T>
+struct edge_rec {  // edge b -> a of the reference's walk (b = previous vertex of the ring)
+  T ax, ay, bx, by;
+};
+
+constexpr u32 kFirstFlag = 0x80000000u;
+constexpr u32 kMaxSlabs  = 2048;
+
+// floor((y - ymin) * inv_h) clamped to the polygon's slabs; monotone in y, which is all the
+// build/query consistency needs (two overlapping y-intervals map to overlapping slab intervals)
+template <typename T>
+__device__ __forceinline__ u32 slab_of(T y, const poly_meta<T>& m)
+{
+  T const f = (y - m.ymin) * m.inv_h;
+  if (!(f > (T)0)) return 0u;
+  if (f >= (T)m.n_slabs) return m.n_slabs - 1;
+  return (u32)f;
+}
 
 // one warp per polygon
 template <typename T>
@@ -157,6 +180,7 @@ poly_meta_kernel(const u32* __restrict__ poly_offsets, u32 n_poly,
   u32 const r0 = poly_offsets[p], r1 = poly_offsets[p + 1];
   T xmin = fpp<T>::inf(), ymin = fpp<T>::inf(), xmax = -fpp<T>::inf(), ymax = -fpp<T>::inf();
   bool safe = r0 <= r1 && r1 <= n_rings;
+  u32 nv = 0, nvert = 0;
   if (safe) {
     for (u32 r = r0; r < r1; ++r) {
       u32 const v0 = ring_offsets[r], v1 = ring_offsets[r + 1];
@@ -164,6 +188,7 @@ poly_meta_kernel(const u32* __restrict__ poly_offsets, u32 n_poly,
         safe = false;
         break;
       }
+      nv += v1 - v0;
       for (u32 i = v0 + lane; i < v1; i += 32) {
         u32 const pr = i == v0 ? v1 - 1 : i - 1;
         T const ax = vx[i], ay = vy[i], bx = vx[pr], by = vy[pr];
@@ -171,6 +196,7 @@ poly_meta_kernel(const u32* __restrict__ poly_offsets, u32 n_poly,
         ymin = fmin(ymin, ay); ymax = fmax(ymax, ay);
         safe = safe && comfy(ax) && comfy(ay) && comfy_delta(fpp<T>::sub(bx, ax)) &&
                comfy_delta(fpp<T>::sub(by, ay));
+        nvert += (ax == bx && ay != by);
       }
     }
   }
@@ -180,15 +206,107 @@ poly_meta_kernel(const u32* __restrict__ poly_offsets, u32 n_poly,
     ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
     xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
     ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    nvert += __shfl_xor_sync(0xffffffffu, nvert, o);
   }
   safe = __all_sync(0xffffffffu, safe);
   if (lane == 0) {
     poly_meta<T> m;
     m.xmin = xmin; m.ymin = ymin; m.xmax = xmax; m.ymax = ymax;
-    m.ring_begin = r0; m.ring_end = r1; m.safe = safe ? 1u : 0u; m.pad = 0;
+    m.ring_begin = r0; m.ring_end = r1; m.safe = safe ? 1u : 0u;
+    m.n_verts = nv;
+    // about two edges per slab: a quadrant-sized query then touches a handful of entries
+    u32 ns = 0;
+    if (safe && nv > 0) {
+      ns = 1;
+      while (ns < kMaxSlabs && ns * 2 < nv) ns <<= 1;
+    }
+    T const h = ymax - ymin;
+    m.n_slabs = ns;
+    m.inv_h   = (ns && h > (T)0) ? (T)ns / h : (T)0;
+    m.slab_base = 0; m.n_vertical = safe ? nvert : 0u; m.vert_begin = 0;
     meta[p] = m;
   }
 }
+
+// exclusive scans over the polygons (slab bases, vertical-list bases); one block.
+// totals[0] = total slabs, totals[1] = total vertical edges
+template <typename T>
+__global__ void __launch_bounds__(1024)
+poly_scan_kernel(poly_meta<T>* __restrict__ meta, u32 n_poly, u32* __restrict__ totals)
+{
+  __shared__ u32 s_a[32], s_b[32];
+  __shared__ u32 carry_a, carry_b;
+  int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_a = carry_b = 0;
+  __syncthreads();
+  for (u32 base = 0; base < n_poly; base += 1024) {
+    u32 const i = base + tid;
+    u32 const a = i < n_poly ? meta[i].n_slabs : 0u, b = i < n_poly ? meta[i].n_vertical : 0u;
+    u32 const ia = warp_inclusive_scan(a), ib = warp_inclusive_scan(b);
+    if (lane == 31) { s_a[warp] = ia; s_b[warp] = ib; }
+    __syncthreads();
+    u32 wa = 0, wb = 0, ta = 0, tb = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) { wa += s_a[w]; wb += s_b[w]; }
+      ta += s_a[w]; tb += s_b[w];
+    }
+    if (i < n_poly) {
+      meta[i].slab_base  = carry_a + wa + ia - a;
+      meta[i].vert_begin = carry_b + wb + ib - b;
+    }
+    __syncthreads();
+    if (tid == 0) { carry_a += ta; carry_b += tb; }
+    __syncthreads();
+  }
+  if (tid == 0) { totals[0] = carry_a; totals[1] = carry_b; }
+}
+
+// Edge records + y-slab index, one warp per polygon.  FILL = false: write edge records, count
+// slab entries and list vertical edges; FILL = true: write the entries (order inside a slab is
+// arbitrary -- crossings XOR and on-edge ORs commute, the result does not depend on it).
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(128)
+slab_build_kernel(const poly_meta<T>* __restrict__ meta, u32 n_poly,
+                  const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
+                  const T* __restrict__ vy, edge_rec<T>* __restrict__ edges,
+                  u32* __restrict__ slab_count, const u32* __restrict__ slab_start,
+                  u32* __restrict__ entries, u32* __restrict__ vert_edges,
+                  u32* __restrict__ vert_cursor)
+{
+  u32 const p    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  u32 const lane = lane_id();
+  if (p >= n_poly) return;
+  poly_meta<T> const m = meta[p];
+  if (m.n_slabs == 0) return;
+  for (u32 r = m.ring_begin; r < m.ring_end; ++r) {
+    u32 const v0 = ring_offsets[r], v1 = ring_offsets[r + 1];
+    for (u32 i = v0 + lane; i < v1; i += 32) {
+      u32 const pr = i == v0 ? v1 - 1 : i - 1;
+      T const ax = vx[i], ay = vy[i], bx = vx[pr], by = vy[pr];
+      if (!FILL) edges[i] = edge_rec<T>{ax, ay, bx, by};
+      if (ax == bx && ay == by) continue;  // degenerate: skipped by the reference
+      T const dl  = fpp<T>::eps() * fmax(fabs(ay), fabs(by));
+      u32 const s0 = slab_of<T>(fmin(ay, by) - dl, m), s1 = slab_of<T>(fmax(ay, by) + dl, m);
+      for (u32 sl = s0; sl <= s1; ++sl) {
+        if (!FILL) {
+          atomicAdd(&slab_count[m.slab_base + sl], 1u);
+        } else {
+          u32 const at = atomicAdd(&slab_count[m.slab_base + sl], 1u);
+          entries[slab_start[m.slab_base + sl] + at] = i | (sl == s0 ? kFirstFlag : 0u);
+        }
+      }
+      if (!FILL && ax == bx) vert_edges[m.vert_begin + atomicAdd(&vert_cursor[p], 1u)] = i;
+    }
+  }
+}
+
+template <typename T>
+struct edge_index {  // device view of the per-call polygon edge index
+  const edge_rec<T>* edges;
+  const u32* slab_start;
+  const u32* entries;
+  const u32* vert_edges;
+};
 
 // ---------------------------------------------------------------------------------------------
 // Whole-quadrant classification from the cell rectangle (optional bsj_grid hint).
@@ -224,11 +342,10 @@ __device__ __forceinline__ u32 undilate16p(u32 v)
 // warp-cooperative; all lanes return the same class
 template <typename T>
 __device__ int classify_quadrant(const grid_info& g, u32 key, u32 level, const poly_meta<T>& m,
-                                 const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
-                                 const T* __restrict__ vy)
+                                 const edge_index<T>& ix)
 {
   int const sh = g.max_depth - 1 - (int)level;
-  if (!g.valid || !m.safe || sh < 0) return kClsBoundary;
+  if (!g.valid || !m.safe || sh < 0 || m.n_slabs == 0) return kClsBoundary;
   // the last cell also receives every out-of-box point, whatever its coordinates
   if (g.has_oob && level < 16 && key == ((1u << (2 * (level + 1))) - 1u)) return kClsBoundary;
   double const ls = g.scale * (double)(1u << sh);
@@ -249,28 +366,32 @@ __device__ int classify_quadrant(const grid_info& g, u32 key, u32 level, const p
   u32 const lane = lane_id();
   bool near  = false;
   u32 cross  = 0;
-  for (u32 ring = m.ring_begin; ring < m.ring_end; ++ring) {
-    u32 const v0 = ring_offsets[ring], v1 = ring_offsets[ring + 1];
-    u32 const nv = v1 - v0;
-    for (u32 e = lane; e < nv; e += 32) {
-      u32 const pr = e == 0 ? nv - 1 : e - 1;
-      T const ax = __ldg(vx + v0 + e), ay = __ldg(vy + v0 + e);
-      T const bx = __ldg(vx + v0 + pr), by = __ldg(vy + v0 + pr);
-      if (ax == bx && ay == by) continue;  // degenerate segment: skipped by the reference
-      double const d = eps * fmax(fmax(fabs((double)ax), fabs((double)bx)),
-                                  fmax(fabs((double)ay), fabs((double)by)));
-      double const lx = fmin((double)ax, (double)bx) - d, hx = fmax((double)ax, (double)bx) + d;
-      double const ly = fmin((double)ay, (double)by) - d, hy = fmax((double)ay, (double)by) + d;
-      bool const overlap = !(hx < ex0 || lx > ex1 || hy < ey0 || ly > ey1);
-      bool const vert    = ax == bx && (double)ax >= ex0 && (double)ax <= ex1;
-      near = near || overlap || vert;
-      bool const f1 = ay > cy, f0 = by > cy;
-      if (f1 != f0) {
-        T const u = fpp<T>::mul(fpp<T>::sub(bx, ax), fpp<T>::sub(cy, ay));
-        T const v = fpp<T>::mul(fpp<T>::sub(cx, ax), fpp<T>::sub(by, ay));
-        cross ^= (u32)((v < u) != f1);
-      }
+  // edges whose (tolerance-widened) y-range meets the rectangle's: slabs q0..q1 of the index.
+  // An edge listed in several slabs is taken once: in slab q0, or where it is flagged "first".
+  u32 const q0 = slab_of<T>((T)ey0, m), q1 = slab_of<T>((T)ey1, m);
+  u32 const kbeg = __ldg(ix.slab_start + m.slab_base + q0);
+  u32 const kmid = __ldg(ix.slab_start + m.slab_base + q0 + 1);
+  u32 const kend = __ldg(ix.slab_start + m.slab_base + q1 + 1);
+  for (u32 k = kbeg + lane; k < kend; k += 32) {
+    u32 const ent = __ldg(ix.entries + k);
+    if (k >= kmid && !(ent & kFirstFlag)) continue;
+    edge_rec<T> const e = ix.edges[ent & ~kFirstFlag];
+    double const d = eps * fmax(fmax(fabs((double)e.ax), fabs((double)e.bx)),
+                                fmax(fabs((double)e.ay), fabs((double)e.by)));
+    double const lx = fmin((double)e.ax, (double)e.bx) - d, hx = fmax((double)e.ax, (double)e.bx) + d;
+    double const ly = fmin((double)e.ay, (double)e.by) - d, hy = fmax((double)e.ay, (double)e.by) + d;
+    near = near || !(hx < ex0 || lx > ex1 || hy < ey0 || ly > ey1);
+    bool const f1 = e.ay > cy, f0 = e.by > cy;
+    if (f1 != f0) {
+      T const u = fpp<T>::mul(fpp<T>::sub(e.bx, e.ax), fpp<T>::sub(cy, e.ay));
+      T const v = fpp<T>::mul(fpp<T>::sub(cx, e.ax), fpp<T>::sub(e.by, e.ay));
+      cross ^= (u32)((v < u) != f1);
     }
+  }
+  // vertical edges reject points with the same x at ANY y
+  for (u32 k = lane; k < m.n_vertical; k += 32) {
+    T const ax = ix.edges[__ldg(ix.vert_edges + m.vert_begin + k)].ax;
+    near = near || ((double)ax >= ex0 && (double)ax <= ex1);
   }
   if (__any_sync(0xffffffffu, near)) return kClsBoundary;
   return (__popc(__ballot_sync(0xffffffffu, cross & 1u)) & 1) ? kClsInside : kClsOutside;
@@ -292,6 +413,13 @@ pair_prep_kernel(const u32* __restrict__ pair_quad, u32 n_pairs, const u32* __re
   pair_off[j]   = q < num_nodes ? offset[q] : 0u;
   words[j]      = len / 32 + ((len & 31) != 0);
   heads[j]      = (j == 0 || pair_quad[j - 1] != q) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+narrow_u64_kernel(const u64* __restrict__ in, u32* __restrict__ out, u32 n)
+{
+  u32 const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (u32)in[i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -322,7 +450,8 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
                 const T* __restrict__ vy, const u64* __restrict__ wbase,
                 u32* __restrict__ mask_words, u32* __restrict__ hits, u32* __restrict__ ticket,
                 int force_reference, const u32* __restrict__ node_key,
-                const u8* __restrict__ node_level, grid_info grid, u8* __restrict__ cls)
+                const u8* __restrict__ node_level, grid_info grid, u8* __restrict__ cls,
+                edge_index<T> ix)
 {
   u32 const lane   = lane_id();
   u32 const n_runs = (u32)*n_runs_ptr;
@@ -358,18 +487,19 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
         int c          = kClsOutside;
         if (poly < n_poly) {
           poly_meta<T> const m = meta[poly];
-          c = (grid.valid && !force_reference)
-                ? classify_quadrant<T>(grid, nkey, nlev, m, ring_offsets, vx, vy)
+          c = (grid.valid && force_reference != 1)
+                ? classify_quadrant<T>(grid, nkey, nlev, m, ix)
                 : kClsBoundary;
         }
         if (lane == 0) {
           cls[j] = (u8)c;
           if (c != kClsBoundary) hits[j] = c == kClsInside ? nvalid : 0u;
+          else if (force_reference == 2) hits[j] = 0u;
         }
         need_points = need_points || c == kClsBoundary;
       }
     }
-    if (!need_points) continue;
+    if (!need_points || force_reference == 2) continue;  // 2: timing experiment, classify only
     __syncwarp();  // cls[] written by lane 0 is read by every lane below
 
     for (u32 base = 0; base < len; base += kPipTile) {
@@ -412,7 +542,7 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
         tx1 = fmax(tx1, __shfl_xor_sync(0xffffffffu, tx1, o));
         ty1 = fmax(ty1, __shfl_xor_sync(0xffffffffu, ty1, o));
       }
-      bool const tile_safe = __all_sync(0xffffffffu, pts_ok) && !force_reference;
+      bool const tile_safe = __all_sync(0xffffffffu, pts_ok) && force_reference != 1;
       u32 const tile_words = (min(len - base, (u32)kPipTile) + 31) / 32;  // <= 8
 
       for (u32 j = j0; j < j1; ++j) {
@@ -427,48 +557,91 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
                               tx0 > m.xmax + mx;
             if (!miss) {
               u32 within = 0, onedge = 0;
-              for (u32 ring = m.ring_begin; ring < m.ring_end; ++ring) {
-                u32 const v0 = ring_offsets[ring], v1 = ring_offsets[ring + 1];
-                u32 const nv = v1 - v0;
-                for (u32 c0 = 0; c0 < nv; c0 += 32) {
-                  u32 const e    = c0 + lane;
-                  bool const has = e < nv;
+              // evaluate one edge (held by lane `src`) against this lane's points, with the
+              // reference's own arithmetic (is_point_in_polygon.cuh:60-96)
+              auto eval_edges = [&](u32 em, T ax, T ay, T bx, T by) {
+                while (em) {
+                  int const src = __ffs(em) - 1;
+                  em &= em - 1;
+                  T const eax = __shfl_sync(0xffffffffu, ax, src);
+                  T const eay = __shfl_sync(0xffffffffu, ay, src);
+                  T const ebx = __shfl_sync(0xffffffffu, bx, src);
+                  T const eby = __shfl_sync(0xffffffffu, by, src);
+                  T const run  = fpp<T>::sub(ebx, eax);
+                  T const rise = fpp<T>::sub(eby, eay);
+                  T const lo = fmin(eax, ebx), hi = fmax(eax, ebx);
+#pragma unroll
+                  for (int i = 0; i < kPPL; ++i) {
+                    T const rtp  = fpp<T>::sub(y[i], eay);
+                    T const rntp = fpp<T>::sub(x[i], eax);
+                    T const u    = fpp<T>::mul(run, rtp);
+                    T const v    = fpp<T>::mul(rntp, rise);
+                    if (lo <= x[i] && x[i] <= hi) {
+                      if (float_equal(u, v)) onedge |= 1u << i;
+                    }
+                    bool const y1 = eay > y[i], y0 = eby > y[i];
+                    bool const cross = (y1 != y0) && ((v < u) != y1);
+                    within ^= (u32)cross << i;
+                  }
+                }
+              };
+              if (m.n_slabs) {
+                // candidate edges from the y-slab index (slabs covering the tile's y-range)
+                u32 const q0 = slab_of<T>(ty0, m), q1 = slab_of<T>(ty1, m);
+                u32 const kbeg = __ldg(ix.slab_start + m.slab_base + q0);
+                u32 const kmid = __ldg(ix.slab_start + m.slab_base + q0 + 1);
+                u32 const kend = __ldg(ix.slab_start + m.slab_base + q1 + 1);
+                for (u32 k0 = kbeg; k0 < kend; k0 += 32) {
+                  u32 const k = k0 + lane;
                   T ax = 0, ay = 0, bx = 0, by = 0;
                   bool rel = false;
-                  if (has) {
-                    u32 const pr = e == 0 ? nv - 1 : e - 1;
-                    ax = __ldg(vx + v0 + e);  ay = __ldg(vy + v0 + e);
-                    bx = __ldg(vx + v0 + pr); by = __ldg(vy + v0 + pr);
+                  if (k < kend) {
+                    u32 const ent = __ldg(ix.entries + k);
+                    if (k < kmid || (ent & kFirstFlag)) {
+                      edge_rec<T> const e = ix.edges[ent & ~kFirstFlag];
+                      ax = e.ax; ay = e.ay; bx = e.bx; by = e.by;
+                      T const ylo = fmin(ay, by), yhi = fmax(ay, by);
+                      T const dl  = fpp<T>::eps() * fmax(fabs(ay), fabs(by));
+                      rel = ty1 >= ylo - dl && ty0 <= yhi + dl;
+                    }
+                  }
+                  eval_edges(__ballot_sync(0xffffffffu, rel), ax, ay, bx, by);
+                }
+                // vertical edges inside the tile's x-range whose y-range misses the tile
+                for (u32 k0 = 0; k0 < m.n_vertical; k0 += 32) {
+                  u32 const k = k0 + lane;
+                  T ax = 0, ay = 0, bx = 0, by = 0;
+                  bool rel = false;
+                  if (k < m.n_vertical) {
+                    edge_rec<T> const e = ix.edges[__ldg(ix.vert_edges + m.vert_begin + k)];
+                    ax = e.ax; ay = e.ay; bx = e.bx; by = e.by;
                     T const ylo = fmin(ay, by), yhi = fmax(ay, by);
                     T const dl  = fpp<T>::eps() * fmax(fabs(ay), fabs(by));
-                    bool const yrel = ty1 >= ylo - dl && ty0 <= yhi + dl;
-                    bool const vert = ax == bx && tx0 <= ax && ax <= tx1;
-                    rel = !(ax == bx && ay == by) && (yrel || vert);
+                    bool const yrel = ty1 >= ylo - dl && ty0 <= yhi + dl;  // taken above
+                    rel = !yrel && tx0 <= ax && ax <= tx1;
                   }
-                  u32 em = __ballot_sync(0xffffffffu, rel);
-                  while (em) {
-                    int const src = __ffs(em) - 1;
-                    em &= em - 1;
-                    T const eax = __shfl_sync(0xffffffffu, ax, src);
-                    T const eay = __shfl_sync(0xffffffffu, ay, src);
-                    T const ebx = __shfl_sync(0xffffffffu, bx, src);
-                    T const eby = __shfl_sync(0xffffffffu, by, src);
-                    T const run  = fpp<T>::sub(ebx, eax);
-                    T const rise = fpp<T>::sub(eby, eay);
-                    T const lo = fmin(eax, ebx), hi = fmax(eax, ebx);
-#pragma unroll
-                    for (int i = 0; i < kPPL; ++i) {
-                      T const rtp  = fpp<T>::sub(y[i], eay);
-                      T const rntp = fpp<T>::sub(x[i], eax);
-                      T const u    = fpp<T>::mul(run, rtp);
-                      T const v    = fpp<T>::mul(rntp, rise);
-                      if (lo <= x[i] && x[i] <= hi) {
-                        if (float_equal(u, v)) onedge |= 1u << i;
-                      }
-                      bool const y1 = eay > y[i], y0 = eby > y[i];
-                      bool const cross = (y1 != y0) && ((v < u) != y1);
-                      within ^= (u32)cross << i;
+                  eval_edges(__ballot_sync(0xffffffffu, rel), ax, ay, bx, by);
+                }
+              } else {
+                for (u32 ring = m.ring_begin; ring < m.ring_end; ++ring) {
+                  u32 const v0 = ring_offsets[ring], v1 = ring_offsets[ring + 1];
+                  u32 const nv = v1 - v0;
+                  for (u32 c0 = 0; c0 < nv; c0 += 32) {
+                    u32 const e    = c0 + lane;
+                    bool const has = e < nv;
+                    T ax = 0, ay = 0, bx = 0, by = 0;
+                    bool rel = false;
+                    if (has) {
+                      u32 const pr = e == 0 ? nv - 1 : e - 1;
+                      ax = __ldg(vx + v0 + e);  ay = __ldg(vy + v0 + e);
+                      bx = __ldg(vx + v0 + pr); by = __ldg(vy + v0 + pr);
+                      T const ylo = fmin(ay, by), yhi = fmax(ay, by);
+                      T const dl  = fpp<T>::eps() * fmax(fabs(ay), fabs(by));
+                      bool const yrel = ty1 >= ylo - dl && ty0 <= yhi + dl;
+                      bool const vert = ax == bx && tx0 <= ax && ax <= tx1;
+                      rel = !(ax == bx && ay == by) && (yrel || vert);
                     }
+                    eval_edges(__ballot_sync(0xffffffffu, rel), ax, ay, bx, by);
                   }
                 }
               }
@@ -632,7 +805,7 @@ int force_reference_mode()
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("BSJ_PIP_REFERENCE_LOOP");
-    v             = (e && e[0] == '1') ? 1 : 0;
+    v             = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;
   }
   return v;
 }
@@ -675,12 +848,31 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
     }
   }
   dev_buf<poly_meta<T>> meta(std::max<u32>(n_poly, 1), s);
-  if (n_poly) {
-    poly_meta_kernel<T><<<div_up((u64)n_poly * 32, 128), 128, 0, s>>>(
-      poly_offsets, n_poly, ring_offsets, (u32)(n_ring_offsets ? n_ring_offsets - 1 : 0),
-      (const T*)vx, (const T*)vy, (u32)n_verts, meta.get());
-    BSJ_CHECK_LAUNCH();
-  }
+  dev_buf<u32> idx_totals(2, s);
+  dev_buf<edge_rec<T>> edges(std::max<u64>(n_verts, 1), s);
+  dev_buf<u32> vert_cursor(std::max<u32>(n_poly, 1), s);
+  int const poly_grid = div_up((u64)std::max<u32>(n_poly, 1) * 32, 128);
+  poly_meta_kernel<T><<<poly_grid, 128, 0, s>>>(
+    poly_offsets, n_poly, ring_offsets, (u32)(n_ring_offsets ? n_ring_offsets - 1 : 0),
+    (const T*)vx, (const T*)vy, (u32)n_verts, meta.get());
+  BSJ_CHECK_LAUNCH();
+  poly_scan_kernel<T><<<1, 1024, 0, s>>>(meta.get(), n_poly, idx_totals.get());
+  BSJ_CHECK_LAUNCH();
+  BSJ_CUDA_TRY(cudaMemsetAsync(vert_cursor.get(), 0, vert_cursor.size() * sizeof(u32), s));
+  // sizes bounded without a host round trip: a polygon gets at most as many slabs as vertices
+  // (and at least one), and at most one vertical-list entry per vertex
+  u32 const total_slabs = (u32)std::min<u64>(n_verts + n_poly, 0xFFFFFFF0ull);
+  u32 const total_vertical = (u32)n_verts;
+  dev_buf<u32> slab_count(total_slabs + 1, s), vert_edges(std::max<u32>(total_vertical, 1), s);
+  dev_buf<u64> slab_start64(total_slabs + 1, s), entry_total(1, s);
+  dev_buf<u32> slab_start(total_slabs + 1, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(slab_count.get(), 0, slab_count.size() * sizeof(u32), s));
+  slab_build_kernel<T, false><<<poly_grid, 128, 0, s>>>(
+    meta.get(), n_poly, ring_offsets, (const T*)vx, (const T*)vy, edges.get(), slab_count.get(),
+    nullptr, nullptr, vert_edges.get(), vert_cursor.get());
+  BSJ_CHECK_LAUNCH();
+  exclusive_scan_u32_to_u64(slab_count.get(), slab_start64.get(), total_slabs + 1,
+                            entry_total.get(), s);
   c->n_pairs        = n_pairs;
   c->pair_offset    = oa.get<u32>(n_pairs);
   c->pair_length    = oa.get<u32>(n_pairs);
@@ -701,10 +893,22 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
   run_start_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(heads.get(), run_idx.get(), (u32)n_pairs,
                                                         totals.get() + 1, run_start.get());
   BSJ_CHECK_LAUNCH();
-  u64 h_tot[2] = {0, 0};
+  u64 h_tot[2] = {0, 0}, h_entries = 0;
   BSJ_CUDA_TRY(cudaMemcpyAsync(h_tot, totals.get(), 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  BSJ_CUDA_TRY(cudaMemcpyAsync(&h_entries, entry_total.get(), sizeof(u64), cudaMemcpyDeviceToHost, s));
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
   u64 const total_words = h_tot[0], n_runs = h_tot[1];
+  BSJ_EXPECTS(h_entries < 0xFFFFFFFFull, "polygon edge index too large");
+  dev_buf<u32> entries(std::max<u64>(h_entries, 1), s);
+  narrow_u64_kernel<<<div_up(total_slabs + 1, 256), 256, 0, s>>>(slab_start64.get(),
+                                                                 slab_start.get(), total_slabs + 1);
+  BSJ_CHECK_LAUNCH();
+  BSJ_CUDA_TRY(cudaMemsetAsync(slab_count.get(), 0, slab_count.size() * sizeof(u32), s));
+  slab_build_kernel<T, true><<<poly_grid, 128, 0, s>>>(
+    meta.get(), n_poly, ring_offsets, (const T*)vx, (const T*)vy, edges.get(), slab_count.get(),
+    slab_start.get(), entries.get(), vert_edges.get(), vert_cursor.get());
+  BSJ_CHECK_LAUNCH();
+  edge_index<T> ix{edges.get(), slab_start.get(), entries.get(), vert_edges.get()};
   prof_mark("pair_prep");
 
   c->n_words    = total_words;
@@ -715,7 +919,7 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
       pair_poly, pair_quad, run_start.get(), totals.get() + 1, length, offset, (u32)num_nodes,
       point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly, ring_offsets,
       (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words, c->pair_hits, ticket.get(),
-      force_reference_mode(), node_key, node_level, gi, c->pair_class);
+      force_reference_mode(), node_key, node_level, gi, c->pair_class, ix);
     BSJ_CHECK_LAUNCH();
   }
   prof_mark("pip_eval");

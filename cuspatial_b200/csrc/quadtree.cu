@@ -335,6 +335,19 @@ expand_level_kernel(const u32* __restrict__ keys, int L, int max_depth, u32 max_
   (void)done;
 }
 
+// one launch instead of five device-to-device copies
+__global__ void __launch_bounds__(256)
+copy_tree_kernel(const u32* __restrict__ k, const u8* __restrict__ l, const u8* __restrict__ f,
+                 const u32* __restrict__ n, const u32* __restrict__ o, u32 q, u32* __restrict__ ok,
+                 u8* __restrict__ ol, u8* __restrict__ of, u32* __restrict__ on,
+                 u32* __restrict__ oo)
+{
+  u32 const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q) {
+    ok[i] = k[i]; ol[i] = l[i]; of[i] = f[i]; on[i] = n[i]; oo[i] = o[i];
+  }
+}
+
 template <typename T>
 void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_max, double y_min,
                    double y_max, double scale_d, int max_depth, int passes, u32* keys, u32* hist,
@@ -480,11 +493,13 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
   out->is_internal_node = oa.get<u8>(q);
   out->length           = oa.get<u32>(q);
   out->offset           = oa.get<u32>(q);
-  BSJ_CUDA_TRY(cudaMemcpyAsync(out->key, tkey.get(), q * 4, cudaMemcpyDeviceToDevice, s));
-  BSJ_CUDA_TRY(cudaMemcpyAsync(out->level, tlevel.get(), q, cudaMemcpyDeviceToDevice, s));
-  BSJ_CUDA_TRY(cudaMemcpyAsync(out->is_internal_node, tint.get(), q, cudaMemcpyDeviceToDevice, s));
-  BSJ_CUDA_TRY(cudaMemcpyAsync(out->length, tlen.get(), q * 4, cudaMemcpyDeviceToDevice, s));
-  BSJ_CUDA_TRY(cudaMemcpyAsync(out->offset, toff.get(), q * 4, cudaMemcpyDeviceToDevice, s));
+  if (q) {
+    copy_tree_kernel<<<div_up(q, 256), 256, 0, s>>>(tkey.get(), tlevel.get(), tint.get(),
+                                                   tlen.get(), toff.get(), (u32)q, out->key,
+                                                   out->level, out->is_internal_node, out->length,
+                                                   out->offset);
+    BSJ_CHECK_LAUNCH();
+  }
   tm.mark("finalize");
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
   tm.finish();

@@ -9,8 +9,7 @@ constexpr int kWarps = kSortBlock / 32;
 
 // shared-memory layout of one onesweep CTA (dynamic)
 struct sort_smem {
-  u32 keys[kSortTile];
-  u32 vals[kSortTile];
+  uint2 kv[kSortTile];  // tile-sorted {key, value} slots: one 64-bit store / load per element
   // per-warp, per-digit {x: running count -> exclusive warp offset, y: match mask of the
   // current round}
   uint2 whist[kWarps * kRadixDigits];
@@ -161,20 +160,21 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
       st_relaxed_u64(col + (u64)tile * kRadixDigits, lb_pack(tag_pre, excl + my_total));
     }
     sm.gbase[tid] = digit_offsets[tid] + excl - bin_start;
+    // fold the digit's tile offset into every warp's offset: one random lookup per element
+    // in the placement below instead of two
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) sm.whist[w * kRadixDigits + tid].x += bin_start;
   }
   __syncthreads();
 
-  // ---- place keys (and values) at their tile-sorted slot in shared memory
-#pragma unroll
-  for (int i = 0; i < kSortIPT; ++i) {
-    u32 const d   = (key[i] >> shift) & 0xFFu;
-    u32 const pos = sm.bin_start[d] + wh[d].x + rank[i];
-    sm.keys[pos]  = key[i];
-    key[i]        = pos;  // reuse the register for the slot
-  }
+  // ---- place {key, value} at their tile-sorted slot in shared memory
   if (IOTA) {
 #pragma unroll
-    for (int i = 0; i < kSortIPT; ++i) sm.vals[key[i]] = warp_base + i * 32 + lane;
+    for (int i = 0; i < kSortIPT; ++i) {
+      u32 const d   = (key[i] >> shift) & 0xFFu;
+      u32 const pos = wh[d].x + rank[i];
+      sm.kv[pos]    = make_uint2(key[i], warp_base + i * 32 + lane);
+    }
   } else {
     u32 v[kSortIPT];
 #pragma unroll
@@ -183,7 +183,11 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
       v[i]          = idx < n ? ld_stream(vals_in + idx) : 0u;
     }
 #pragma unroll
-    for (int i = 0; i < kSortIPT; ++i) sm.vals[key[i]] = v[i];
+    for (int i = 0; i < kSortIPT; ++i) {
+      u32 const d   = (key[i] >> shift) & 0xFFu;
+      u32 const pos = wh[d].x + rank[i];
+      sm.kv[pos]    = make_uint2(key[i], v[i]);
+    }
   }
   __syncthreads();
 
@@ -192,10 +196,10 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
   for (int i = 0; i < kSortIPT; ++i) {
     u32 const j = i * kSortBlock + tid;
     if (j < valid) {
-      u32 const k   = sm.keys[j];
-      u32 const dst = sm.gbase[(k >> shift) & 0xFFu] + j;
-      keys_out[dst] = k;
-      vals_out[dst] = sm.vals[j];
+      uint2 const e = sm.kv[j];
+      u32 const dst = sm.gbase[(e.x >> shift) & 0xFFu] + j;
+      keys_out[dst] = e.x;
+      vals_out[dst] = e.y;
     }
   }
 }
