@@ -146,6 +146,48 @@ def run_reference(args):
     }))
 
 
+def run_bitmask(args):
+    """configs[2]: non-indexed point_in_polygon, 100 M fp64 points x 31 polygons, one B200."""
+    import torch
+
+    import cuspatial_b200 as cs
+    from cuspatial_b200 import _lib
+    from cuspatial_b200 import datagen as D
+
+    dev = torch.device("cuda", 0)
+    (po, ro, vx, vy), ext, _ = make_polygons()
+    polys = (torch.as_tensor(po[:32].astype("int32"), device=dev),
+             torch.as_tensor(ro.astype("int32"), device=dev),
+             torch.as_tensor(vx, device=dev), torch.as_tensor(vy, device=dev))
+    n = args.points
+    x, y = D.uniform_points_torch(n, ext, SEED, torch.float64, dev)
+    for _ in range(max(args.warmup, 1)):
+        m = cs.point_in_polygon_bitmask((x, y), polys)
+    inside = int((m != 0).sum())
+    torch.cuda.synchronize()
+    l0 = _lib.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        m = cs.point_in_polygon_bitmask((x, y), polys)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    peak, src = read_peaks()
+    gbs = n * (2 * 8 + 4) / (ms / 1e3) / 1e9
+    print(json.dumps({
+        "metric": "bitmask point_in_polygon points/sec", "value": n / (ms / 1e3),
+        "unit": "points/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[2]: %d uniform fp64 points x 31 polygons, bitmask API"
+                               % n, "points_in_some_polygon": inside},
+        "roofline": {"bound": "hbm", "kernel": "pip_bitmask", "achieved": gbs, "peak": peak,
+                     "unit": "GB/s", "frac": gbs / peak, "traffic": None, "peak_source": src},
+        "gpu_launches": int(_lib.kernel_launch_count() - l0),
+    }))
+
+
 def run_sharded(args, dist, dev, rank, world, x, y, polys, ext, scale):
     """N > 1: the distributed join (cuspatial_b200/multi_gpu.py).  Every rank holds an arbitrary
     shard of `--points` points; a step = keys + histogram all-reduce, Morton-range partition +
@@ -222,9 +264,14 @@ def main():
     ap.add_argument("--points", type=int, default=N_POINTS, help="points per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="join", choices=["join", "bitmask"],
+                    help="join = configs[1] (the headline); bitmask = configs[2], the non-indexed "
+                         "point_in_polygon API on 31 polygons (informational)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "bitmask":
+        return run_bitmask(args)
 
     import numpy as np
     import torch

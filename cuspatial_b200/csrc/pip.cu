@@ -301,6 +301,11 @@ slab_build_kernel(const poly_meta<T>* __restrict__ meta, u32 n_poly,
 }
 
 template <typename T>
+struct edge_index;
+template <typename T>
+struct polygon_index;  // owning builder, defined after the kernels
+
+template <typename T>
 struct edge_index {  // device view of the per-call polygon edge index
   const edge_rec<T>* edges;
   const u32* slab_start;
@@ -740,12 +745,45 @@ pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
 // ---------------------------------------------------------------------------------------------
 // bitmask point_in_polygon (<= 31 polygons): one thread per point
 // ---------------------------------------------------------------------------------------------
+// Exact predicate of ONE point against one indexed polygon: only the edges of the point's y-slab
+// (those whose tolerance-widened y-range contains y) can cross or lie under the point; a vertical
+// edge with the point's x rejects it at any y.  Same per-edge arithmetic as the reference.
+template <typename T>
+__device__ bool pip_indexed(T px, T py, const poly_meta<T>& m, const edge_index<T>& ix)
+{
+  for (u32 k = 0; k < m.n_vertical; ++k)
+    if (ix.edges[__ldg(ix.vert_edges + m.vert_begin + k)].ax == px) return false;
+  u32 const sl   = slab_of<T>(py, m);
+  u32 const kbeg = __ldg(ix.slab_start + m.slab_base + sl);
+  u32 const kend = __ldg(ix.slab_start + m.slab_base + sl + 1);
+  bool within = false;
+  for (u32 k = kbeg; k < kend; ++k) {
+    edge_rec<T> const e = ix.edges[__ldg(ix.entries + k) & ~kFirstFlag];
+    T const run  = fpp<T>::sub(e.bx, e.ax);
+    T const rise = fpp<T>::sub(e.by, e.ay);
+    T const rtp  = fpp<T>::sub(py, e.ay);
+    T const rntp = fpp<T>::sub(px, e.ax);
+    T const u    = fpp<T>::mul(run, rtp);
+    T const v    = fpp<T>::mul(rntp, rise);
+    if (fmin(e.ax, e.bx) <= px && px <= fmax(e.ax, e.bx)) {
+      if (float_equal(u, v)) return false;  // on an edge: outside, whatever the crossings say
+    }
+    bool const y1 = e.ay > py, y0 = e.by > py;
+    if (y1 != y0 && ((v < u) != y1)) within = !within;
+  }
+  return within;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bitmask point_in_polygon (<= 31 polygons): one thread per point
+// ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
 pip_bitmask_kernel(const T* __restrict__ px, const T* __restrict__ py, u64 n_points,
                    const poly_meta<T>* __restrict__ meta, u32 n_poly,
                    const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
-                   const T* __restrict__ vy, i32* __restrict__ out, int force_reference)
+                   const T* __restrict__ vy, i32* __restrict__ out, int force_reference,
+                   edge_index<T> ix)
 {
   __shared__ poly_meta<T> s_meta[31];
   for (u32 i = threadIdx.x; i < n_poly; i += blockDim.x) s_meta[i] = meta[i];
@@ -757,13 +795,18 @@ pip_bitmask_kernel(const T* __restrict__ px, const T* __restrict__ py, u64 n_poi
     i32 mask = 0;
     for (u32 p = 0; p < n_poly; ++p) {
       poly_meta<T> const& m = s_meta[p];
+      bool hit;
       if (p_ok && m.safe) {
         // exact rejections: no edge can straddle y outside [ymin, ymax); x beyond the widened
         // extent decides every crossing comparison with certainty (parity even => outside)
         T const mx = fpp<T>::eps() * fmax(fabs(m.xmin), fabs(m.xmax));
         if (y < m.ymin || y >= m.ymax || x < m.xmin - mx || x > m.xmax + mx) continue;
+        hit = m.n_slabs ? pip_indexed<T>(x, y, m, ix)
+                        : pip_reference<T>(x, y, ring_offsets, m.ring_begin, m.ring_end, vx, vy);
+      } else {
+        hit = pip_reference<T>(x, y, ring_offsets, m.ring_begin, m.ring_end, vx, vy);
       }
-      mask |= (i32)pip_reference<T>(x, y, ring_offsets, m.ring_begin, m.ring_end, vx, vy) << p;
+      mask |= (i32)hit << p;
     }
     __stcs(out + i, mask);
   }
@@ -799,6 +842,77 @@ poly_bbox_kernel(const u32* __restrict__ poly_offsets, u32 n_poly,
     ox0[p] = xmin; oy0[p] = ymin; ox1[p] = xmax; oy1[p] = ymax;
   }
 }
+
+// Builds (and owns) the per-call polygon metadata + y-slab edge index.  `finish()` needs one host
+// round trip (the number of index entries); callers merge it with a synchronisation they need
+// anyway by calling begin() early and finish() after their own cudaStreamSynchronize.
+template <typename T>
+struct polygon_index {
+  dev_buf<poly_meta<T>> meta;
+  dev_buf<edge_rec<T>> edges;
+  dev_buf<u32> idx_totals, vert_cursor, slab_count, vert_edges, slab_start, entries;
+  dev_buf<u64> slab_start64, entry_total;
+  u32 n_poly{0}, total_slabs{0};
+  int poly_grid{1};
+  const u32* ring_offsets{nullptr};
+  const T* vx{nullptr};
+  const T* vy{nullptr};
+  u64 h_entries{0};
+
+  void begin(const u32* poly_offsets, u64 n_poly_offsets, const u32* ring_off, u64 n_ring_offsets,
+             const void* vx_, const void* vy_, u64 n_verts, cudaStream_t s)
+  {
+    n_poly       = (u32)(n_poly_offsets ? n_poly_offsets - 1 : 0);
+    ring_offsets = ring_off;
+    vx           = (const T*)vx_;
+    vy           = (const T*)vy_;
+    meta.alloc(std::max<u32>(n_poly, 1), s);
+    idx_totals.alloc(2, s);
+    edges.alloc(std::max<u64>(n_verts, 1), s);
+    vert_cursor.alloc(std::max<u32>(n_poly, 1), s);
+    poly_grid = div_up((u64)std::max<u32>(n_poly, 1) * 32, 128);
+    poly_meta_kernel<T><<<poly_grid, 128, 0, s>>>(
+      poly_offsets, n_poly, ring_offsets, (u32)(n_ring_offsets ? n_ring_offsets - 1 : 0), vx, vy,
+      (u32)n_verts, meta.get());
+    BSJ_CHECK_LAUNCH();
+    poly_scan_kernel<T><<<1, 1024, 0, s>>>(meta.get(), n_poly, idx_totals.get());
+    BSJ_CHECK_LAUNCH();
+    BSJ_CUDA_TRY(cudaMemsetAsync(vert_cursor.get(), 0, vert_cursor.size() * sizeof(u32), s));
+    // sizes bounded without a host round trip: a polygon gets at most as many slabs as vertices
+    // (and at least one), and at most one vertical-list entry per vertex
+    total_slabs = (u32)std::min<u64>(n_verts + n_poly, 0xFFFFFFF0ull);
+    slab_count.alloc(total_slabs + 1, s);
+    vert_edges.alloc(std::max<u64>(n_verts, 1), s);
+    slab_start64.alloc(total_slabs + 1, s);
+    entry_total.alloc(1, s);
+    slab_start.alloc(total_slabs + 1, s);
+    BSJ_CUDA_TRY(cudaMemsetAsync(slab_count.get(), 0, slab_count.size() * sizeof(u32), s));
+    slab_build_kernel<T, false><<<poly_grid, 128, 0, s>>>(
+      meta.get(), n_poly, ring_offsets, vx, vy, edges.get(), slab_count.get(), nullptr, nullptr,
+      vert_edges.get(), vert_cursor.get());
+    BSJ_CHECK_LAUNCH();
+    exclusive_scan_u32_to_u64(slab_count.get(), slab_start64.get(), total_slabs + 1,
+                              entry_total.get(), s);
+    BSJ_CUDA_TRY(cudaMemcpyAsync(&h_entries, entry_total.get(), sizeof(u64),
+                                 cudaMemcpyDeviceToHost, s));
+  }
+  // the stream must have been synchronised after begin()
+  edge_index<T> finish(cudaStream_t s)
+  {
+    BSJ_EXPECTS(h_entries < 0xFFFFFFFFull, "polygon edge index too large");
+    entries.alloc(std::max<u64>(h_entries, 1), s);
+    narrow_u64_kernel<<<div_up(total_slabs + 1, 256), 256, 0, s>>>(slab_start64.get(),
+                                                                   slab_start.get(),
+                                                                   total_slabs + 1);
+    BSJ_CHECK_LAUNCH();
+    BSJ_CUDA_TRY(cudaMemsetAsync(slab_count.get(), 0, slab_count.size() * sizeof(u32), s));
+    slab_build_kernel<T, true><<<poly_grid, 128, 0, s>>>(
+      meta.get(), n_poly, ring_offsets, vx, vy, edges.get(), slab_count.get(), slab_start.get(),
+      entries.get(), vert_edges.get(), vert_cursor.get());
+    BSJ_CHECK_LAUNCH();
+    return edge_index<T>{edges.get(), slab_start.get(), entries.get(), vert_edges.get()};
+  }
+};
 
 int force_reference_mode()
 {
@@ -847,32 +961,9 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
                           std::fabs(grid->max_y - grid->min_y));
     }
   }
-  dev_buf<poly_meta<T>> meta(std::max<u32>(n_poly, 1), s);
-  dev_buf<u32> idx_totals(2, s);
-  dev_buf<edge_rec<T>> edges(std::max<u64>(n_verts, 1), s);
-  dev_buf<u32> vert_cursor(std::max<u32>(n_poly, 1), s);
-  int const poly_grid = div_up((u64)std::max<u32>(n_poly, 1) * 32, 128);
-  poly_meta_kernel<T><<<poly_grid, 128, 0, s>>>(
-    poly_offsets, n_poly, ring_offsets, (u32)(n_ring_offsets ? n_ring_offsets - 1 : 0),
-    (const T*)vx, (const T*)vy, (u32)n_verts, meta.get());
-  BSJ_CHECK_LAUNCH();
-  poly_scan_kernel<T><<<1, 1024, 0, s>>>(meta.get(), n_poly, idx_totals.get());
-  BSJ_CHECK_LAUNCH();
-  BSJ_CUDA_TRY(cudaMemsetAsync(vert_cursor.get(), 0, vert_cursor.size() * sizeof(u32), s));
-  // sizes bounded without a host round trip: a polygon gets at most as many slabs as vertices
-  // (and at least one), and at most one vertical-list entry per vertex
-  u32 const total_slabs = (u32)std::min<u64>(n_verts + n_poly, 0xFFFFFFF0ull);
-  u32 const total_vertical = (u32)n_verts;
-  dev_buf<u32> slab_count(total_slabs + 1, s), vert_edges(std::max<u32>(total_vertical, 1), s);
-  dev_buf<u64> slab_start64(total_slabs + 1, s), entry_total(1, s);
-  dev_buf<u32> slab_start(total_slabs + 1, s);
-  BSJ_CUDA_TRY(cudaMemsetAsync(slab_count.get(), 0, slab_count.size() * sizeof(u32), s));
-  slab_build_kernel<T, false><<<poly_grid, 128, 0, s>>>(
-    meta.get(), n_poly, ring_offsets, (const T*)vx, (const T*)vy, edges.get(), slab_count.get(),
-    nullptr, nullptr, vert_edges.get(), vert_cursor.get());
-  BSJ_CHECK_LAUNCH();
-  exclusive_scan_u32_to_u64(slab_count.get(), slab_start64.get(), total_slabs + 1,
-                            entry_total.get(), s);
+  polygon_index<T> pidx;
+  pidx.begin(poly_offsets, n_poly_offsets, ring_offsets, n_ring_offsets, vx, vy, n_verts, s);
+  auto& meta = pidx.meta;
   c->n_pairs        = n_pairs;
   c->pair_offset    = oa.get<u32>(n_pairs);
   c->pair_length    = oa.get<u32>(n_pairs);
@@ -893,22 +984,11 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
   run_start_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(heads.get(), run_idx.get(), (u32)n_pairs,
                                                         totals.get() + 1, run_start.get());
   BSJ_CHECK_LAUNCH();
-  u64 h_tot[2] = {0, 0}, h_entries = 0;
+  u64 h_tot[2] = {0, 0};
   BSJ_CUDA_TRY(cudaMemcpyAsync(h_tot, totals.get(), 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
-  BSJ_CUDA_TRY(cudaMemcpyAsync(&h_entries, entry_total.get(), sizeof(u64), cudaMemcpyDeviceToHost, s));
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
   u64 const total_words = h_tot[0], n_runs = h_tot[1];
-  BSJ_EXPECTS(h_entries < 0xFFFFFFFFull, "polygon edge index too large");
-  dev_buf<u32> entries(std::max<u64>(h_entries, 1), s);
-  narrow_u64_kernel<<<div_up(total_slabs + 1, 256), 256, 0, s>>>(slab_start64.get(),
-                                                                 slab_start.get(), total_slabs + 1);
-  BSJ_CHECK_LAUNCH();
-  BSJ_CUDA_TRY(cudaMemsetAsync(slab_count.get(), 0, slab_count.size() * sizeof(u32), s));
-  slab_build_kernel<T, true><<<poly_grid, 128, 0, s>>>(
-    meta.get(), n_poly, ring_offsets, (const T*)vx, (const T*)vy, edges.get(), slab_count.get(),
-    slab_start.get(), entries.get(), vert_edges.get(), vert_cursor.get());
-  BSJ_CHECK_LAUNCH();
-  edge_index<T> ix{edges.get(), slab_start.get(), entries.get(), vert_edges.get()};
+  edge_index<T> ix = pidx.finish(s);
   prof_mark("pair_prep");
 
   c->n_words    = total_words;
@@ -950,17 +1030,15 @@ void pip_bitmask_t(const void* px, const void* py, u64 n_points, const u32* poly
 {
   stage_timer tm(s);
   u32 const n_poly = (u32)(n_poly_offsets ? n_poly_offsets - 1 : 0);
-  dev_buf<poly_meta<T>> meta(std::max<u32>(n_poly, 1), s);
-  if (n_poly) {
-    poly_meta_kernel<T><<<div_up((u64)n_poly * 32, 128), 128, 0, s>>>(
-      poly_offsets, n_poly, ring_offsets, (u32)(n_ring_offsets ? n_ring_offsets - 1 : 0),
-      (const T*)vx, (const T*)vy, (u32)n_verts, meta.get());
-    BSJ_CHECK_LAUNCH();
-  }
+  polygon_index<T> pidx;
+  pidx.begin(poly_offsets, n_poly_offsets, ring_offsets, n_ring_offsets, vx, vy, n_verts, s);
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+  edge_index<T> ix = pidx.finish(s);
+  prof_mark("polygon_index");
   int const grid = (int)std::min<u64>((u64)kNumSMs * 16, (u64)div_up(n_points, 256));
   pip_bitmask_kernel<T><<<std::max(grid, 1), 256, 0, s>>>(
-    (const T*)px, (const T*)py, n_points, meta.get(), n_poly, ring_offsets, (const T*)vx,
-    (const T*)vy, out, force_reference_mode());
+    (const T*)px, (const T*)py, n_points, pidx.meta.get(), n_poly, ring_offsets, (const T*)vx,
+    (const T*)vy, out, force_reference_mode(), ix);
   BSJ_CHECK_LAUNCH();
   tm.mark("pip_bitmask");
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
