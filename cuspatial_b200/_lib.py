@@ -24,6 +24,7 @@ class bsj_grid(C.Structure):
         ("valid", C.c_int32), ("max_depth", C.c_int32),
         ("min_x", C.c_double), ("min_y", C.c_double), ("max_x", C.c_double), ("max_y", C.c_double),
         ("scale", C.c_double), ("has_nan", C.c_int32), ("has_out_of_bbox", C.c_int32),
+        ("sorted_keys", C.c_void_p), ("n_sorted_keys", C.c_uint64),
     ]
 
 
@@ -32,7 +33,7 @@ class bsj_quadtree(C.Structure):
         ("point_indices", C.c_void_p), ("num_points", C.c_uint64),
         ("key", C.c_void_p), ("level", C.c_void_p), ("is_internal_node", C.c_void_p),
         ("length", C.c_void_p), ("offset", C.c_void_p), ("num_nodes", C.c_uint64),
-        ("grid", bsj_grid),
+        ("grid", bsj_grid), ("sorted_keys", C.c_void_p),
     ]
 
 

@@ -156,6 +156,8 @@ def quadtree_on_points(points, x_min, x_max, y_min, y_max, scale, max_depth, max
     g = _lib.bsj_grid()
     C.memmove(C.byref(g), C.byref(out.grid), C.sizeof(_lib.bsj_grid))
     tree._grid = g
+    # the hint points at the sorted Morton keys: keep that buffer alive with the Frame
+    tree._sorted_keys = alloc.take(out.sorted_keys, n, torch.uint32)
     return point_indices, tree
 
 

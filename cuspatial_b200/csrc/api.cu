@@ -365,6 +365,7 @@ void bsj_free_quadtree(bsj_quadtree* t, bsj_stream_t stream)
   bsj_free(t->is_internal_node, stream);
   bsj_free(t->length, stream);
   bsj_free(t->offset, stream);
+  bsj_free(t->sorted_keys, stream);
   *t = bsj_quadtree{};
 }
 void bsj_free_pairs(bsj_pairs* p, bsj_stream_t stream)

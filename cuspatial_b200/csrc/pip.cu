@@ -330,6 +330,7 @@ struct grid_info {
   int has_oob;
   double min_x, min_y, scale;
   double margin_x, margin_y;  // rounding margin of the point -> cell assignment
+  const u32* sorted_keys;     // Morton keys of the points in sorted order (optional)
 };
 
 constexpr int kClsOutside = 0, kClsInside = 1, kClsBoundary = 2;
@@ -444,68 +445,77 @@ constexpr int kPipWarps = 4;
 constexpr int kPPL      = 8;          // points per lane
 constexpr int kPipTile  = 32 * kPPL;  // points per tile
 
+// Stage 1 of the evaluation: one warp per (polygon, quadrant) pair decides whole quadrants from
+// their cell rectangle (classify_quadrant).  Pairs are independent, so the grid keeps every SM
+// full of warps and the dependent index/edge loads of one pair hide behind the others.  Quadrants
+// that need their points are appended (once) to a work list for stage 2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pip_classify_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad,
+                    u32 n_pairs, const u32* __restrict__ heads, const u64* __restrict__ run_idx,
+                    const u32* __restrict__ length, const u32* __restrict__ offset, u32 num_nodes,
+                    u32 n_points, const poly_meta<T>* __restrict__ meta, u32 n_poly,
+                    int force_reference, const u32* __restrict__ node_key,
+                    const u8* __restrict__ node_level, grid_info grid, edge_index<T> ix,
+                    u8* __restrict__ cls, u32* __restrict__ hits, u32* __restrict__ run_flag,
+                    u32* __restrict__ run_list, u32* __restrict__ run_count)
+{
+  u32 const lane  = lane_id();
+  u32 const warps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_pairs; j += warps) {
+    u32 const quad = pair_quad[j];
+    int c          = kClsOutside;
+    u32 nvalid     = 0;
+    if (quad < num_nodes) {
+      u32 const len = length[quad], off = offset[quad];
+      nvalid        = off < n_points ? min(len, n_points - off) : 0u;
+      u32 const poly = pair_poly[j];
+      if (len != 0 && poly < n_poly) {
+        poly_meta<T> const m = meta[poly];
+        c = (grid.valid && force_reference != 1)
+              ? classify_quadrant<T>(grid, node_key[quad], node_level[quad], m, ix)
+              : kClsBoundary;
+      }
+    }
+    if (lane == 0) {
+      cls[j]  = (u8)c;
+      hits[j] = c == kClsInside ? nvalid : 0u;  // boundary pairs are counted by stage 2
+      if (c == kClsBoundary) {
+        u32 const run = (u32)run_idx[j] - (heads[j] ? 0u : 1u);
+        if (atomicExch(&run_flag[run], 1u) == 0u) run_list[atomicAdd(run_count, 1u)] = run;
+      }
+    }
+  }
+}
+
+// Stage 2: one warp per listed quadrant gathers its points once and tests them against every
+// polygon of the run that stage 1 left undecided.
 template <typename T>
 __global__ void __launch_bounds__(kPipWarps * 32)
 pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad,
-                const u32* __restrict__ run_start, const u64* __restrict__ n_runs_ptr,
-                const u32* __restrict__ length, const u32* __restrict__ offset, u32 num_nodes,
-                const u32* __restrict__ point_indices, u32 n_points, const T* __restrict__ px,
-                const T* __restrict__ py, const poly_meta<T>* __restrict__ meta, u32 n_poly,
+                const u32* __restrict__ run_start, const u32* __restrict__ run_list,
+                const u32* __restrict__ run_count, const u32* __restrict__ length,
+                const u32* __restrict__ offset, const u32* __restrict__ point_indices,
+                u32 n_points, const T* __restrict__ px, const T* __restrict__ py,
+                const poly_meta<T>* __restrict__ meta, u32 n_poly,
                 const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
                 const T* __restrict__ vy, const u64* __restrict__ wbase,
                 u32* __restrict__ mask_words, u32* __restrict__ hits, u32* __restrict__ ticket,
-                int force_reference, const u32* __restrict__ node_key,
-                const u8* __restrict__ node_level, grid_info grid, u8* __restrict__ cls,
-                edge_index<T> ix)
+                int force_reference, const u8* __restrict__ cls, edge_index<T> ix)
 {
   u32 const lane   = lane_id();
-  u32 const n_runs = (u32)*n_runs_ptr;
+  u32 const n_list = *run_count;
 
   while (true) {
-    u32 r = 0;
-    if (lane == 0) r = atomicAdd(ticket, 1u);
-    r = __shfl_sync(0xffffffffu, r, 0);
-    if (r >= n_runs) break;
+    u32 slot = 0;
+    if (lane == 0) slot = atomicAdd(ticket, 1u);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= n_list) break;
+    u32 const r = run_list[slot];
 
     u32 const j0 = run_start[r], j1 = run_start[r + 1];
     u32 const quad = pair_quad[j0];
-    if (quad >= num_nodes) {  // malformed pair: no candidates (words == 0 as well)
-      for (u32 j = j0 + lane; j < j1; j += 32) hits[j] = 0;
-      continue;
-    }
     u32 const len = length[quad], off = offset[quad];
-    if (len == 0) {
-      for (u32 j = j0 + lane; j < j1; j += 32) {
-        hits[j] = 0;
-        cls[j]  = kClsOutside;
-      }
-      continue;
-    }
-
-    // ---- whole-quadrant decisions first: pairs settled here never touch the points
-    bool need_points = false;
-    {
-      u32 const nkey = node_key[quad], nlev = node_level[quad];
-      u32 const nvalid = off < n_points ? min(len, n_points - off) : 0u;
-      for (u32 j = j0; j < j1; ++j) {
-        u32 const poly = pair_poly[j];
-        int c          = kClsOutside;
-        if (poly < n_poly) {
-          poly_meta<T> const m = meta[poly];
-          c = (grid.valid && force_reference != 1)
-                ? classify_quadrant<T>(grid, nkey, nlev, m, ix)
-                : kClsBoundary;
-        }
-        if (lane == 0) {
-          cls[j] = (u8)c;
-          if (c != kClsBoundary) hits[j] = c == kClsInside ? nvalid : 0u;
-          else if (force_reference == 2) hits[j] = 0u;
-        }
-        need_points = need_points || c == kClsBoundary;
-      }
-    }
-    if (!need_points || force_reference == 2) continue;  // 2: timing experiment, classify only
-    __syncwarp();  // cls[] written by lane 0 is read by every lane below
 
     for (u32 base = 0; base < len; base += kPipTile) {
       // ---- gather this tile's points once (quadtree_point_in_polygon.cuh:66,170)
@@ -551,7 +561,7 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
       u32 const tile_words = (min(len - base, (u32)kPipTile) + 31) / 32;  // <= 8
 
       for (u32 j = j0; j < j1; ++j) {
-        if (__ldcg(cls + j) != kClsBoundary) continue;  // settled from the cell rectangle
+        if (cls[j] != kClsBoundary) continue;  // settled from the cell rectangle by stage 1
         u32 const poly = pair_poly[j];
         u32 inside     = 0;  // bit i: point i of this lane is inside
         if (poly < n_poly) {
@@ -666,6 +676,272 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
         u32 mine = 0, cnt = 0;
 #pragma unroll
         for (int i = 0; i < kPPL; ++i) {
+          u32 const w = __ballot_sync(0xffffffffu, (inside >> i) & 1u);
+          if (lane == (u32)i) mine = w;
+          cnt += __popc(w);
+        }
+        if (lane < tile_words) mask_words[wbase[j] + base / 32 + lane] = mine;
+        if (lane == 0) hits[j] = (base == 0 ? 0u : hits[j]) + cnt;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 2, cell-centre form (needs the sorted Morton keys of the points, part of the bsj_grid
+// hint).  A point's key names its finest cell, a square of side `scale` that contains the point
+// (plus the rounding margin of the key computation).  If no edge of the polygon passes through
+// that (margin-widened) square and no vertical edge has its x inside the square's x-range, the
+// point and the square's centre lie in the same face of the polygon's edge arrangement, every
+// crossing comparison of the reference is sign-certain for both, and the reference's answer for
+// the point equals the plain crossing parity of the CENTRE -- which needs the 4-byte key, read
+// coalesced, instead of two random 8-byte gathers that cost ~115 B of HBM traffic each.  Only the
+// points whose square is touched by an edge (a fraction of a percent) are gathered and put
+// through the reference's own arithmetic.  Out-of-box points share the last key whatever their
+// coordinates: they always take the exact path.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCellPPL  = 4;
+constexpr int kCellTile = 32 * kCellPPL;
+
+template <typename T>
+__global__ void __launch_bounds__(kPipWarps * 32, 4)
+pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad,
+                      const u32* __restrict__ run_start, const u32* __restrict__ run_list,
+                      const u32* __restrict__ run_count, const u32* __restrict__ length,
+                      const u32* __restrict__ offset, const u32* __restrict__ point_indices,
+                      u32 n_points, const T* __restrict__ px, const T* __restrict__ py,
+                      const poly_meta<T>* __restrict__ meta, u32 n_poly,
+                      const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
+                      const T* __restrict__ vy, const u64* __restrict__ wbase,
+                      u32* __restrict__ mask_words, u32* __restrict__ hits,
+                      u32* __restrict__ ticket, const u8* __restrict__ cls, edge_index<T> ix,
+                      grid_info grid, const u32* __restrict__ sorted_keys)
+{
+  u32 const lane   = lane_id();
+  u32 const n_list = *run_count;
+  double const hw  = 0.5 * grid.scale + grid.margin_x;  // half extents of a widened finest cell
+  double const hh  = 0.5 * grid.scale + grid.margin_y;
+  u32 const oob_key = grid.max_depth >= 16 ? 0xFFFFFFFFu : ((1u << (2 * grid.max_depth)) - 1u);
+  double const eps  = (double)fpp<T>::eps();
+
+  while (true) {
+    u32 slot = 0;
+    if (lane == 0) slot = atomicAdd(ticket, 1u);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= n_list) break;
+    u32 const r  = run_list[slot];
+    u32 const j0 = run_start[r], j1 = run_start[r + 1];
+    u32 const quad = pair_quad[j0];
+    u32 const len = length[quad], off = offset[quad];
+
+    for (u32 base = 0; base < len; base += kCellTile) {
+      u32 valid = 0, oob = 0;
+      double cx[kCellPPL], cy[kCellPPL];
+#pragma unroll
+      for (int i = 0; i < kCellPPL; ++i) {
+        u32 const l   = base + i * 32 + lane;
+        bool const ok = l < len && off + l < n_points;
+        u32 const k   = ok ? __ldcs(sorted_keys + off + l) : 0u;
+        valid |= (u32)ok << i;
+        oob |= (u32)(ok && grid.has_oob && k == oob_key) << i;
+        cx[i] = grid.min_x + ((double)undilate16p(k) + 0.5) * grid.scale;
+        cy[i] = grid.min_y + ((double)undilate16p(k >> 1) + 0.5) * grid.scale;
+      }
+      // tile extent (cell squares of the valid points)
+      double tx0 = 1e300, tx1 = -1e300, ty0 = 1e300, ty1 = -1e300;
+#pragma unroll
+      for (int i = 0; i < kCellPPL; ++i)
+        if ((valid >> i) & 1u) {
+          tx0 = fmin(tx0, cx[i] - hw); tx1 = fmax(tx1, cx[i] + hw);
+          ty0 = fmin(ty0, cy[i] - hh); ty1 = fmax(ty1, cy[i] + hh);
+        }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        tx0 = fmin(tx0, __shfl_xor_sync(0xffffffffu, tx0, o));
+        ty0 = fmin(ty0, __shfl_xor_sync(0xffffffffu, ty0, o));
+        tx1 = fmax(tx1, __shfl_xor_sync(0xffffffffu, tx1, o));
+        ty1 = fmax(ty1, __shfl_xor_sync(0xffffffffu, ty1, o));
+      }
+      // real coordinates, gathered lazily and only for the points that need them
+      T xr[kCellPPL], yr[kCellPPL];
+      u32 loaded = 0, unsafe_pt = 0;
+      auto load_points = [&](u32 want) {
+        want &= valid & ~loaded;
+#pragma unroll
+        for (int i = 0; i < kCellPPL; ++i)
+          if ((want >> i) & 1u) {
+            u32 const id = __ldg(point_indices + off + base + i * 32 + lane);
+            if (id < n_points) {
+              xr[i] = __ldg(px + id);
+              yr[i] = __ldg(py + id);
+              if (!(comfy(xr[i]) && comfy(yr[i]))) unsafe_pt |= 1u << i;
+            } else {
+              valid &= ~(1u << i);
+            }
+          }
+        loaded |= want;
+      };
+      u32 const tile_words = (min(len - base, (u32)kCellTile) + 31) / 32;  // <= kCellPPL
+
+      for (u32 j = j0; j < j1; ++j) {
+        if (cls[j] != kClsBoundary) continue;
+        u32 const poly = pair_poly[j];
+        u32 inside     = 0;
+        if (poly < n_poly) {
+          poly_meta<T> const m = meta[poly];
+          if (!(m.safe && m.n_slabs)) {
+            // unusual polygon (NaN/Inf/extreme magnitudes): the literal reference loop
+            load_points(0xFFFFFFFFu);
+#pragma unroll
+            for (int i = 0; i < kCellPPL; ++i)
+              if ((valid >> i) & 1u)
+                inside |= (u32)pip_reference<T>(xr[i], yr[i], ring_offsets, m.ring_begin,
+                                                m.ring_end, vx, vy) << i;
+          } else {
+            double const dx = eps * fmax(fabs((double)m.xmin), fabs((double)m.xmax));
+            double const dy = eps * fmax(fabs((double)m.ymin), fabs((double)m.ymax));
+            bool const miss = tx1 < (double)m.xmin - dx || tx0 > (double)m.xmax + dx ||
+                              ty1 < (double)m.ymin - dy || ty0 > (double)m.ymax + dy;
+            if (!miss) {
+              // relevant edges: slabs covering the tile's y-range, taken once each
+              T const qy0 = (T)ty0, qy1 = (T)ty1;
+              u32 const q0 = slab_of<T>(qy0, m), q1 = slab_of<T>(qy1, m);
+              u32 const kbeg = __ldg(ix.slab_start + m.slab_base + q0);
+              u32 const kmid = __ldg(ix.slab_start + m.slab_base + q0 + 1);
+              u32 const kend = __ldg(ix.slab_start + m.slab_base + q1 + 1);
+              auto fetch = [&](u32 k, T& ax, T& ay, T& bx, T& by) -> bool {
+                if (k >= kend) return false;
+                u32 const ent = __ldg(ix.entries + k);
+                if (k >= kmid && !(ent & kFirstFlag)) return false;
+                edge_rec<T> const e = ix.edges[ent & ~kFirstFlag];
+                ax = e.ax; ay = e.ay; bx = e.bx; by = e.by;
+                double const dl = eps * fmax(fabs((double)ay), fabs((double)by));
+                return ty1 >= fmin((double)ay, (double)by) - dl &&
+                       ty0 <= fmax((double)ay, (double)by) + dl;
+              };
+              // ---- pass 1: crossing parity of the cell centres + "an edge touches my cell"
+              u32 cross = 0, near = oob;
+              for (u32 k0 = kbeg; k0 < kend; k0 += 32) {
+                T ax = 0, ay = 0, bx = 0, by = 0;
+                bool const rel = fetch(k0 + lane, ax, ay, bx, by);
+                u32 em = __ballot_sync(0xffffffffu, rel);
+                while (em) {
+                  int const src = __ffs(em) - 1;
+                  em &= em - 1;
+                  double const eax = (double)__shfl_sync(0xffffffffu, ax, src);
+                  double const eay = (double)__shfl_sync(0xffffffffu, ay, src);
+                  double const ebx = (double)__shfl_sync(0xffffffffu, bx, src);
+                  double const eby = (double)__shfl_sync(0xffffffffu, by, src);
+                  double const run = ebx - eax, rise = eby - eay;
+                  double const d   = eps * fmax(fmax(fabs(eax), fabs(ebx)), fmax(fabs(eay), fabs(eby)));
+                  double const lx = fmin(eax, ebx) - d, hx = fmax(eax, ebx) + d;
+                  double const ly = fmin(eay, eby) - d, hy = fmax(eay, eby) + d;
+                  double const reach = fabs(rise) * hw + fabs(run) * hh;
+#pragma unroll
+                  for (int i = 0; i < kCellPPL; ++i) {
+                    double const ddx = cx[i] - eax, ddy = cy[i] - eay;
+                    double const f   = ddx * rise - run * ddy;  // (v - u) of the reference
+                    // the edge's line passes through the widened cell square, within the edge's
+                    // own (tolerance-widened) extent?
+                    double const tol = 1e-9 * (fabs(ddx * rise) + fabs(run * ddy));
+                    bool const touch = fabs(f) <= reach * 1.000001 + tol &&
+                                       cx[i] + hw >= lx && cx[i] - hw <= hx &&
+                                       cy[i] + hh >= ly && cy[i] - hh <= hy;
+                    near |= (u32)touch << i;
+                    bool const y1 = eay > cy[i], y0 = eby > cy[i];
+                    cross ^= (u32)((y1 != y0) && ((f < 0.0) != y1)) << i;
+                  }
+                }
+              }
+              for (u32 k = 0; k < m.n_vertical; ++k) {  // x-only rule of vertical edges
+                double const ax = (double)ix.edges[__ldg(ix.vert_edges + m.vert_begin + k)].ax;
+#pragma unroll
+                for (int i = 0; i < kCellPPL; ++i)
+                  near |= (u32)(ax >= cx[i] - hw && ax <= cx[i] + hw) << i;
+              }
+              near &= valid;
+              inside = cross & ~near;
+              // ---- pass 2: the touched points, with their real coordinates and the reference's
+              // own arithmetic over the same edges
+              if (__any_sync(0xffffffffu, near != 0)) {
+                load_points(near);
+                near &= valid;
+                u32 const exact = near & ~unsafe_pt;
+                u32 within = 0, onedge = 0;
+                auto eval_edges = [&](u32 em, T ax, T ay, T bx, T by) {
+                  while (em) {
+                    int const src = __ffs(em) - 1;
+                    em &= em - 1;
+                    T const eax = __shfl_sync(0xffffffffu, ax, src);
+                    T const eay = __shfl_sync(0xffffffffu, ay, src);
+                    T const ebx = __shfl_sync(0xffffffffu, bx, src);
+                    T const eby = __shfl_sync(0xffffffffu, by, src);
+                    if (!exact) continue;
+                    T const run  = fpp<T>::sub(ebx, eax);
+                    T const rise = fpp<T>::sub(eby, eay);
+                    T const lo = fmin(eax, ebx), hi = fmax(eax, ebx);
+#pragma unroll
+                    for (int i = 0; i < kCellPPL; ++i)
+                      if ((exact >> i) & 1u) {
+                        T const rtp  = fpp<T>::sub(yr[i], eay);
+                        T const rntp = fpp<T>::sub(xr[i], eax);
+                        T const u    = fpp<T>::mul(run, rtp);
+                        T const v    = fpp<T>::mul(rntp, rise);
+                        if (lo <= xr[i] && xr[i] <= hi) {
+                          if (float_equal(u, v)) onedge |= 1u << i;
+                        }
+                        bool const y1 = eay > yr[i], y0 = eby > yr[i];
+                        within ^= (u32)((y1 != y0) && ((v < u) != y1)) << i;
+                      }
+                  }
+                };
+                // the exact path needs every edge whose y-range meets the POINT (a subset of the
+                // tile's list) plus vertical edges at the point's x: both are covered by the
+                // tile-level lists below, exactly as in pip_eval_kernel
+                T rx0 = fpp<T>::inf(), rx1 = -fpp<T>::inf();
+#pragma unroll
+                for (int i = 0; i < kCellPPL; ++i)
+                  if ((exact >> i) & 1u) { rx0 = fmin(rx0, xr[i]); rx1 = fmax(rx1, xr[i]); }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                  rx0 = fmin(rx0, __shfl_xor_sync(0xffffffffu, rx0, o));
+                  rx1 = fmax(rx1, __shfl_xor_sync(0xffffffffu, rx1, o));
+                }
+                for (u32 k0 = kbeg; k0 < kend; k0 += 32) {
+                  T ax = 0, ay = 0, bx = 0, by = 0;
+                  bool const rel = fetch(k0 + lane, ax, ay, bx, by);
+                  eval_edges(__ballot_sync(0xffffffffu, rel), ax, ay, bx, by);
+                }
+                for (u32 k0 = 0; k0 < m.n_vertical; k0 += 32) {
+                  u32 const k = k0 + lane;
+                  T ax = 0, ay = 0, bx = 0, by = 0;
+                  bool rel = false;
+                  if (k < m.n_vertical) {
+                    edge_rec<T> const e = ix.edges[__ldg(ix.vert_edges + m.vert_begin + k)];
+                    ax = e.ax; ay = e.ay; bx = e.bx; by = e.by;
+                    double const dl = eps * fmax(fabs((double)ay), fabs((double)by));
+                    bool const yrel = ty1 >= fmin((double)ay, (double)by) - dl &&
+                                      ty0 <= fmax((double)ay, (double)by) + dl;  // taken above
+                    rel = !yrel && rx0 <= ax && ax <= rx1;
+                  }
+                  eval_edges(__ballot_sync(0xffffffffu, rel), ax, ay, bx, by);
+                }
+                inside = (inside & ~near) | (within & ~onedge & exact);
+                if (unsafe_pt & near) {
+#pragma unroll
+                  for (int i = 0; i < kCellPPL; ++i)
+                    if (((unsafe_pt & near) >> i) & 1u)
+                      inside |= (u32)pip_reference<T>(xr[i], yr[i], ring_offsets, m.ring_begin,
+                                                      m.ring_end, vx, vy) << i;
+                }
+              }
+            }
+          }
+        }
+        inside &= valid;
+        u32 mine = 0, cnt = 0;
+#pragma unroll
+        for (int i = 0; i < kCellPPL; ++i) {
           u32 const w = __ballot_sync(0xffffffffu, (inside >> i) & 1u);
           if (lane == (u32)i) mine = w;
           cnt += __popc(w);
@@ -959,6 +1235,13 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
                           std::fabs(grid->max_x - grid->min_x));
       gi.margin_y = cm * (std::fabs(grid->min_y) + std::fabs(grid->max_y) +
                           std::fabs(grid->max_y - grid->min_y));
+      static int no_keys = -1;
+      if (no_keys < 0) {
+        const char* e = std::getenv("BSJ_PIP_NO_KEYS");
+        no_keys       = (e && e[0] == '1') ? 1 : 0;
+      }
+      gi.sorted_keys = (grid->sorted_keys && grid->n_sorted_keys == n_points && !no_keys)
+                         ? grid->sorted_keys : nullptr;
     }
   }
   polygon_index<T> pidx;
@@ -994,13 +1277,34 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
   c->n_words    = total_words;
   c->mask_words = oa.get<u32>(std::max<u64>(total_words, 1));
   {
-    int const grid_dim = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_runs, kPipWarps));
-    pip_eval_kernel<T><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
-      pair_poly, pair_quad, run_start.get(), totals.get() + 1, length, offset, (u32)num_nodes,
-      point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly, ring_offsets,
-      (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words, c->pair_hits, ticket.get(),
-      force_reference_mode(), node_key, node_level, gi, c->pair_class, ix);
+    dev_buf<u32> run_flag(n_runs + 1, s), run_list(n_runs + 1, s), run_count(1, s);
+    BSJ_CUDA_TRY(cudaMemsetAsync(run_flag.get(), 0, (n_runs + 1) * sizeof(u32), s));
+    BSJ_CUDA_TRY(cudaMemsetAsync(run_count.get(), 0, sizeof(u32), s));
+    int const cgrid = (int)std::min<u64>((u64)kNumSMs * 16, (u64)div_up(n_pairs * 32, 256));
+    pip_classify_kernel<T><<<std::max(cgrid, 1), 256, 0, s>>>(
+      pair_poly, pair_quad, (u32)n_pairs, heads.get(), run_idx.get(), length, offset,
+      (u32)num_nodes, (u32)n_points, meta.get(), n_poly, force_reference_mode(), node_key,
+      node_level, gi, ix, c->pair_class, c->pair_hits, run_flag.get(), run_list.get(),
+      run_count.get());
     BSJ_CHECK_LAUNCH();
+    prof_mark("pip_classify");
+    if (force_reference_mode() == 0 && gi.valid && gi.sorted_keys) {
+      int const grid_dim = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_runs, kPipWarps));
+      pip_eval_cells_kernel<T><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
+        pair_poly, pair_quad, run_start.get(), run_list.get(), run_count.get(), length, offset,
+        point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly,
+        ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words, c->pair_hits,
+        ticket.get(), c->pair_class, ix, gi, gi.sorted_keys);
+      BSJ_CHECK_LAUNCH();
+    } else if (force_reference_mode() != 2) {  // 2: timing experiment, classification only
+      int const grid_dim = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_runs, kPipWarps));
+      pip_eval_kernel<T><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
+        pair_poly, pair_quad, run_start.get(), run_list.get(), run_count.get(), length, offset,
+        point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly,
+        ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words, c->pair_hits,
+        ticket.get(), force_reference_mode(), c->pair_class, ix);
+      BSJ_CHECK_LAUNCH();
+    }
   }
   prof_mark("pip_eval");
   exclusive_scan_u32_to_u64(c->pair_hits, c->pair_row_base, n_pairs, totals.get() + 2, s);

@@ -414,7 +414,13 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
   // the sorted permutation ends in `idx_a` or `idx_b` depending on pass parity; make the final
   // target the caller-visible output buffer
   u32* out_idx = oa.get<u32>(n);
-  dev_buf<u32> keys_a(n, s), keys_b(n, s), idx_tmp(n, s);
+  // likewise the sorted keys end in side A (even number of passes) or B: that side is allocated
+  // through the output allocator and handed out as part of the bsj_grid hint
+  bool const even_passes = (passes % 2) == 0;
+  u32* out_keys = oa.get<u32>(n);
+  dev_buf<u32> keys_tmp(n, s), idx_tmp(n, s);
+  struct { u32* p; u32* get() const { return p; } } keys_a{even_passes ? out_keys : keys_tmp.get()},
+    keys_b{even_passes ? keys_tmp.get() : out_keys};
   sort_workspace ws;
   ws.alloc(n, s);
   sort_workspace_reset(ws, s);
@@ -482,6 +488,9 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
   int const last = d >= 2 ? d - 1 : 0;
   u64 const q    = h.level_end[last];
 
+  grid.sorted_keys      = out_keys;
+  grid.n_sorted_keys    = n;
+  out->sorted_keys      = out_keys;
   grid.has_out_of_bbox  = (h.point_flags & 1u) ? 1 : 0;
   grid.has_nan          = (h.point_flags & 2u) ? 1 : 0;
   out->grid             = grid;

@@ -72,6 +72,10 @@ typedef struct bsj_grid {
   double scale;
   int32_t has_nan;         /* some coordinate was NaN (such points key into row/column 0)       */
   int32_t has_out_of_bbox; /* some point lay outside the box (all keyed to the last cell)       */
+  const uint32_t* sorted_keys; /* optional: Morton keys of the points in sorted order (device);
+                                  lets the refinement decide most points of boundary quadrants
+                                  from their finest cell instead of gathering coordinates    */
+  uint64_t n_sorted_keys;
 } bsj_grid;
 
 /* Result of bsj_quadtree_on_points == the reference's
@@ -87,6 +91,8 @@ typedef struct bsj_quadtree {
   uint32_t* offset;          /* UINT32[num_nodes]: first child row (internal) / first point pos */
   uint64_t num_nodes;
   bsj_grid grid;             /* not part of the reference's result: optional hint, see bsj_grid */
+  uint32_t* sorted_keys;     /* UINT32[num_points], owned like the columns above; grid.sorted_keys
+                                points at it.  Free it (or drop the hint) when not needed.     */
 } bsj_quadtree;
 
 /* A two-column UINT32 table: (bbox_offset, quad_offset) or (polygon_index, point_index). */

@@ -72,6 +72,7 @@ struct quadtree_table {
   column<uint32_t> length;
   column<uint32_t> offset;
   bsj_grid grid{};  // optional acceleration hint for quadtree_point_in_polygon
+  column<uint32_t> sorted_keys;  // backing store of grid.sorted_keys
 };
 
 struct pair_table {  // (bbox_offset, quad_offset) or (polygon_index, point_index)
@@ -117,6 +118,7 @@ std::pair<column<uint32_t>, quadtree_table> quadtree_on_points(column_view<T> x,
   q.length           = column<uint32_t>(t.length, t.num_nodes, stream);
   q.offset           = column<uint32_t>(t.offset, t.num_nodes, stream);
   q.grid             = t.grid;
+  q.sorted_keys      = column<uint32_t>(t.sorted_keys, t.num_points, stream);
   return {column<uint32_t>(t.point_indices, t.num_points, stream), std::move(q)};
 }
 

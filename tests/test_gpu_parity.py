@@ -119,6 +119,7 @@ def test_random_inputs_equal_oracle(oracle_lib, case, dtype):
     want = run_host(oracle_lib, c, max_size)
     assert_same(run_gpu(c, max_size), want, "gpu vs oracle")
     assert_same(run_gpu(c, max_size, use_grid_hint=False), want, "gpu (no grid hint) vs oracle")
+    assert_same(run_gpu(c, max_size, use_grid_hint="no_keys"), want, "gpu (no keys) vs oracle")
 
 
 def test_config1_1M_uniform_263_polygons_equals_oracle_and_reference(oracle_lib):
@@ -160,6 +161,7 @@ def test_near_edge_points_equal_oracle(oracle_lib, dtype):
         want = run_host(oracle_lib, c2, max_size)
         assert_same(run_gpu(c2, max_size), want, "near-edge")
         assert_same(run_gpu(c2, max_size, use_grid_hint=False), want, "near-edge (no hint)")
+        assert_same(run_gpu(c2, max_size, use_grid_hint="no_keys"), want, "near-edge (no keys)")
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -190,6 +192,7 @@ def test_grid_aligned_polygons_and_lattice_points(oracle_lib, dtype, depth, max_
     want = run_host(oracle_lib, c, max_size)
     assert_same(run_gpu(c, max_size), want, "lattice")
     assert_same(run_gpu(c, max_size, use_grid_hint=False), want, "lattice (no hint)")
+    assert_same(run_gpu(c, max_size, use_grid_hint="no_keys"), want, "lattice (no keys)")
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

@@ -60,7 +60,10 @@ def run_gpu(c, max_size, use_grid_hint=True):
     if c["depth"] >= 1:
         pairs = cs.join_quadtree_and_bounding_boxes(tree, bb, ext[0], ext[1], ext[2], ext[3],
                                                     c["scale"], c["depth"])
-        if not use_grid_hint:
+        if use_grid_hint == "no_keys":      # cell rectangles only, no per-point cell test
+            tree._grid.sorted_keys = None
+            tree._grid.n_sorted_keys = 0
+        elif not use_grid_hint:
             tree._grid = None
         hits = cs.quadtree_point_in_polygon(pairs, tree, pidx, (x, y), polys)
         out["pairs"] = (pairs["bbox_offset"].cpu().numpy(), pairs["quad_offset"].cpu().numpy())
