@@ -976,9 +976,34 @@ pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
     u64 const wb    = wbase[j];
     u64 o           = obase[j];
     if (cls[j] == kClsInside) {  // whole quadrant inside: rows are (poly, off .. off+nh-1)
-      for (u32 r = lane; r < nh; r += 32) {
-        __stcs(out_poly + o + r, poly);
-        __stcs(out_point + o + r, off + r);
+      u32* const op = out_poly + o;
+      u32* const oq = out_point + o;
+      uintptr_t const ph = reinterpret_cast<uintptr_t>(op) & 15;
+      if (ph == (reinterpret_cast<uintptr_t>(oq) & 15)) {
+        // 128-bit streaming stores between a scalar head and tail
+        u32 const head = min((u32)(((16 - ph) & 15) >> 2), nh);
+        if (lane < head) {
+          __stcs(op + lane, poly);
+          __stcs(oq + lane, off + lane);
+        }
+        u32 const nvec = (nh - head) >> 2;
+        uint4* const vp = reinterpret_cast<uint4*>(op + head);
+        uint4* const vq = reinterpret_cast<uint4*>(oq + head);
+        for (u32 v = lane; v < nvec; v += 32) {
+          u32 const p0 = off + head + v * 4;
+          __stcs(vp + v, make_uint4(poly, poly, poly, poly));
+          __stcs(vq + v, make_uint4(p0, p0 + 1, p0 + 2, p0 + 3));
+        }
+        u32 const r = head + nvec * 4 + lane;
+        if (r < nh) {
+          __stcs(op + r, poly);
+          __stcs(oq + r, off + r);
+        }
+      } else {
+        for (u32 r = lane; r < nh; r += 32) {
+          __stcs(op + r, poly);
+          __stcs(oq + r, off + r);
+        }
       }
       continue;
     }
@@ -1345,8 +1370,7 @@ void pip_bitmask_t(const void* px, const void* py, u64 n_points, const u32* poly
     (const T*)vy, out, force_reference_mode(), ix);
   BSJ_CHECK_LAUNCH();
   tm.mark("pip_bitmask");
-  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
-  tm.finish();
+  tm.finish();  // results are ready in stream order; no trailing host synchronisation
 }
 
 }  // namespace
@@ -1401,8 +1425,7 @@ void expand_pip_compact_impl(const u32* pair_poly, const bsj_pip_compact* c, u32
 {
   stage_timer tm(s);
   expand_compact(pair_poly, c, position_base, out_poly, out_point, s);
-  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
-  tm.finish();
+  tm.finish();  // results are ready in stream order; no trailing host synchronisation
 }
 
 void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, u64 n_pairs,
@@ -1441,8 +1464,7 @@ void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, 
     out->second = oa.get<u32>(c.n_hits);
     expand_compact(pair_poly, &c, 0u, out->first, out->second, s);
   }
-  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
-  tm.finish();
+  tm.finish();  // results are ready in stream order; no trailing host synchronisation
   oa.commit();
   // `scratch` is not committed: its destructor releases the compact buffers
 }
@@ -1480,7 +1502,6 @@ void polygon_bounding_boxes_impl(const u32* poly_offsets, u64 n_poly_offsets,
       poly_offsets, n_poly, ring_offsets, (const double*)vx, (const double*)vy, (u32)n_verts, r,
       (double*)x0, (double*)y0, (double*)x1, (double*)y1);
   BSJ_CHECK_LAUNCH();
-  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
 }
 
 }  // namespace bsj

@@ -17,8 +17,9 @@
  *   - All data pointers are DEVICE pointers.  `dtype`: 0 = float32, 1 = float64 (the only
  *     coordinate types the reference dispatches on, cpp/src/indexing/point_quadtree.cu:61).
  *   - `stream` is a cudaStream_t (NULL = default stream, which is what the reference uses:
- *     rmm::cuda_stream_default).  Calls are synchronous from the caller's view, re-entrant and
- *     stateless, like the reference.
+ *     rmm::cuda_stream_default).  Calls are re-entrant and stateless like the reference; sizes
+ *     written to the result structs are exact on return, the column CONTENTS are ready in stream
+ *     order on `stream` (as with the reference's Thrust calls: no trailing host synchronisation).
  *   - `mr` plays the role of the reference's `rmm::device_async_resource_ref mr`: OUTPUT columns
  *     are allocated through it (so a host framework can hand in its own allocator, e.g. a torch
  *     caching-allocator callback).  NULL = library default (cudaMallocAsync on `stream`); such
