@@ -89,11 +89,15 @@ traverse_kernel(const uint4* __restrict__ nodes, const T* __restrict__ bx0,
   u32 const n_top     = min(st->n_top, (u32)kJoinStackCap);
   u32 const num_warps = gridDim.x * kJoinWarps;
 
-  for (u32 box = blockIdx.x * kJoinWarps + warp; box < n_boxes; box += num_warps) {
+  // one warp per (bounding box, level-0 node): 4x the parallelism of a warp per box, and the
+  // four sub-traversals of a box are independent
+  u64 const n_units = (u64)n_boxes * max(n_top, 1u);
+  for (u64 unit = (u64)blockIdx.x * kJoinWarps + warp; unit < n_units; unit += num_warps) {
+    u32 const box = (u32)(unit / max(n_top, 1u));
     T const qx0 = __ldg(bx0 + box), qy0 = __ldg(by0 + box);
     T const qx1 = __ldg(bx1 + box), qy1 = __ldg(by1 + box);
-    for (u32 i = lane; i < n_top; i += 32) stack[i] = i;
-    u32 sp = n_top;
+    if (lane == 0) stack[0] = (u32)(unit % max(n_top, 1u));
+    u32 sp = n_top ? 1u : 0u;
     __syncwarp();
     while (sp > 0) {
       u32 const take  = min(sp, 32u);
@@ -218,7 +222,7 @@ void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32*
   u64 capacity = std::max<u64>(1u << 20, n_boxes * 64);
   dev_buf<u32> hit_box, hit_node;
   join_state h{};
-  int const grid = (int)std::min<u64>((u64)kNumSMs * 3, (u64)div_up(n_boxes, kJoinWarps));
+  int const grid = (int)std::min<u64>((u64)kNumSMs * 3, (u64)div_up(n_boxes * 4, kJoinWarps));
   for (int attempt = 0; attempt < 2; ++attempt) {
     hit_box.alloc(capacity, s);
     hit_node.alloc(capacity, s);

@@ -385,6 +385,7 @@ __device__ int classify_quadrant(const grid_info& g, u32 key, u32 level, const p
     double const d = eps * fmax(fmax(fabs((double)e.ax), fabs((double)e.bx)),
                                 fmax(fabs((double)e.ay), fabs((double)e.by)));
     double const lx = fmin((double)e.ax, (double)e.bx) - d, hx = fmax((double)e.ax, (double)e.bx) + d;
+    if (hx < ex0) continue;  // wholly left of the rectangle: cannot touch it, never toggles
     double const ly = fmin((double)e.ay, (double)e.by) - d, hy = fmax((double)e.ay, (double)e.by) + d;
     near = near || !(hx < ex0 || lx > ex1 || hy < ey0 || ly > ey1);
     bool const f1 = e.ay > cy, f0 = e.by > cy;
@@ -816,8 +817,13 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                 edge_rec<T> const e = ix.edges[ent & ~kFirstFlag];
                 ax = e.ax; ay = e.ay; bx = e.bx; by = e.by;
                 double const dl = eps * fmax(fabs((double)ay), fabs((double)by));
+                // an edge wholly to the LEFT of the tile (beyond the tolerance) can neither be
+                // touched nor toggle a crossing: for a point right of a straddling edge the
+                // reference's test never toggles (sign-certain), see DESIGN.md section 5
+                double const dxl = eps * fmax(fabs((double)ax), fabs((double)bx));
                 return ty1 >= fmin((double)ay, (double)by) - dl &&
-                       ty0 <= fmax((double)ay, (double)by) + dl;
+                       ty0 <= fmax((double)ay, (double)by) + dl &&
+                       fmax((double)ax, (double)bx) + dxl >= tx0;
               };
               // ---- pass 1: crossing parity of the cell centres + "an edge touches my cell"
               u32 cross = 0, near = oob;

@@ -335,6 +335,116 @@ expand_level_kernel(const u32* __restrict__ keys, int L, int max_depth, u32 max_
   (void)done;
 }
 
+// Warp-per-node form of expand_level_kernel for the first levels, where there are few nodes but
+// each spans a huge key range: the three child boundaries are searched CONCURRENTLY by three
+// 10-lane groups, 11-ary (8 dependent loads for a 100 M range instead of 27).
+constexpr int kExpandWarpNodes = kExpandBlock / 32;
+__global__ void __launch_bounds__(kExpandBlock)
+expand_level_warp_kernel(const u32* __restrict__ keys, int L, int max_depth, u32 max_size, u32 cap,
+                         u32* __restrict__ okey, u8* __restrict__ olevel,
+                         u8* __restrict__ ointernal, u32* __restrict__ olength,
+                         u32* __restrict__ ooffset, tree_state* st, u64* __restrict__ lookback,
+                         u32* __restrict__ ticket)
+{
+  __shared__ u32 s_tile, s_base, s_nchild[kExpandWarpNodes];
+  u32 const lbeg      = st->level_begin[L];
+  u32 const lend      = st->level_end[L];
+  u32 const count     = lend - lbeg;
+  u32 const num_tiles = (count + kExpandWarpNodes - 1) / kExpandWarpNodes;
+  u32 const tag_agg = 2u * (L + 1), tag_pre = 2u * (L + 1) + 1u;
+  int const shift   = 2 * (max_depth - 2 - L);
+  int const tid = threadIdx.x, warp = tid >> 5;
+  u32 const lane = lane_id();
+  u32 const grp  = min(lane / 10u, 2u), li = lane - grp * 10u;  // lanes 30,31 shadow group 2
+  bool const active_lane = lane < 30;
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    u32 const tile = s_tile;
+    if (tile >= num_tiles) break;
+    u32 const row = lbeg + tile * kExpandWarpNodes + warp;
+    u32 k = 0, cnt = 0, start = 0, b1 = 0, b2 = 0, b3 = 0, nchild = 0;
+    if (row < lend) {
+      k     = okey[row];
+      cnt   = olength[row];
+      start = ooffset[row];
+      if (cnt > max_size) {
+        u64 const target = (((u64)k << 2) + grp + 1) << shift;
+        u32 lo = start, hi = start + cnt;
+        while (__any_sync(0xffffffffu, hi - lo > 10)) {
+          bool less = false;
+          u32 probe = lo;
+          if (hi - lo > 10) {
+            probe = lo + (u32)(((u64)(hi - lo) * (li + 1)) / 11);  // 10 interior probes
+            less  = active_lane && (u64)__ldg(keys + probe) < target;
+          }
+          u32 const m  = (__ballot_sync(0xffffffffu, less) >> (10 * grp)) & 0x3FFu;
+          int const c  = __popc(m);  // probes [0,c) of my group are < target
+          u32 const pl = __shfl_sync(0xffffffffu, probe, grp * 10 + max(c - 1, 0));
+          u32 const ph = __shfl_sync(0xffffffffu, probe, grp * 10 + min(c, 9));
+          if (hi - lo > 10) {
+            u32 const nlo = c == 0 ? lo : pl + 1;
+            u32 const nhi = c == 10 ? hi : ph;
+            lo = nlo;
+            hi = nhi;
+          }
+        }
+        // final step: at most 10 candidates per group, one per lane
+        u32 const idx   = lo + li;
+        bool const less = active_lane && idx < hi && (u64)__ldg(keys + idx) < target;
+        u32 const m     = (__ballot_sync(0xffffffffu, less) >> (10 * grp)) & 0x3FFu;
+        u32 const bound = lo + __popc(m);
+        b1 = __shfl_sync(0xffffffffu, bound, 0);
+        b2 = __shfl_sync(0xffffffffu, bound, 10);
+        b3 = __shfl_sync(0xffffffffu, bound, 20);
+        nchild = (b1 > start) + (b2 > b1) + (b3 > b2) + (start + cnt > b3);
+      }
+    }
+    if (lane == 0) s_nchild[warp] = nchild;
+    __syncthreads();
+    u32 wbase = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kExpandWarpNodes; ++w) {
+      if (w < warp) wbase += s_nchild[w];
+      block_total += s_nchild[w];
+    }
+    if (tid == 0) s_base = lookback_exclusive(lookback, tile, block_total, tag_agg, tag_pre);
+    __syncthreads();
+    if (nchild && lane == 0) {
+      u32 const first_child = lend + s_base + wbase;
+      ointernal[row] = 1;
+      olength[row]   = nchild;
+      ooffset[row]   = first_child;
+      u32 const b[5] = {start, b1, b2, b3, start + cnt};
+      u32 r          = first_child;
+      for (int c = 0; c < 4; ++c) {
+        if (b[c + 1] > b[c]) {
+          if (r < cap) {
+            okey[r]      = (k << 2) + c;
+            olevel[r]    = (u8)(L + 1);
+            ointernal[r] = 0;
+            olength[r]   = b[c + 1] - b[c];
+            ooffset[r]   = b[c];
+          } else {
+            st->overflow = 1;
+          }
+          ++r;
+        }
+      }
+    }
+    if (tid == 0 && tile == num_tiles - 1) {
+      st->level_begin[L + 1] = lend;
+      st->level_end[L + 1]   = min(lend + s_base + block_total, cap);
+    }
+  }
+  if (num_tiles == 0 && blockIdx.x == 0 && tid == 0) {
+    st->level_begin[L + 1] = lend;
+    st->level_end[L + 1]   = lend;
+  }
+}
+
 // one launch instead of five device-to-device copies
 __global__ void __launch_bounds__(256)
 copy_tree_kernel(const u32* __restrict__ k, const u8* __restrict__ l, const u8* __restrict__ f,
@@ -474,9 +584,16 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
     u64 const geo  = ((2ull << L) + 3) * ((2ull << L) + 3);
     int const grid = (int)std::min<u64>((u64)kNumSMs * 8,
                                         std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandBlock)));
-    expand_level_kernel<<<grid, kExpandBlock, 0, s>>>(
-      sorted_keys, L, d, max_size, (u32)cap, tkey.get(), tlevel.get(), tint.get(), tlen.get(),
-      toff.get(), st.get(), lb.get(), tickets.get() + L, nullptr);
+    if (geo <= 2048) {  // few, huge nodes: warp-cooperative child search
+      int const wgrid = (int)std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandWarpNodes));
+      expand_level_warp_kernel<<<wgrid, kExpandBlock, 0, s>>>(
+        sorted_keys, L, d, max_size, (u32)cap, tkey.get(), tlevel.get(), tint.get(), tlen.get(),
+        toff.get(), st.get(), lb.get(), tickets.get() + L);
+    } else {
+      expand_level_kernel<<<grid, kExpandBlock, 0, s>>>(
+        sorted_keys, L, d, max_size, (u32)cap, tkey.get(), tlevel.get(), tint.get(), tlen.get(),
+        toff.get(), st.get(), lb.get(), tickets.get() + L, nullptr);
+    }
     BSJ_CHECK_LAUNCH();
   }
   tm.mark("tree_levels");
