@@ -363,16 +363,22 @@ def main():
     alg_bytes = {
         "onesweep_pass": n * (12 + 16 * (passes - 1)) / passes,
         "encode_hist": n * (2 * 8 + 4),
-        "pip_eval": n * c * (4 + 2 * 8),
+        "pip_eval": n * c * (4 + 2 * 8),   # index + gathered coords per candidate
         "pip_emit": n * h * 8,
     }
     dom = max(alg_bytes, key=lambda k: stage_per_step.get(k, 0.0))
     dom_ms = stage_avg.get(dom, float("nan"))
     achieved = alg_bytes[dom] / (dom_ms / 1e3) / 1e9
     b_alg = (2 * 8 + 4) + (12 + 16 * (passes - 1)) + 4 + c * (4 + 2 * 8) + 8 * h
+    traffic = None
+    try:  # per-launch DRAM bytes of that kernel from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "kernel_ms_per_launch": dom_ms, "kernel_share_of_step": stage_per_step.get(dom, 0) / ms_step,
         "pipeline": {"alg_bytes_per_point": b_alg, "candidates_per_point": c,
                      "hits_per_point": h,

@@ -55,7 +55,7 @@ EXPORTED_SYMBOLS = [
     "bsj_quadtree_on_points", "bsj_join_quadtree_and_bounding_boxes",
     "bsj_quadtree_point_in_polygon", "bsj_quadtree_point_in_polygon_ex", "bsj_quadtree_point_in_polygon_compact",
     "bsj_expand_pip_compact", "bsj_point_in_polygon", "bsj_polygon_bounding_boxes",
-    "bsj_point_keys_histogram", "bsj_partition_points", "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
+    "bsj_point_keys_histogram", "bsj_key_subhistogram", "bsj_partition_points", "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
     "bsj_kernel_launch_count", "bsj_set_profiling", "bsj_get_profile",
 ]
 
@@ -97,6 +97,7 @@ def lib():
                                              vp, vp, vp, vp]
     L.bsj_point_keys_histogram.argtypes = [vp, vp, C.c_int, u64, dbl, dbl, dbl, dbl, dbl, C.c_int8,
                                            C.c_int, vp, vp, u64, vp]
+    L.bsj_key_subhistogram.argtypes = [vp, u64, C.c_int, vp, C.c_int, C.c_int, C.c_uint32, vp, vp]
     L.bsj_partition_points.argtypes = [vp, vp, vp, C.c_int, u64, C.c_uint32, vp, C.c_int, vp, vp,
                                        vp, vp]
     L.bsj_free.argtypes = [vp, vp]

@@ -53,6 +53,8 @@ void point_keys_histogram_impl(const void* x, const void* y, int dtype, u64 n, d
                                double x_max, double y_min, double y_max, double scale,
                                int max_depth, int hist_shift, u32* keys, u32* bins, u64 n_bins,
                                cudaStream_t s);
+void key_subhistogram_impl(const u32* keys, u64 n, int shift1, const u32* h_targets, int n_targets,
+                           int shift2, u32 n_sub, u32* bins, cudaStream_t s);
 void partition_points_impl(const u32* keys, const void* x, const void* y, int dtype, u64 n,
                            u32 gid_base, const u32* h_splitters, int n_ranks,
                            void* const* dst_x, void* const* dst_y, u32* const* dst_gid,
@@ -336,6 +338,17 @@ int bsj_point_keys_histogram(const void* x, const void* y, int dtype, uint64_t n
     BSJ_EXPECTS(n == 0 || (x && y && keys), "x and y columns must have the same length");
     point_keys_histogram_impl(x, y, dtype, n, x_min, x_max, y_min, y_max, scale, max_depth,
                               hist_shift, keys, bins, n_bins, (cudaStream_t)stream);
+  });
+}
+
+int bsj_key_subhistogram(const uint32_t* keys, uint64_t n, int shift1,
+                         const uint32_t* host_target_bins, int n_targets, int shift2,
+                         uint32_t n_sub, uint32_t* bins, bsj_stream_t stream)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(n == 0 || (keys && bins), "keys and bins must not be NULL");
+    key_subhistogram_impl(keys, n, shift1, host_target_bins, n_targets, shift2, n_sub, bins,
+                          (cudaStream_t)stream);
   });
 }
 

@@ -75,6 +75,33 @@ key_histogram_kernel(const u32* __restrict__ keys, u64 n, int shift, u32 n_bins,
   }
 }
 
+// second-level histogram: only keys whose leading bits (key >> shift1) equal one of the target
+// bins are counted, by their next bits ((key >> shift2) & (n_sub - 1)).  Used to place the rank
+// splitters INSIDE a heavy first-level bin (clustered data).
+struct targets_t {
+  u32 bin[kMaxRanks];
+  int n;
+};
+__global__ void __launch_bounds__(512)
+key_subhistogram_kernel(const u32* __restrict__ keys, u64 n, int shift1, targets_t tg, int shift2,
+                        u32 n_sub, u32* __restrict__ bins)
+{
+  extern __shared__ u32 s_sub[];
+  u32 const total = (u32)tg.n * n_sub;
+  for (u32 i = threadIdx.x; i < total; i += blockDim.x) s_sub[i] = 0;
+  __syncthreads();
+  u64 const stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u32 const k = __ldcs(keys + i);
+    u32 const b = k >> shift1;
+    for (int t = 0; t < tg.n; ++t)
+      if (b == tg.bin[t]) atomicAdd(&s_sub[(u32)t * n_sub + ((k >> shift2) & (n_sub - 1))], 1u);
+  }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < total; i += blockDim.x)
+    if (s_sub[i]) atomicAdd(&bins[i], s_sub[i]);
+}
+
 __device__ __forceinline__ int dest_of(u32 key, const splitters_t& sp)
 {
   int d = 0;
@@ -249,6 +276,24 @@ void point_keys_histogram_impl(const void* x, const void* y, int dtype, u64 n, d
     key_histogram_kernel<<<std::max(grid, 1), 512, 0, s>>>(keys, n, hist_shift, (u32)n_bins, bins);
     BSJ_CHECK_LAUNCH();
   }
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+}
+
+void key_subhistogram_impl(const u32* keys, u64 n, int shift1, const u32* h_targets, int n_targets,
+                           int shift2, u32 n_sub, u32* bins, cudaStream_t s)
+{
+  BSJ_EXPECTS(n_targets >= 0 && n_targets <= kMaxRanks, "too many target bins");
+  BSJ_EXPECTS(n_sub >= 1 && (n_sub & (n_sub - 1)) == 0 && (u64)n_targets * n_sub <= 12288,
+              "sub-histogram does not fit shared memory");
+  BSJ_EXPECTS(shift1 >= shift2 && shift1 < 32 && shift2 >= 0, "invalid histogram shifts");
+  if (n == 0 || n_targets == 0) return;
+  targets_t tg{};
+  tg.n = n_targets;
+  for (int t = 0; t < n_targets; ++t) tg.bin[t] = h_targets[t];
+  int const grid = (int)std::min<u64>((u64)kNumSMs * 2, (u64)div_up(n, 2048));
+  key_subhistogram_kernel<<<std::max(grid, 1), 512, (size_t)n_targets * n_sub * sizeof(u32), s>>>(
+    keys, n, shift1, tg, shift2, n_sub, bins);
+  BSJ_CHECK_LAUNCH();
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
 }
 

@@ -65,6 +65,74 @@ def choose_splitters(global_hist, n_ranks, shift):
     return np.asarray(out, dtype=np.uint32)
 
 
+SUB_BITS = 10
+
+
+def refine_splitters(global_hist, n_ranks, shift):
+    """First step of the two-level splitter search: for every rank boundary the first-level bin
+    in which the target cumulative count is reached, and how many points are still missing when
+    that bin starts.  Returns (target_bins sorted unique, [(bin, missing)] per boundary)."""
+    h = np.asarray(global_hist, dtype=np.int64)
+    csum = np.cumsum(h)
+    total = int(csum[-1]) if len(csum) else 0
+    bounds = []
+    for r in range(1, n_ranks):
+        target = (total * r + n_ranks - 1) // n_ranks
+        b = int(np.searchsorted(csum, target, side="left"))
+        b = min(b, len(h) - 1)
+        before = int(csum[b] - h[b])
+        bounds.append((b, max(target - before, 0)))
+    return sorted(set(b for b, _ in bounds)), bounds
+
+
+def splitters_from_subhist(bounds, targets, sub_global, shift, shift2):
+    """Second step: inside each target bin, the sub-bin boundary where the missing count is met."""
+    n_sub = sub_global.shape[1]
+    out = []
+    for b, missing in bounds:
+        t = targets.index(b)
+        cs = np.cumsum(sub_global[t].astype(np.int64))
+        j = int(np.searchsorted(cs, missing, side="left")) if missing > 0 else -1
+        j = min(j, n_sub - 1)
+        v = (b << shift) + ((j + 1) << shift2)  # first key of the next rank
+        if out and v < out[-1]:
+            v = out[-1]
+        out.append(min(v, 0xFFFFFFFF))
+    return np.asarray(out, dtype=np.uint32)
+
+
+def send_counts_for(splitters, local_hist, targets, sub_local, shift, shift2, world):
+    """Points this rank sends to every destination, from its local (sub-)histograms."""
+    sp = splitters.astype(np.int64)
+    n_bins = len(local_hist)
+    owner = np.searchsorted(sp, np.arange(n_bins, dtype=np.int64) << shift, side="right")
+    lh = np.asarray(local_hist, dtype=np.int64).copy()
+    counts = np.zeros(world, dtype=np.int64)
+    for t, b in enumerate(targets):  # bins that may be cut by a splitter: count by sub-bin
+        lh[b] = 0
+        n_sub = sub_local.shape[1]
+        sub_owner = np.searchsorted(sp, (b << shift) + (np.arange(n_sub, dtype=np.int64) << shift2),
+                                    side="right")
+        counts += np.bincount(sub_owner, weights=sub_local[t], minlength=world).astype(np.int64)
+    counts += np.bincount(owner, weights=lh, minlength=world).astype(np.int64)
+    return counts
+
+
+def cuda_sub_histogram(keys, shift, targets, shift2, n_sub):
+    import ctypes as C
+
+    from . import _lib
+    from .api import _ptr, _stream
+
+    bins = torch.zeros(len(targets) * n_sub, dtype=torch.int32, device=keys.device)
+    tg = np.ascontiguousarray(targets, dtype=np.uint32)
+    with torch.cuda.device(keys.device):
+        _lib.check(_lib.lib().bsj_key_subhistogram(
+            _ptr(keys), keys.shape[0], int(shift), tg.ctypes.data_as(C.c_void_p), len(targets),
+            int(shift2), int(n_sub), _ptr(bins), _stream(keys.device)))
+    return bins.to(torch.int64).view(len(targets), n_sub)
+
+
 def hist_shift_for(max_depth):
     key_bits = min(32, 2 * (max(0, min(15, int(max_depth))) + 2))
     return max(0, key_bits - HIST_BITS)
@@ -260,13 +328,23 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     local_hist = hist.detach().clone().cpu().numpy()
     dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     hist_h = hist.cpu().numpy()
-    splitters = choose_splitters(hist_h, world, shift)
-
+    # two-level splitters: a first-level bin can hold a whole cluster, so the boundary is placed
+    # inside it with a second histogram of the next SUB_BITS key bits (one more all-reduce)
+    sub_hist = steps.get("sub_hist", cuda_sub_histogram)
+    shift2 = max(0, shift - SUB_BITS)
+    n_sub = 1 << (shift - shift2)
+    targets, bounds = refine_splitters(hist_h, world, shift)
+    if n_sub > 1 and targets:
+        sub = sub_hist(keys, shift, targets, shift2, n_sub)
+        sub_local = sub.detach().clone().cpu().numpy()
+        dist.all_reduce(sub, op=dist.ReduceOp.SUM, group=group)
+        splitters = splitters_from_subhist(bounds, targets, sub.cpu().numpy(), shift, shift2)
+    else:
+        targets, sub_local = [], np.zeros((0, 1), dtype=np.int64)
+        splitters = choose_splitters(hist_h, world, shift)
     prof.mark("allreduce_splitters")
     # 3. stable partition by destination + all-to-all
-    bin_owner = np.searchsorted(splitters.astype(np.int64) >> shift,
-                                np.arange(n_bins, dtype=np.int64), side="right")
-    send_counts = np.bincount(bin_owner, weights=local_hist, minlength=world).astype(np.int64)
+    send_counts = send_counts_for(splitters, local_hist, targets, sub_local, shift, shift2, world)
     sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
     rows = [torch.zeros_like(sc) for _ in range(world)]
     dist.all_gather(rows, sc, group=group)       # also orders this step after every rank's

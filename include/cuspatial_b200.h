@@ -252,6 +252,11 @@ int bsj_point_keys_histogram(const void* x, const void* y, int dtype, uint64_t n
                              double x_max, double y_min, double y_max, double scale,
                              int8_t max_depth, int hist_shift, uint32_t* keys, uint32_t* bins,
                              uint64_t n_bins, bsj_stream_t stream);
+/* bins[t * n_sub + ((key >> shift2) & (n_sub-1))] += 1 for every key with
+ * (key >> shift1) == host_target_bins[t]; refines the splitters inside heavy first-level bins. */
+int bsj_key_subhistogram(const uint32_t* keys, uint64_t n, int shift1,
+                         const uint32_t* host_target_bins, int n_targets, int shift2,
+                         uint32_t n_sub, uint32_t* bins, bsj_stream_t stream);
 int bsj_partition_points(const uint32_t* keys, const void* x, const void* y, int dtype, uint64_t n,
                          uint32_t gid_base, const uint32_t* host_splitters, int n_ranks,
                          void* const* dst_x, void* const* dst_y, uint32_t* const* dst_gid,

@@ -65,8 +65,16 @@ def _host_steps(oracle):
         out_poly.copy_(comp["poly"])
         out_point.copy_((comp["pos"].to(torch.int64) + position_base).to(torch.int32))
 
+    def sub_hist(keys, shift, targets, shift2, n_sub):
+        k = keys.numpy().view(np.uint32).astype(np.int64)
+        out = np.zeros((len(targets), n_sub), dtype=np.int64)
+        for t, b in enumerate(targets):
+            sel = k[(k >> shift) == b]
+            out[t] = np.bincount((sel >> shift2) & (n_sub - 1), minlength=n_sub)
+        return torch.from_numpy(out)
+
     return {"keys_hist": keys_hist, "partition": partition, "local_compact": local_join,
-            "expand": expand}
+            "expand": expand, "sub_hist": sub_hist}
 
 
 def _worker(rank, world, port, kind, dtype_name, q):
@@ -136,7 +144,29 @@ def test_sharded_join_world2_equals_single_process_oracle(oracle_lib, kind, dtyp
         got = got[np.lexsort((got[:, 1], got[:, 0]))]
         np.testing.assert_array_equal(got, want)               # same pair set on every rank
         np.testing.assert_array_equal(pidx.view(np.uint32), ref["tree"]["point_indices"])
-        assert sum(counts) == len(c["x"]) and min(counts) > 0.3 * len(c["x"]) / world
+        # two-level splitters: the ranks are balanced to within a sub-bin even for clustered data
+        assert sum(counts) == len(c["x"]) and min(counts) > 0.9 * len(c["x"]) / world
+
+
+def test_two_level_splitters_balance_a_heavy_bin():
+    from cuspatial_b200.multi_gpu import (refine_splitters, send_counts_for,
+                                          splitters_from_subhist)
+
+    rng = np.random.default_rng(1)
+    shift, shift2, n_sub = 19, 9, 1024
+    keys = np.concatenate([rng.integers(0, 1 << 30, 50_000),
+                           (777 << shift) + rng.integers(0, 1 << shift, 150_000)])  # one heavy bin
+    hist = np.bincount(keys >> shift, minlength=1 << 11)
+    for R in (2, 4, 8):
+        targets, bounds = refine_splitters(hist, R, shift)
+        sub = np.stack([np.bincount((keys[(keys >> shift) == b] >> shift2) & (n_sub - 1),
+                                    minlength=n_sub) for b in targets])
+        sp = splitters_from_subhist(bounds, targets, sub, shift, shift2)
+        dest = np.searchsorted(sp.astype(np.int64), keys, side="right")
+        loads = np.bincount(dest, minlength=R)
+        assert loads.max() < 1.02 * len(keys) / R + 400, (R, loads)
+        counts = send_counts_for(sp, hist, targets, sub, shift, shift2, R)
+        np.testing.assert_array_equal(counts, loads)
 
 
 def test_choose_splitters_balances_and_stays_on_bin_boundaries():
