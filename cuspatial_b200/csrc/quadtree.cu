@@ -339,6 +339,7 @@ expand_level_kernel(const u32* __restrict__ keys, int L, int max_depth, u32 max_
 // each spans a huge key range: the three child boundaries are searched CONCURRENTLY by three
 // 10-lane groups, 11-ary (8 dependent loads for a 100 M range instead of 27).
 constexpr int kExpandWarpNodes = kExpandBlock / 32;
+constexpr u64 kWarpLevelNodes  = 2048;  // levels with at most this many cells use the warp kernel
 __global__ void __launch_bounds__(kExpandBlock)
 expand_level_warp_kernel(const u32* __restrict__ keys, int L, int max_depth, u32 max_size, u32 cap,
                          u32* __restrict__ okey, u8* __restrict__ olevel,
@@ -569,7 +570,10 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
   }
   dev_buf<u32> tkey(cap, s), tlen(cap, s), toff(cap, s);
   dev_buf<u8> tlevel(cap, s), tint(cap, s);
-  u32 const max_tiles = (u32)div_up(cap, kExpandBlock) + 1;
+  // one look-back descriptor per tile of the largest level: 256-node tiles in the thread kernel,
+  // 8-node tiles in the warp kernel (which only runs on levels with <= kWarpLevelNodes nodes)
+  u32 const max_tiles = (u32)std::max<u64>(div_up(cap, kExpandBlock),
+                                           div_up(std::min<u64>(cap, kWarpLevelNodes), kExpandWarpNodes)) + 1;
   dev_buf<u64> lb(max_tiles, s);
   dev_buf<u32> tickets(16, s);
   BSJ_CUDA_TRY(cudaMemsetAsync(lb.get(), 0, max_tiles * sizeof(u64), s));
@@ -584,7 +588,7 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
     u64 const geo  = ((2ull << L) + 3) * ((2ull << L) + 3);
     int const grid = (int)std::min<u64>((u64)kNumSMs * 8,
                                         std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandBlock)));
-    if (geo <= 2048) {  // few, huge nodes: warp-cooperative child search
+    if (geo <= kWarpLevelNodes) {  // few, huge nodes: warp-cooperative child search
       int const wgrid = (int)std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandWarpNodes));
       expand_level_warp_kernel<<<wgrid, kExpandBlock, 0, s>>>(
         sorted_keys, L, d, max_size, (u32)cap, tkey.get(), tlevel.get(), tint.get(), tlen.get(),
