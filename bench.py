@@ -16,6 +16,11 @@ max_depth = 15, max_size = 512 (per GPU; weak scaling over GPUs).
                  (oracle/_ref, Thrust OpenMP; kind "reference") or, if absent, the repo's CPU
                  restatement (kind "port"), on a bounded sample of the same workload
 
+  gpu_reference: the reference's own CUDA implementation (its header-only Thrust/CUB path,
+                 compiled in place into oracle/_ref/libcuspatial_ref_cuda.so) on the same B200
+                 and the same inputs, run in a child process (`--impl reference-cuda`); null
+                 when that library was not built
+
 `--impl reference` times that CPU implementation only (rank 0; other ranks exit).
 """
 import argparse
@@ -146,6 +151,76 @@ def run_reference(args):
     }))
 
 
+def run_reference_cuda(args):
+    """The reference's CUDA build (oracle/_ref/libcuspatial_ref_cuda.so) on configs[1], one GPU.
+
+    Same inputs as the main arm (same generator and seed), inputs resident in HBM, each of the
+    three reference calls timed around its own synchronous call (it ends in a stream sync).
+    """
+    import torch
+
+    from cuspatial_b200 import datagen as D
+    from oracle import cudalib
+
+    if not cudalib.available():
+        print(json.dumps({"impl": "reference-cuda", "unavailable":
+                          "oracle/_ref/libcuspatial_ref_cuda.so not built or no GPU"}))
+        return
+    lib = cudalib.reference_cuda()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    n = args.points
+    (po, ro, vx, vy), ext, scale = make_polygons()
+    po, ro, vx, vy = (torch.as_tensor(a, device=dev) for a in (po, ro, vx, vy))
+    x, y = D.uniform_points_torch(n, ext, SEED, torch.float64, dev)
+    bb = lib.polygon_bounding_boxes(po, ro, vx, vy)
+    stages, rows = [], None
+    for i in range(args.warmup + args.steps):
+        tree, t1 = lib.quadtree_on_points(x, y, ext[0], ext[1], ext[2], ext[3], scale, MAX_DEPTH,
+                                          MAX_SIZE)
+        pairs, t2 = lib.join_quadtree_and_bounding_boxes(tree, *bb, ext[0], ext[2], scale,
+                                                         MAX_DEPTH)
+        hits, t3 = lib.quadtree_point_in_polygon(pairs[0], pairs[1], tree, tree["point_indices"],
+                                                 x, y, po, ro, vx, vy)
+        rows = (tree["key"].numel(), pairs[0].numel(), hits[0].numel())
+        del tree, pairs, hits
+        if i >= args.warmup:
+            stages.append((t1, t2, t3))
+    k = len(stages)
+    avg = [1e3 * sum(s[j] for s in stages) / k for j in range(3)]
+    ms = sum(avg)
+    print(json.dumps({
+        "impl": "reference-cuda", "metric": "quadtree PIP join points/sec",
+        "value": n / (ms / 1e3), "unit": "points/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "points": n,
+        "stage_ms": {"quadtree_on_points": avg[0], "join_quadtree_and_bounding_boxes": avg[1],
+                     "quadtree_point_in_polygon": avg[2]},
+        "nodes": rows[0], "pairs": rows[1], "hits": rows[2],
+        "peak_mem_GB": torch.cuda.mem_get_info(dev)[1] / 1e9 - torch.cuda.mem_get_info(dev)[0] / 1e9,
+        "what": "rapidsai/cuspatial header-only path (Thrust/CUB), nvcc sm_100a, default FP "
+                "flags, stream-ordered pool allocator; inputs resident in HBM",
+    }))
+
+
+def gpu_reference_leg(points, timeout_s=600):
+    """Run `--impl reference-cuda` in a child process (a crash or OOM there cannot take the
+    main bench line down) and return its JSON, or a dict saying why there is none."""
+    from oracle import cudalib
+
+    if not os.path.exists(cudalib.REF_CUDA_PATH):
+        return None
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-cuda",
+                              "--points", str(points), "--steps", "3", "--warmup", "1"],
+                             capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+        for line in reversed(out.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"failed": (out.stderr or out.stdout).strip()[-300:], "rc": out.returncode}
+    except Exception as e:  # timeout etc.
+        return {"failed": repr(e)[:300]}
+
+
 def run_bitmask(args):
     """configs[2]: non-indexed point_in_polygon, 100 M fp64 points x 31 polygons, one B200."""
     import torch
@@ -231,6 +306,7 @@ def run_sharded(args, dist, dev, rank, world, x, y, polys, ext, scale):
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_step = float(tmax.item()) / args.steps
     value = world * n / (ms_step / 1e3)
+
     if rank == 0:
         print(json.dumps({
             "metric": "quadtree PIP join points/sec", "value": value, "unit": "points/s",
@@ -260,16 +336,19 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--points", type=int, default=N_POINTS, help="points per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--workload", default="join", choices=["join", "bitmask"],
                     help="join = configs[1] (the headline); bitmask = configs[2], the non-indexed "
                          "point_in_polygon API on 31 polygons (informational)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference-cuda":
+        return run_reference_cuda(args)
     if args.workload == "bitmask":
         return run_bitmask(args)
 
@@ -436,6 +515,12 @@ def main():
         cpu = cpu_baseline(2_000_000)
         cpu.pop("seconds", None)
 
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        del x, y
+        torch.cuda.empty_cache()
+        gpu_ref = gpu_reference_leg(n)
+
     if rank == 0:
         print(json.dumps({
             "metric": "quadtree PIP join points/sec", "value": value, "unit": "points/s",
@@ -451,7 +536,7 @@ def main():
                        "parallelism": "replicated polygons, independent point shards"
                        if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": clocks, "gpu_reference": gpu_ref,
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage_per_step.items()},
         }))
     if dist is not None:

@@ -52,21 +52,32 @@ constexpr bool kCuda = true;
 constexpr bool kCuda = false;
 #endif
 
-// Move a result uvector into a plain buffer the caller releases with ref_free().
+// Hand a result uvector's allocation to the caller, who releases it with ref_free().
 template <typename T>
 void* release(rmm::device_uvector<T>& v, uint64_t* n)
 {
   *n = v.size();
   if (v.size() == 0) return nullptr;
-  void* p = nullptr;
+  return v.shim_release();
+}
+
+// CUDA flavour: keep freed blocks in the stream-ordered pool between calls, as the RMM pool
+// resource the reference normally runs on does (otherwise every call pays cudaMalloc/cudaFree).
+void init_once()
+{
 #if defined(__CUDACC__)
-  cudaMalloc(&p, v.size() * sizeof(T));
-  cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyDeviceToDevice);
-#else
-  p = std::malloc(v.size() * sizeof(T));
-  std::memcpy(p, v.data(), v.size() * sizeof(T));
+  static bool done = false;
+  if (!done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done = true;
+  }
 #endif
-  return p;
 }
 
 template <typename T>
@@ -188,6 +199,7 @@ template <typename F>
 int guarded(F&& f)
 {
   try {
+    init_once();
     return f();
   } catch (std::exception const& e) {
     g_err = e.what();
@@ -205,7 +217,7 @@ const char* ref_last_error() { return g_err.c_str(); }
 void ref_free(void* p)
 {
 #if defined(__CUDACC__)
-  cudaFree(p);
+  cudaFreeAsync(p, 0);
 #else
   std::free(p);
 #endif

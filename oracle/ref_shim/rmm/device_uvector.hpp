@@ -99,6 +99,14 @@ class device_uvector {
     return p_[i];
 #endif
   }
+  // shim-only: hand the allocation to the caller (freed with the resource's deallocate)
+  T* shim_release() noexcept
+  {
+    T* p = p_;
+    p_   = nullptr;
+    n_ = cap_ = 0;
+    return p;
+  }
   T front_element(cuda_stream_view s) const { return element(0, s); }
   T back_element(cuda_stream_view s) const { return element(n_ - 1, s); }
 

@@ -134,6 +134,21 @@ def test_config1_1M_uniform_263_polygons_equals_oracle_and_reference(oracle_lib)
     assert len(g["hits"][0]) > 500_000
 
 
+@pytest.mark.parametrize("dtype,n,kind", [(np.float64, 5_000_000, "u"), (np.float32, 5_000_000, "u"),
+                                          (np.float64, 3_000_000, "c")])
+def test_equals_reference_cuda_build(dtype, n, kind):
+    """GPU vs GPU: the reference's own Thrust/CUB implementation (real nvcc FMA contraction,
+    real device float->u16 conversion) compiled in place from its headers, on the same B200.
+    Sizes the CPU checkers cannot reach in seconds; duplicates and out-of-bbox points included."""
+    from oracle import cudalib
+    from util import run_ref_cuda
+
+    if not cudalib.available():
+        pytest.skip("oracle/_ref/libcuspatial_ref_cuda.so not built (needs /root/reference)")
+    c = make_case(n, 263, 15, kind, dtype, seed=77, median_vertices=120, oob=1000, dups=5000)
+    assert_same(run_gpu(c, 512), run_ref_cuda(c, 512), "gpu vs reference CUDA build")
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_near_edge_points_equal_oracle(oracle_lib, dtype):
     """The 4-ULP on-edge rule, vertical-edge quirk and exact edge skipping near boundaries."""

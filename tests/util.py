@@ -73,6 +73,30 @@ def run_gpu(c, max_size, use_grid_hint=True):
     return out
 
 
+def run_ref_cuda(c, max_size):
+    """Full path on the reference's own CUDA build (oracle/_ref/libcuspatial_ref_cuda.so)."""
+    import torch
+
+    from oracle import cudalib
+
+    lib = cudalib.reference_cuda()
+    dev = "cuda"
+    ext = c["ext"]
+    x, y = torch.as_tensor(c["x"], device=dev), torch.as_tensor(c["y"], device=dev)
+    po, ro, vx, vy = (torch.as_tensor(a, device=dev) for a in (c["po"], c["ro"], c["vx"], c["vy"]))
+    tree, _ = lib.quadtree_on_points(x, y, ext[0], ext[1], ext[2], ext[3], c["scale"], c["depth"],
+                                     max_size)
+    bb = lib.polygon_bounding_boxes(po, ro, vx, vy)
+    pairs, _ = lib.join_quadtree_and_bounding_boxes(tree, *bb, ext[0], ext[2], c["scale"],
+                                                    c["depth"])
+    hits, _ = lib.quadtree_point_in_polygon(pairs[0], pairs[1], tree, tree["point_indices"], x, y,
+                                            po, ro, vx, vy)
+    return dict(tree={k: v.cpu().numpy() for k, v in tree.items()},
+                bbox=tuple(b.cpu().numpy() for b in bb),
+                pairs=tuple(p.cpu().numpy() for p in pairs),
+                hits=tuple(h.cpu().numpy() for h in hits))
+
+
 def assert_same(a, b, what=""):
     for k in TREE_COLS + ("point_indices",):
         np.testing.assert_array_equal(a["tree"][k], b["tree"][k], err_msg="%s tree.%s" % (what, k))
