@@ -1,16 +1,18 @@
 """cuspatial_b200 -- B200-native quadtree point-in-polygon spatial join.
 
 Drop-in for one hot path of rapidsai/cuspatial (quadtree_on_points ->
-join_quadtree_and_bounding_boxes -> quadtree_point_in_polygon, plus the bitmask point_in_polygon
-and polygon_bounding_boxes).  Hand-written sm_100a CUDA behind a C ABI
+join_quadtree_and_bounding_boxes -> quadtree_point_in_polygon, plus the bitmask and pairwise
+point_in_polygon, polygon_bounding_boxes and the contains_properly driver).  Hand-written sm_100a CUDA behind a C ABI
 (include/cuspatial_b200.h); this package is the thin ctypes layer mirroring the reference's Python
 functions.  There is no CPU fallback.
 """
-from .api import (join_quadtree_and_bounding_boxes, point_in_polygon, point_in_polygon_bitmask,
+from .api import (contains_properly, join_quadtree_and_bounding_boxes,
+                  pairwise_point_in_polygon, point_in_polygon, point_in_polygon_bitmask,
                   polygon_bounding_boxes, quadtree_on_points, quadtree_point_in_polygon)
 from .frame import Frame
 
 __all__ = [
     "quadtree_on_points", "join_quadtree_and_bounding_boxes", "quadtree_point_in_polygon",
-    "point_in_polygon", "point_in_polygon_bitmask", "polygon_bounding_boxes", "Frame",
+    "point_in_polygon", "point_in_polygon_bitmask", "polygon_bounding_boxes",
+    "pairwise_point_in_polygon", "contains_properly", "Frame",
 ]

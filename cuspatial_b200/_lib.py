@@ -54,7 +54,8 @@ class bsj_pairs(C.Structure):
 EXPORTED_SYMBOLS = [
     "bsj_quadtree_on_points", "bsj_join_quadtree_and_bounding_boxes",
     "bsj_quadtree_point_in_polygon", "bsj_quadtree_point_in_polygon_ex", "bsj_quadtree_point_in_polygon_compact",
-    "bsj_expand_pip_compact", "bsj_point_in_polygon", "bsj_polygon_bounding_boxes",
+    "bsj_expand_pip_compact", "bsj_point_in_polygon", "bsj_pairwise_point_in_polygon",
+    "bsj_polygon_bounding_boxes",
     "bsj_point_keys_histogram", "bsj_key_subhistogram", "bsj_partition_points", "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
     "bsj_kernel_launch_count", "bsj_set_profiling", "bsj_get_profile",
 ]
@@ -93,6 +94,8 @@ def lib():
         u64, C.POINTER(bsj_grid), C.POINTER(bsj_allocator), vp, C.POINTER(bsj_pip_compact)]
     L.bsj_expand_pip_compact.argtypes = [vp, C.POINTER(bsj_pip_compact), C.c_uint32, vp, vp, vp]
     L.bsj_point_in_polygon.argtypes = [vp, vp, C.c_int, u64, vp, u64, vp, u64, vp, vp, u64, vp, vp]
+    L.bsj_pairwise_point_in_polygon.argtypes = [vp, vp, C.c_int, u64, vp, u64, vp, u64, vp, vp, u64,
+                                                vp, vp]
     L.bsj_polygon_bounding_boxes.argtypes = [vp, u64, vp, u64, vp, vp, C.c_int, u64, dbl, vp,
                                              vp, vp, vp, vp]
     L.bsj_point_keys_histogram.argtypes = [vp, vp, C.c_int, u64, dbl, dbl, dbl, dbl, dbl, C.c_int8,

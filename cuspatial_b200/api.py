@@ -334,6 +334,83 @@ def point_in_polygon(points, polygons):
     return Frame([(i, ((mask >> i) & 1).to(torch.bool)) for i in range(n_poly)])
 
 
+def pairwise_point_in_polygon(points, polygons):
+    """Point i against polygon i: one UINT8 per pair, 1 = strictly inside
+    (reference: _lib/pairwise_point_in_polygon.pyx:15-44 over
+    cpp/src/point_in_polygon/point_in_polygon.cu:172-190)."""
+    x, y = _split_points(points)
+    po, ro, vx, vy = _split_polygons(polygons)
+    if x.dtype != vx.dtype or vx.dtype != vy.dtype:
+        raise RuntimeError("All points much have the same type for both x and y")
+    po = _as_cuda(po, torch.int32)
+    ro = _as_cuda(ro, torch.int32)
+    out = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().bsj_pairwise_point_in_polygon(
+            _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], _ptr(po), po.shape[0], _ptr(ro),
+            ro.shape[0], _ptr(vx), _ptr(vy), vx.shape[0], _stream(x.device), _ptr(out))
+        _lib.check(rc)
+    return out
+
+
+def _quadtree_contains_properly(points, polygons):
+    """core/binpreds/contains.py:19-74: the GeoPandas-compatible `contains_properly` driver of the
+    hot path (max_depth 15, max_size ceil(sqrt(N)), minimum scale, extent of the polygon
+    vertices).  Returns Frame[point_index (ORIGINAL point id), part_index (polygon id)]."""
+    from math import ceil, sqrt
+
+    x, y = _split_points(points)
+    po, ro, vx, vy = _split_polygons(polygons)
+    max_depth = 15
+    min_size = ceil(sqrt(x.shape[0])) if x.shape[0] else 1
+    if max(int(po.shape[0]) - 1, 0) == 0:
+        return Frame([])
+    x_min, x_max = float(vx.min()), float(vx.max())
+    y_min, y_max = float(vy.min()), float(vy.max())
+    scale = max(x_max - x_min, y_max - y_min) / ((1 << max_depth) + 2)
+    point_indices, quadtree = quadtree_on_points((x, y), x_min, x_max, y_min, y_max, scale,
+                                                 max_depth, min_size)
+    poly_bboxes = polygon_bounding_boxes((po, ro, vx, vy))
+    intersections = join_quadtree_and_bounding_boxes(quadtree, poly_bboxes, x_min, x_max, y_min,
+                                                     y_max, scale, max_depth)
+    rows = quadtree_point_in_polygon(intersections, quadtree, point_indices, (x, y),
+                                     (po, ro, vx, vy))
+    # (torch has no uint32 gather: same bits through an int32 view)
+    original = point_indices.view(torch.int32)[rows["point_index"].to(torch.int64)].view(torch.uint32)
+    return Frame([("point_index", original), ("part_index", rows["polygon_index"])])
+
+
+def _pairwise_contains_properly(points, polygons):
+    """contains.py:123-170 -> Frame[pairwise_index, point_index, result] of the true pairs."""
+    flags = pairwise_point_in_polygon(points, polygons).to(torch.bool)
+    trues = torch.nonzero(flags).reshape(-1)
+    return Frame([("pairwise_index", trues), ("point_index", trues),
+                  ("result", torch.ones_like(trues, dtype=torch.bool))])
+
+
+def _brute_force_contains_properly(points, polygons):
+    """contains.py:77-120 -> Frame with one bool column per polygon."""
+    return point_in_polygon(points, polygons)
+
+
+def contains_properly(polygons, points, mode="pairwise"):
+    """core/binpreds/contains.py:173-185: which points are properly contained (boundary excluded)
+    by which polygons; `mode` = "quadtree" (the indexed hot path), "pairwise" or anything else
+    for the <= 31-polygon all-pairs bitmask."""
+    if mode == "quadtree":
+        return _quadtree_contains_properly(points, polygons)
+    if mode == "pairwise":
+        return _pairwise_contains_properly(points, polygons)
+    table = _brute_force_contains_properly(points, polygons)
+    cols = [table[c] for c in table.columns]
+    if not cols:
+        return Frame([])
+    grid = torch.stack(cols, dim=1)                     # [point, polygon], like DataFrame.stack()
+    nz = torch.nonzero(grid)
+    return Frame([("point_index", nz[:, 0]), ("part_index", nz[:, 1]),
+                  ("result", torch.ones(nz.shape[0], dtype=torch.bool, device=grid.device))])
+
+
 def polygon_bounding_boxes(polygons, expansion_radius=0.0):
     """Axis-aligned bounding box of every polygon -> Frame[minx, miny, maxx, maxy]
     (reference: core/spatial/bounding.py:19-80)."""

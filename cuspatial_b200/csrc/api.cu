@@ -44,6 +44,10 @@ void point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_poin
                            const i32* poly_offsets, u64 n_poly_offsets, const i32* ring_offsets,
                            u64 n_ring_offsets, const void* vx, const void* vy, u64 n_verts,
                            cudaStream_t s, i32* out_mask);
+void pairwise_point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_points,
+                                    const i32* poly_offsets, u64 n_poly_offsets,
+                                    const i32* ring_offsets, u64 n_ring_offsets, const void* vx,
+                                    const void* vy, u64 n_verts, cudaStream_t s, u8* out);
 void polygon_bounding_boxes_impl(const u32* poly_offsets, u64 n_poly_offsets,
                                  const u32* ring_offsets, u64 n_ring_offsets, const void* vx,
                                  const void* vy, int dtype, u64 n_verts, double r, cudaStream_t s,
@@ -307,6 +311,24 @@ int bsj_point_in_polygon(const void* point_x, const void* point_y, int dtype, ui
     point_in_polygon_impl(point_x, point_y, dtype, n_points, poly_offsets, n_poly_offsets,
                           ring_offsets, n_ring_offsets, poly_points_x, poly_points_y, n_poly_points,
                           (cudaStream_t)stream, out_mask);
+  });
+}
+
+int bsj_pairwise_point_in_polygon(const void* point_x, const void* point_y, int dtype,
+                                  uint64_t n_points, const int32_t* poly_offsets,
+                                  uint64_t n_poly_offsets, const int32_t* ring_offsets,
+                                  uint64_t n_ring_offsets, const void* poly_points_x,
+                                  const void* poly_points_y, uint64_t n_poly_points,
+                                  bsj_stream_t stream, uint8_t* out_flags)
+{
+  return guarded([&] {
+    check_dtype(dtype);
+    // point_in_polygon.cu:108-110
+    BSJ_EXPECTS(n_points == 0 || (point_x && point_y && out_flags),
+                "All points must have both x and y values");
+    pairwise_point_in_polygon_impl(point_x, point_y, dtype, n_points, poly_offsets, n_poly_offsets,
+                                   ring_offsets, n_ring_offsets, poly_points_x, poly_points_y,
+                                   n_poly_points, (cudaStream_t)stream, out_flags);
   });
 }
 

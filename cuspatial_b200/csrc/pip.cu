@@ -1119,6 +1119,61 @@ pip_bitmask_kernel(const T* __restrict__ px, const T* __restrict__ py, u64 n_poi
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// pairwise point_in_polygon (detail/point_in_polygon.cuh:104-145): point i against polygon i.
+// One warp per pair, lanes stride the ring's edges (coalesced vertex loads), crossing parity by
+// ballot/popc.  The reference walks the ring sequentially and keeps `b` unchanged over a
+// degenerate segment (is_point_in_polygon.cuh:65-66), so the lane-parallel form (b = previous
+// vertex) is exact only if no segment of the polygon is degenerate -- then no `continue` ever
+// fires and b is always the previous vertex.  Otherwise lane 0 replays the reference loop.
+// On-edge anywhere => false, independent of order (the reference breaks out with within=false).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+pip_pairwise_kernel(const T* __restrict__ px, const T* __restrict__ py, u64 n_pairs,
+                    const u32* __restrict__ poly_offsets, const u32* __restrict__ ring_offsets,
+                    const T* __restrict__ vx, const T* __restrict__ vy, u8* __restrict__ out)
+{
+  u32 const lane    = lane_id();
+  u64 const warp    = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  u64 const n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  for (u64 i = warp; i < n_pairs; i += n_warps) {
+    T const x = __ldg(px + i), y = __ldg(py + i);
+    u32 const r0 = __ldg(poly_offsets + i), r1 = __ldg(poly_offsets + i + 1);
+    u32 flips = 0;
+    bool degenerate = false, on_edge = false;
+    for (u32 r = r0; r < r1; ++r) {
+      u32 const v0 = __ldg(ring_offsets + r), v1 = __ldg(ring_offsets + r + 1);
+      for (u32 e = v0 + lane; e < v1; e += 32) {
+        u32 const pe = e == v0 ? v1 - 1 : e - 1;
+        T const ax = __ldg(vx + e), ay = __ldg(vy + e);
+        T const bx = __ldg(vx + pe), by = __ldg(vy + pe);
+        T const run  = fpp<T>::sub(bx, ax);
+        T const rise = fpp<T>::sub(by, ay);
+        if (float_equal(run, (T)0) && float_equal(rise, (T)0)) degenerate = true;
+        T const rtp  = fpp<T>::sub(y, ay);
+        T const rntp = fpp<T>::sub(x, ax);
+        T const u    = fpp<T>::mul(run, rtp);
+        T const v    = fpp<T>::mul(rntp, rise);
+        if (float_equal(u, v)) {
+          T const lo = ax > bx ? bx : ax, hi = ax > bx ? ax : bx;
+          if (lo <= x && x <= hi) on_edge = true;
+        }
+        bool const y1 = ay > y, y0 = by > y;
+        if (y1 != y0 && ((v < u) != y1)) flips ^= 1u;
+      }
+    }
+    bool const any_degenerate = __any_sync(0xffffffffu, degenerate);
+    bool const any_on_edge    = __any_sync(0xffffffffu, on_edge);
+    u32 const parity          = __popc(__ballot_sync(0xffffffffu, flips & 1u)) & 1u;
+    if (lane == 0) {
+      bool hit = !any_on_edge && parity;
+      if (any_degenerate) hit = pip_reference<T>(x, y, ring_offsets, r0, r1, vx, vy);
+      out[i] = hit ? 1 : 0;
+    }
+  }
+}
+
 // per-polygon bounding boxes (detail/bounding_boxes.cuh:36-60,136-184): min/max of (v -+ r)
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -1490,6 +1545,30 @@ void point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_poin
   else
     pip_bitmask_t<double>(px, py, n_points, (const u32*)poly_offsets, n_poly_offsets,
                           (const u32*)ring_offsets, n_ring_offsets, vx, vy, n_verts, s, out_mask);
+}
+
+void pairwise_point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_points,
+                                    const i32* poly_offsets, u64 n_poly_offsets,
+                                    const i32* ring_offsets, u64 n_ring_offsets, const void* vx,
+                                    const void* vy, u64 n_verts, cudaStream_t s, u8* out)
+{
+  // cpp/src/point_in_polygon/point_in_polygon.cu:122-125
+  BSJ_EXPECTS(n_points == (n_poly_offsets ? n_poly_offsets - 1 : 0),
+              "Must pass in the same number of points as polygons.");
+  if (n_points == 0) return;
+  (void)n_ring_offsets;
+  (void)n_verts;
+  int const grid = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_points * 32, 256));
+  // offsets are non-negative int32: reinterpreting as uint32 is value preserving
+  if (dtype == BSJ_FLOAT32)
+    pip_pairwise_kernel<float><<<std::max(grid, 1), 256, 0, s>>>(
+      (const float*)px, (const float*)py, n_points, (const u32*)poly_offsets,
+      (const u32*)ring_offsets, (const float*)vx, (const float*)vy, out);
+  else
+    pip_pairwise_kernel<double><<<std::max(grid, 1), 256, 0, s>>>(
+      (const double*)px, (const double*)py, n_points, (const u32*)poly_offsets,
+      (const u32*)ring_offsets, (const double*)vx, (const double*)vy, out);
+  BSJ_CHECK_LAUNCH();
 }
 
 void polygon_bounding_boxes_impl(const u32* poly_offsets, u64 n_poly_offsets,

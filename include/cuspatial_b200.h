@@ -222,6 +222,20 @@ int bsj_point_in_polygon(const void* point_x, const void* point_y, int dtype, ui
                          uint64_t n_poly_points, bsj_stream_t stream, int32_t* out_mask);
 
 /*
+ * Replaces cuspatial::pairwise_point_in_polygon
+ *   (cpp/include/cuspatial/point_in_polygon.hpp:124-131, cpp/src/point_in_polygon/point_in_polygon.cu:172-190;
+ *    header form cpp/include/cuspatial/detail/point_in_polygon.cuh:104-145): point i is tested
+ * against polygon i only. n_points must equal n_poly_offsets-1 (point_in_polygon.cu:122-125).
+ * out_flags: caller-allocated UINT8[n_points], 1 iff point i is inside polygon i (boundary => 0).
+ */
+int bsj_pairwise_point_in_polygon(const void* point_x, const void* point_y, int dtype,
+                                  uint64_t n_points, const int32_t* poly_offsets,
+                                  uint64_t n_poly_offsets, const int32_t* ring_offsets,
+                                  uint64_t n_ring_offsets, const void* poly_points_x,
+                                  const void* poly_points_y, uint64_t n_poly_points,
+                                  bsj_stream_t stream, uint8_t* out_flags);
+
+/*
  * Replaces cuspatial::polygon_bounding_boxes
  *   (cpp/include/cuspatial/bounding_boxes.hpp, cpp/src/bounding_boxes/polygon_bounding_boxes.cu:132-161):
  * the producer of the bbox table the join consumes. Outputs: 4 caller-allocated columns of

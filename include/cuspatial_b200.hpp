@@ -6,6 +6,7 @@
 //   cuspatial::join_quadtree_and_bounding_boxes  cpp/include/cuspatial/spatial_join.hpp:66-75
 //   cuspatial::quadtree_point_in_polygon         cpp/include/cuspatial/spatial_join.hpp:116-126
 //   cuspatial::point_in_polygon                  cpp/include/cuspatial/point_in_polygon.hpp:75-82
+//   cuspatial::pairwise_point_in_polygon         cpp/include/cuspatial/point_in_polygon.hpp:124-131
 //
 // Header only; link against libcuspatial_b200.so.  Errors are rethrown as the reference does:
 // std::logic_error for CUSPATIAL_EXPECTS conditions (cuspatial::logic_error derives from it,
@@ -182,6 +183,23 @@ void point_in_polygon(column_view<T> test_points_x, column_view<T> test_points_y
                                      poly_ring_offsets.data, poly_ring_offsets.size,
                                      poly_points_x.data, poly_points_y.data, poly_points_x.size,
                                      stream, out_mask));
+}
+
+/// cuspatial::pairwise_point_in_polygon(test_points_x, test_points_y, poly_offsets,
+/// poly_ring_offsets, poly_points_x, poly_points_y, mr) -> UINT8 column (caller-allocated here).
+template <typename T>
+void pairwise_point_in_polygon(column_view<T> test_points_x, column_view<T> test_points_y,
+                               column_view<int32_t> poly_offsets,
+                               column_view<int32_t> poly_ring_offsets,
+                               column_view<T> poly_points_x, column_view<T> poly_points_y,
+                               uint8_t* out_flags, bsj_stream_t stream = nullptr)
+{
+  if (test_points_x.size != test_points_y.size || poly_points_x.size != poly_points_y.size)
+    throw std::logic_error("All points must have both x and y values");
+  detail::check(bsj_pairwise_point_in_polygon(
+    test_points_x.data, test_points_y.data, detail::dtype_of<T>(), test_points_x.size,
+    poly_offsets.data, poly_offsets.size, poly_ring_offsets.data, poly_ring_offsets.size,
+    poly_points_x.data, poly_points_y.data, poly_points_x.size, stream, out_flags));
 }
 
 }  // namespace cuspatial_b200

@@ -127,6 +127,18 @@ class HostLib:
             _p(vx), _p(vy), C.c_uint64(len(vx)), _p(out)))
         return out
 
+    def pairwise_point_in_polygon(self, px, py, poly_offsets, ring_offsets, vx, vy):
+        px = np.ascontiguousarray(px)
+        py, vx, vy = (np.ascontiguousarray(a, dtype=px.dtype) for a in (py, vx, vy))
+        poly_offsets = np.ascontiguousarray(poly_offsets, dtype=np.int32)
+        ring_offsets = np.ascontiguousarray(ring_offsets, dtype=np.int32)
+        out = np.zeros(len(px), dtype=np.uint8)
+        self._check(self._f("pairwise_point_in_polygon")(
+            _p(px), _p(py), _dt(px), C.c_uint64(len(px)), _p(poly_offsets),
+            C.c_uint64(len(poly_offsets)), _p(ring_offsets), C.c_uint64(len(ring_offsets)),
+            _p(vx), _p(vy), C.c_uint64(len(vx)), _p(out)))
+        return out
+
     def polygon_bounding_boxes(self, poly_offsets, ring_offsets, vx, vy, expansion=0.0):
         vx = np.ascontiguousarray(vx)
         vy = np.ascontiguousarray(vy, dtype=vx.dtype)

@@ -515,6 +515,26 @@ int pip_t(T const* px, T const* py, uint64_t n_points, int32_t const* poly_offse
   return 0;
 }
 
+// detail/point_in_polygon.cuh:104-145  pairwise: point i against polygon i, uint8 result
+template <typename T>
+int pairwise_pip_t(T const* px, T const* py, uint64_t n_points, int32_t const* poly_offsets,
+                   uint64_t n_poly_offsets, int32_t const* ring_offsets, T const* vx, T const* vy,
+                   uint8_t* out)
+{
+  // cpp/src/point_in_polygon/point_in_polygon.cu:122-125
+  if (n_points != (n_poly_offsets ? n_poly_offsets - 1 : 0)) {
+    g_err = "Must pass in the same number of points as polygons.";
+    return 1;
+  }
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t i = 0; i < (int64_t)n_points; ++i)
+    out[i] = is_point_in_polygon<T, int32_t>(px[i], py[i], ring_offsets, poly_offsets[i],
+                                             poly_offsets[i + 1], vx, vy)
+               ? 1
+               : 0;
+  return 0;
+}
+
 // detail/bounding_boxes.cuh:36-60,136-184  per-polygon min/max of (v - r, v + r)
 template <typename T>
 int poly_bbox_t(uint32_t const* poly_offsets, uint64_t n_poly_offsets,
@@ -612,6 +632,21 @@ int orc_point_in_polygon(void const* px, void const* py, int dtype, uint64_t n_p
            : pip_t<double>((double const*)px, (double const*)py, n_points, poly_offsets,
                            n_poly_offsets, ring_offsets, n_ring_offsets, (double const*)vx,
                            (double const*)vy, out_mask);
+}
+
+int orc_pairwise_point_in_polygon(void const* px, void const* py, int dtype, uint64_t n_points,
+                                  int32_t const* poly_offsets, uint64_t n_poly_offsets,
+                                  int32_t const* ring_offsets, uint64_t n_ring_offsets,
+                                  void const* vx, void const* vy, uint64_t n_verts, uint8_t* out)
+{
+  (void)n_verts;
+  (void)n_ring_offsets;
+  return dtype == 0 ? pairwise_pip_t<float>((float const*)px, (float const*)py, n_points,
+                                            poly_offsets, n_poly_offsets, ring_offsets,
+                                            (float const*)vx, (float const*)vy, out)
+                    : pairwise_pip_t<double>((double const*)px, (double const*)py, n_points,
+                                             poly_offsets, n_poly_offsets, ring_offsets,
+                                             (double const*)vx, (double const*)vy, out);
 }
 
 int orc_polygon_bounding_boxes(uint32_t const* poly_offsets, uint64_t n_poly_offsets,

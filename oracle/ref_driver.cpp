@@ -7,6 +7,7 @@
 //   - join_quadtree_and_bboxes  : cpp/src/join/quadtree_bbox_filtering.cu:40-80
 //   - quadtree_point_in_polygon : cpp/src/join/quadtree_point_in_polygon.cu:45-120
 //   - point_in_polygon (bitmask): cpp/src/point_in_polygon/point_in_polygon.cu:52-98
+//   - pairwise_point_in_polygon : cpp/src/point_in_polygon/point_in_polygon.cu:52-98,172-190
 //   - polygon_bounding_boxes    : cpp/src/bounding_boxes/polygon_bounding_boxes.cu:132-161
 // i.e. cast the double parameters to T, wrap raw columns into the reference's iterators,
 // call the header-only entry point, hand the result arrays back.
@@ -170,6 +171,28 @@ int pip_t(T const* px, T const* py, uint64_t n_points, int32_t const* poly_offse
 }
 
 template <typename T>
+int pairwise_pip_t(T const* px, T const* py, uint64_t n_points, int32_t const* poly_offsets,
+                   uint64_t n_poly_offsets, int32_t const* ring_offsets, uint64_t n_ring_offsets,
+                   T const* vx, T const* vy, uint64_t n_verts, uint8_t* out)
+{
+  rmm::cuda_stream_view stream{};
+  // cpp/src/point_in_polygon/point_in_polygon.cu:122-125 (column-layer check)
+  if (n_points != (n_poly_offsets ? n_poly_offsets - 1 : 0))
+    throw std::logic_error("Must pass in the same number of points as polygons.");
+  // same construction as cpp/src/point_in_polygon/point_in_polygon.cu:71-93
+  auto points_begin = cuspatial::make_vec_2d_iterator(px, py);
+  auto multipoints  = cuspatial::make_multipoint_range(
+    n_points, thrust::make_counting_iterator(0), n_points, points_begin);
+  auto polygon_size = n_poly_offsets - 1;
+  auto multipolygons = cuspatial::make_multipolygon_range(
+    polygon_size, thrust::make_counting_iterator(0), polygon_size, poly_offsets,
+    n_ring_offsets - 1, ring_offsets, n_verts, cuspatial::make_vec_2d_iterator(vx, vy));
+  cuspatial::pairwise_point_in_polygon(multipoints, multipolygons, out, stream);
+  stream.synchronize();
+  return 0;
+}
+
+template <typename T>
 int poly_bbox_t(uint32_t const* poly_offsets, uint64_t n_poly_offsets, uint32_t const* ring_offsets,
                 uint64_t n_ring_offsets, T const* vx, T const* vy, uint64_t n_verts, T expansion,
                 T* x0, T* y0, T* x1, T* y1)
@@ -296,6 +319,23 @@ int ref_point_in_polygon(void const* px, void const* py, int dtype, uint64_t n_p
              : pip_t<double>((double const*)px, (double const*)py, n_points, poly_offsets,
                              n_poly_offsets, ring_offsets, n_ring_offsets, (double const*)vx,
                              (double const*)vy, n_verts, out_mask);
+  });
+}
+
+int ref_pairwise_point_in_polygon(void const* px, void const* py, int dtype, uint64_t n_points,
+                                  int32_t const* poly_offsets, uint64_t n_poly_offsets,
+                                  int32_t const* ring_offsets, uint64_t n_ring_offsets,
+                                  void const* vx, void const* vy, uint64_t n_verts, uint8_t* out)
+{
+  return guarded([&] {
+    if (n_points == 0 && n_poly_offsets <= 1) return 0;
+    return dtype == 0
+             ? pairwise_pip_t<float>((float const*)px, (float const*)py, n_points, poly_offsets,
+                                     n_poly_offsets, ring_offsets, n_ring_offsets,
+                                     (float const*)vx, (float const*)vy, n_verts, out)
+             : pairwise_pip_t<double>((double const*)px, (double const*)py, n_points, poly_offsets,
+                                      n_poly_offsets, ring_offsets, n_ring_offsets,
+                                      (double const*)vx, (double const*)vy, n_verts, out);
   });
 }
 

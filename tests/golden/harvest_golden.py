@@ -9,6 +9,7 @@ Sources (rapidsai/cuspatial 25.06):
   cpp/tests/index/point_quadtree_test.cu:82-222            quadtree known answers
   cpp/tests/join/quadtree_point_in_polygon_test_small.cu   71 points, 4 polygons, pairs, PIP rows
   cpp/tests/point_in_polygon/point_in_polygon_test.cu      predicate edge cases (planar)
+  cpp/tests/point_in_polygon/pairwise_point_in_polygon_test.cu:75-325  pairwise known answers
   python/.../tests/spatial/join/test_spatial_join.py:321-432  linestring bbox join (21 pairs)
 
 Run:  python tests/golden/harvest_golden.py
@@ -183,6 +184,60 @@ def harvest_pip_tests():
     return cases
 
 
+def _group_after(body, name):
+    """First brace group following `name` in a test body, as a python literal."""
+    i = body.index(name)
+    return brace_to_py(balanced(body, body.index("{", i)))
+
+
+def harvest_pairwise_tests():
+    """pairwise_point_in_polygon_test.cu: every test is reduced to a list of calls
+    {points, expected}, each call pairing point i with polygon i of the shared polygon set."""
+    path = os.path.join(REF, "cpp/tests/point_in_polygon/pairwise_point_in_polygon_test.cu")
+    src = strip_comments(open(path).read())
+    src = re.sub(r"\b0b([01]+)\b", lambda m: str(int(m.group(1), 2)), src)
+    cases = []
+    for m in re.finditer(r"TYPED_TEST\(PairwisePointInPolygonTest,\s*(\w+)\)", src):
+        name = m.group(1)
+        body = balanced(src, src.index("{", m.end()))
+        case = {"name": name,
+                "source": "cpp/tests/point_in_polygon/pairwise_point_in_polygon_test.cu (%s)" % name}
+        if "CUSPATIAL_RUN_TEST(" in body:
+            call = balanced(body, body.index("(", body.index("CUSPATIAL_RUN_TEST(")))[1:-1]
+            pts, part, ring, verts, expected = [brace_to_py(a)
+                                                for a in split_top_level_args(call)[1:]]
+            calls = [{"points": pts, "expected": [int(v) for v in expected]}]
+        elif name == "32PolygonSupport":
+            # polygons come from the two functors above the test (x: -1,-1,1,1,-1; y: -1,1,1,-1,-1
+            # by vertex index % 5; ring k starts at vertex 5k; polygon k = ring k)
+            pts = _group_after(body, "test_point")
+            expected = _group_after(body, "expected")
+            n = len(pts)
+            part = list(range(n + 1))
+            ring = [5 * k for k in range(n + 1)]
+            xs, ys = [-1.0, -1.0, 1.0, 1.0, -1.0], [-1.0, 1.0, 1.0, -1.0, -1.0]
+            verts = [[xs[i % 5], ys[i % 5]] for i in range(5 * n)]
+            calls = [{"points": pts, "expected": [int(v) for v in expected]}]
+        else:
+            pts = _group_after(body, "point_list")
+            part = _group_after(body, "poly_offsets")
+            ring = _group_after(body, "poly_ring_offsets")
+            verts = _group_after(body, "poly_point ")
+            expected = _group_after(body, "expected")
+            while expected and isinstance(expected[0], list):
+                expected = expected[0]
+            expected = [int(v) for v in expected]
+            n_poly = len(part) - 1
+            if n_poly == 1:        # one call per point against the only polygon
+                calls = [{"points": [pts[i]], "expected": [expected[i]]} for i in range(len(pts))]
+            else:                  # `for (i = 0; i < size / 2; i += 2)`: points i, i+1 vs polygons 0, 1
+                calls = [{"points": [pts[i], pts[i + 1]], "expected": [expected[i], expected[i + 1]]}
+                         for i in range(0, len(pts) // 2, 2)]
+        case.update(part_offsets=part, ring_offsets=ring, vertices=verts, calls=calls)
+        cases.append(case)
+    return cases
+
+
 def harvest_linestring_join():
     path = os.path.join(
         REF, "python/cuspatial/cuspatial/tests/spatial/join/test_spatial_join.py"
@@ -211,12 +266,13 @@ def main():
         "small_join": harvest_small_join(),
         "quadtree_cases": harvest_quadtree_tests(),
         "pip_cases": harvest_pip_tests(),
+        "pairwise_cases": harvest_pairwise_tests(),
         "linestring_join": harvest_linestring_join(),
     }
     with open(OUT, "w") as f:
         json.dump(gold, f, indent=1)
     print("wrote", OUT, ":", len(gold["quadtree_cases"]), "quadtree cases,",
-          len(gold["pip_cases"]), "pip cases,", len(gold["small_join"]["points"]), "points")
+          len(gold["pip_cases"]), "pip cases,", len(gold["pairwise_cases"]), "pairwise cases,", len(gold["small_join"]["points"]), "points")
 
 
 if __name__ == "__main__":

@@ -233,6 +233,73 @@ def test_bitmask_equals_oracle(oracle_lib, dtype):
     np.testing.assert_array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_golden_pairwise_cases(golden, dtype):
+    """pairwise_point_in_polygon_test.cu known answers (point i vs polygon i)."""
+    import cuspatial_b200 as cs
+
+    for c in golden["pairwise_cases"]:
+        v = np.array(c["vertices"], dtype=dtype)
+        for call in c["calls"]:
+            p = np.array(call["points"], dtype=dtype)
+            k = len(p)
+            got = cs.pairwise_point_in_polygon(
+                (_t(p[:, 0]), _t(p[:, 1])),
+                (_t(np.array(c["part_offsets"][:k + 1], np.int32)),
+                 _t(np.array(c["ring_offsets"], np.int32)), _t(v[:, 0]), _t(v[:, 1])))
+            assert got.dtype.is_floating_point is False and got.element_size() == 1
+            assert got.cpu().numpy().tolist() == call["expected"], (c["name"], dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("degenerate", [False, True])
+def test_pairwise_equals_oracle(oracle_lib, dtype, degenerate):
+    """Random pairs incl. points on vertices / edges / a few ulps off, and rings with
+    zero-length segments (the reference keeps `b` over those: lane-parallel form must fall back)."""
+    import cuspatial_b200 as cs
+    from util import pairwise_case
+
+    px, py, po, ro, vx, vy = pairwise_case(20000, dtype, 13, degenerate)
+    want = oracle_lib.pairwise_point_in_polygon(px, py, po, ro, vx, vy)
+    got = cs.pairwise_point_in_polygon((_t(px), _t(py)), (_t(po), _t(ro), _t(vx), _t(vy)))
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    pairs = cs.contains_properly((_t(po), _t(ro), _t(vx), _t(vy)), (_t(px), _t(py)), mode="pairwise")
+    np.testing.assert_array_equal(pairs["point_index"].cpu().numpy(), np.nonzero(want)[0])
+    with pytest.raises(RuntimeError, match="same number of points as polygons"):
+        cs.pairwise_point_in_polygon((_t(px[:5]), _t(py[:5])), (_t(po), _t(ro), _t(vx), _t(vy)))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_contains_properly_quadtree_mode_equals_oracle_composition(oracle_lib, dtype):
+    """contains.py:19-74: depth 15, max_size ceil(sqrt(N)), minimum scale, vertex extent; rows
+    carry ORIGINAL point ids.  Also the <=31-polygon brute-force mode gives the same set."""
+    import math
+
+    import cuspatial_b200 as cs
+    from cuspatial_b200 import datagen as D
+
+    n = 30000
+    po, ro, vx, vy = D.taxi_zone_like_polygons(25, seed=3, dtype=dtype, median_vertices=40)
+    ext = (float(vx.min()), float(vx.max()), float(vy.min()), float(vy.max()))
+    x, y = D.uniform_points(n, ext, seed=4, dtype=dtype)
+    scale = max(ext[1] - ext[0], ext[3] - ext[2]) / ((1 << 15) + 2)
+    ms = math.ceil(math.sqrt(n))
+    tree = oracle_lib.quadtree_on_points(x, y, ext[0], ext[1], ext[2], ext[3], scale, 15, ms)
+    bb = oracle_lib.polygon_bounding_boxes(po, ro, vx, vy)
+    pp, pq = oracle_lib.join_quadtree_and_bounding_boxes(tree, *bb, ext[0], ext[2], scale, 15)
+    hp, hq = oracle_lib.quadtree_point_in_polygon(pp, pq, tree, tree["point_indices"], x, y, po, ro,
+                                                  vx, vy)
+    polys = (_t(po), _t(ro), _t(vx), _t(vy))
+    got = cs.contains_properly(polys, (_t(x), _t(y)), mode="quadtree")
+    assert got.columns == ["point_index", "part_index"]
+    np.testing.assert_array_equal(got["part_index"].cpu().numpy(), hp)
+    np.testing.assert_array_equal(got["point_index"].cpu().numpy(), tree["point_indices"][hq])
+    brute = cs.contains_properly(polys, (_t(x), _t(y)), mode="byte")
+    a = set(zip(got["point_index"].cpu().numpy().tolist(), got["part_index"].cpu().numpy().tolist()))
+    b = set(zip(brute["point_index"].cpu().numpy().tolist(), brute["part_index"].cpu().numpy().tolist()))
+    assert a == b and len(a) > 1000
+
+
 def test_error_conditions_match_reference():
     """cpp/tests/join/join_quadtree_and_bounding_boxes_test.cpp:35-86."""
     import cuspatial_b200 as cs

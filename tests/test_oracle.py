@@ -9,7 +9,7 @@
 import numpy as np
 import pytest
 
-from util import assert_same, make_case, run_host
+from util import assert_same, make_case, pairwise_case, run_host
 
 
 def _check_golden(lib, golden):
@@ -48,6 +48,15 @@ def _check_golden(lib, golden):
             m = lib.point_in_polygon(p[:, 0].copy(), p[:, 1].copy(), c["part_offsets"],
                                      c["ring_offsets"], v[:, 0].copy(), v[:, 1].copy())
             assert list(m) == c["expected_mask"], (c["name"], dt)
+        for c in golden["pairwise_cases"]:
+            v = np.array(c["vertices"], dtype=dt)
+            for call in c["calls"]:
+                p = np.array(call["points"], dtype=dt)
+                k = len(p)  # point i vs polygon i of the first k polygons
+                got = lib.pairwise_point_in_polygon(
+                    p[:, 0].copy(), p[:, 1].copy(), c["part_offsets"][:k + 1], c["ring_offsets"],
+                    v[:, 0].copy(), v[:, 1].copy())
+                assert list(got) == call["expected"], (c["name"], dt)
 
 
 def test_oracle_matches_reference_golden_vectors(oracle_lib, golden):
@@ -116,3 +125,19 @@ def test_near_edge_points_oracle_equals_reference(oracle_lib, reference_lib):
         keep = (x > c["ext"][0]) & (x < c["ext"][1]) & (y > c["ext"][2]) & (y < c["ext"][3])
         c2 = dict(c, x=x[keep], y=y[keep], po=po, ro=ro, vx=vx, vy=vy)
         assert_same(run_host(oracle_lib, c2, 8), run_host(reference_lib, c2, 8), "near-edge")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("degenerate", [False, True])
+def test_pairwise_oracle_equals_reference_host_build(oracle_lib, reference_lib, dtype, degenerate):
+    px, py, po, ro, vx, vy = pairwise_case(2000, dtype, 5, degenerate)
+    a = oracle_lib.pairwise_point_in_polygon(px, py, po, ro, vx, vy)
+    b = reference_lib.pairwise_point_in_polygon(px, py, po, ro, vx, vy)
+    np.testing.assert_array_equal(a, b)
+    assert 0 < a.sum() < len(a)
+
+
+def test_pairwise_size_mismatch_is_an_error(oracle_lib):
+    px, py, po, ro, vx, vy = pairwise_case(10, np.float64, 1)
+    with pytest.raises(RuntimeError, match="same number of points as polygons"):
+        oracle_lib.pairwise_point_in_polygon(px[:5], py[:5], po, ro, vx, vy)

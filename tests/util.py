@@ -22,6 +22,38 @@ def make_case(n, n_poly, depth, kind="u", dtype=np.float64, seed=0, median_verti
     return dict(x=x, y=y, po=po, ro=ro, vx=vx, vy=vy, ext=ext, scale=scale, depth=depth)
 
 
+def pairwise_case(n, dtype, seed, degenerate=False):
+    """n (point, polygon) pairs: polygon i from the taxi-zone generator, point i near it."""
+    rng = np.random.default_rng(seed)
+    po, ro, vx, vy = D.taxi_zone_like_polygons(n, seed=seed, dtype=dtype, median_vertices=24)
+    if degenerate:  # repeat a vertex inside some rings: zero-length segments (b is not advanced)
+        for r in rng.choice(len(ro) - 1, size=max(1, (len(ro) - 1) // 3), replace=False):
+            a, b = int(ro[r]), int(ro[r + 1])
+            if b - a > 4:
+                j = int(rng.integers(a + 1, b - 2))
+                vx[j + 1], vy[j + 1] = vx[j], vy[j]
+    px, py = np.empty(n, dtype), np.empty(n, dtype)
+    for i in range(n):
+        a, b = int(ro[po[i]]), int(ro[po[i] + 1])
+        kind = i % 4
+        if kind == 0:      # bbox-uniform
+            px[i] = rng.uniform(vx[a:b].min(), vx[a:b].max())
+            py[i] = rng.uniform(vy[a:b].min(), vy[a:b].max())
+        elif kind == 1:    # exactly a vertex (on the boundary => 0)
+            j = int(rng.integers(a, b))
+            px[i], py[i] = vx[j], vy[j]
+        elif kind == 2:    # on / a few ulps off an edge
+            j = int(rng.integers(a, b - 1))
+            t = dtype(rng.uniform())
+            px[i] = vx[j] + t * (vx[j + 1] - vx[j])
+            py[i] = vy[j] + t * (vy[j + 1] - vy[j])
+            if i % 8 == 2:
+                px[i] = np.nextafter(px[i], dtype(np.inf))
+        else:              # centroid-ish
+            px[i], py[i] = vx[a:b].mean(), vy[a:b].mean()
+    return px, py, po, ro, vx, vy
+
+
 def run_host(lib, c, max_size):
     """Full path on a HostLib (oracle or reference host build)."""
     ext = c["ext"]
