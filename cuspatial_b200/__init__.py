@@ -7,6 +7,7 @@ point_in_polygon, polygon_bounding_boxes and the contains_properly driver).  Han
 functions.  There is no CPU fallback.
 """
 from .api import (contains_properly, join_quadtree_and_bounding_boxes,
+                  linestring_bounding_boxes, quadtree_point_to_nearest_linestring,
                   pairwise_point_in_polygon, point_in_polygon, point_in_polygon_bitmask,
                   polygon_bounding_boxes, quadtree_on_points, quadtree_point_in_polygon)
 from .frame import Frame
@@ -14,5 +15,6 @@ from .frame import Frame
 __all__ = [
     "quadtree_on_points", "join_quadtree_and_bounding_boxes", "quadtree_point_in_polygon",
     "point_in_polygon", "point_in_polygon_bitmask", "polygon_bounding_boxes",
-    "pairwise_point_in_polygon", "contains_properly", "Frame",
+    "pairwise_point_in_polygon", "contains_properly", "quadtree_point_to_nearest_linestring",
+    "linestring_bounding_boxes", "Frame",
 ]

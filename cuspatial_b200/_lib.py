@@ -55,7 +55,8 @@ EXPORTED_SYMBOLS = [
     "bsj_quadtree_on_points", "bsj_join_quadtree_and_bounding_boxes",
     "bsj_quadtree_point_in_polygon", "bsj_quadtree_point_in_polygon_ex", "bsj_quadtree_point_in_polygon_compact",
     "bsj_expand_pip_compact", "bsj_point_in_polygon", "bsj_pairwise_point_in_polygon",
-    "bsj_polygon_bounding_boxes",
+    "bsj_polygon_bounding_boxes", "bsj_quadtree_point_to_nearest_linestring",
+    "bsj_linestring_bounding_boxes",
     "bsj_point_keys_histogram", "bsj_key_subhistogram", "bsj_partition_points", "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
     "bsj_kernel_launch_count", "bsj_set_profiling", "bsj_get_profile",
 ]
@@ -96,6 +97,11 @@ def lib():
     L.bsj_point_in_polygon.argtypes = [vp, vp, C.c_int, u64, vp, u64, vp, u64, vp, vp, u64, vp, vp]
     L.bsj_pairwise_point_in_polygon.argtypes = [vp, vp, C.c_int, u64, vp, u64, vp, u64, vp, vp, u64,
                                                 vp, vp]
+    L.bsj_quadtree_point_to_nearest_linestring.argtypes = [
+        vp, vp, u64, vp, vp, vp, vp, vp, u64, vp, vp, vp, C.c_int, u64, vp, u64, vp, vp, u64, vp,
+        vp, vp, vp, C.POINTER(u64)]
+    L.bsj_linestring_bounding_boxes.argtypes = [vp, u64, vp, vp, C.c_int, u64, dbl, vp, vp, vp, vp,
+                                                vp]
     L.bsj_polygon_bounding_boxes.argtypes = [vp, u64, vp, u64, vp, vp, C.c_int, u64, dbl, vp,
                                              vp, vp, vp, vp]
     L.bsj_point_keys_histogram.argtypes = [vp, vp, C.c_int, u64, dbl, dbl, dbl, dbl, dbl, C.c_int8,

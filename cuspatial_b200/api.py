@@ -334,6 +334,84 @@ def point_in_polygon(points, polygons):
     return Frame([(i, ((mask >> i) & 1).to(torch.bool)) for i in range(n_poly)])
 
 
+def _split_linestrings(linestrings):
+    """(part_offset, x, y) arrays in GeoArrow layout, or an object with .part_offset/.x/.y
+    (the reference takes a GeoSeries and reads linestrings.lines.part_offset/x/y)."""
+    if hasattr(linestrings, "part_offset"):
+        linestrings = (linestrings.part_offset, linestrings.x, linestrings.y)
+    if not (isinstance(linestrings, (tuple, list)) and len(linestrings) == 3):
+        raise ValueError("linestrings must be (part_offset, x, y)")
+    lo, lx, ly = linestrings
+    lx, ly = _as_cuda(lx, name="linestrings.x"), _as_cuda(ly, name="linestrings.y")
+    lo = _as_cuda(lo, torch.uint32 if getattr(lo, "dtype", None) != torch.int32 else None)
+    return lo, lx, ly
+
+
+def linestring_bounding_boxes(linestrings, expansion_radius):
+    """Axis-aligned bounding box of every linestring, grown by `expansion_radius`
+    -> Frame[minx, miny, maxx, maxy] (reference: core/spatial/bounding.py:83-140)."""
+    lo, lx, ly = _split_linestrings(linestrings)
+    if lx.dtype != ly.dtype:
+        raise RuntimeError("Data type mismatch")
+    if lx.shape[0] != ly.shape[0]:
+        raise RuntimeError("x and y must be the same size")
+    n = max(int(lo.shape[0]) - 1, 0)
+    outs = [torch.empty(n, dtype=lx.dtype, device=lx.device) for _ in range(4)]
+    with torch.cuda.device(lx.device):
+        rc = _lib.lib().bsj_linestring_bounding_boxes(
+            _ptr(lo), lo.shape[0], _ptr(lx), _ptr(ly), _DTYPE_CODE[lx.dtype], lx.shape[0],
+            float(expansion_radius), _stream(lx.device), *[_ptr(o) for o in outs])
+        _lib.check(rc)
+    return Frame(zip(("minx", "miny", "maxx", "maxy"), outs))
+
+
+def quadtree_point_to_nearest_linestring(linestring_quad_pairs, quadtree, point_indices, points,
+                                         linestrings):
+    """Finds the nearest linestring to each point in a quadrant, and the distance between them.
+
+    Returns Frame[point_index u32, linestring_index u32, distance T], one row per point in
+    quadtree order; point_index indexes `point_indices` -- reference: join.py:265-352.
+    """
+    x, y = _split_points(points)
+    lo, lx, ly = _split_linestrings(linestrings)
+    if lx.dtype != ly.dtype:
+        raise RuntimeError("linestring columns must have the same data type")
+    if x.dtype != lx.dtype:
+        raise RuntimeError("points and linestrings must have the same data type")
+    if lx.shape[0] != ly.shape[0]:
+        raise RuntimeError("numbers of vertices must be the same for both x and y columns")
+    if isinstance(linestring_quad_pairs, (tuple, list)):
+        pl, pq = linestring_quad_pairs
+    else:
+        names = list(linestring_quad_pairs.columns) if hasattr(linestring_quad_pairs, "columns") \
+            else list(linestring_quad_pairs.keys())
+        if len(names) != 2:
+            raise RuntimeError("a quadrant-linestring table must have 2 columns")
+        pl, pq = linestring_quad_pairs[names[0]], linestring_quad_pairs[names[1]]
+    pl = _as_cuda(pl, torch.uint32)
+    pq = _as_cuda(pq, torch.uint32)
+    pi = _as_cuda(point_indices, torch.uint32)
+    if pi.shape[0] != x.shape[0]:
+        raise RuntimeError("number of points must be the same for both x and y columns")
+    tcols = _quadtree_columns(quadtree)
+    dev = x.device
+    n = x.shape[0]
+    out_p = torch.empty(n, dtype=torch.uint32, device=dev)
+    out_l = torch.empty(n, dtype=torch.uint32, device=dev)
+    out_d = torch.empty(n, dtype=x.dtype, device=dev)
+    rows = C.c_uint64(0)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().bsj_quadtree_point_to_nearest_linestring(
+            _ptr(pl), _ptr(pq), pl.shape[0], *[_ptr(t) for t in tcols], tcols[0].shape[0],
+            _ptr(pi), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], n, _ptr(lo), lo.shape[0], _ptr(lx),
+            _ptr(ly), lx.shape[0], _stream(dev), _ptr(out_p), _ptr(out_l), _ptr(out_d),
+            C.byref(rows))
+        _lib.check(rc)
+    r = int(rows.value)
+    return Frame([("point_index", out_p[:r]), ("linestring_index", out_l[:r]),
+                  ("distance", out_d[:r])])
+
+
 def pairwise_point_in_polygon(points, polygons):
     """Point i against polygon i: one UINT8 per pair, 1 = strictly inside
     (reference: _lib/pairwise_point_in_polygon.pyx:15-44 over

@@ -48,6 +48,14 @@ void pairwise_point_in_polygon_impl(const void* px, const void* py, int dtype, u
                                     const i32* poly_offsets, u64 n_poly_offsets,
                                     const i32* ring_offsets, u64 n_ring_offsets, const void* vx,
                                     const void* vy, u64 n_verts, cudaStream_t s, u8* out);
+void quadtree_point_to_nearest_linestring_impl(
+  const u32* pair_line, const u32* pair_quad, u64 n_pairs, const u32* length, const u32* offset,
+  u64 num_nodes, const u32* point_indices, const void* px, const void* py, int dtype, u64 n_points,
+  const u32* line_offsets, u64 n_line_offsets, const void* lx, const void* ly, u64 n_verts,
+  cudaStream_t s, u32* out_point, u32* out_line, void* out_dist, u64* out_rows);
+void linestring_bounding_boxes_impl(const u32* line_offsets, u64 n_line_offsets, const void* lx,
+                                    const void* ly, int dtype, u64 n_verts, double r,
+                                    cudaStream_t s, void* x0, void* y0, void* x1, void* y1);
 void polygon_bounding_boxes_impl(const u32* poly_offsets, u64 n_poly_offsets,
                                  const u32* ring_offsets, u64 n_ring_offsets, const void* vx,
                                  const void* vy, int dtype, u64 n_verts, double r, cudaStream_t s,
@@ -329,6 +337,55 @@ int bsj_pairwise_point_in_polygon(const void* point_x, const void* point_y, int 
     pairwise_point_in_polygon_impl(point_x, point_y, dtype, n_points, poly_offsets, n_poly_offsets,
                                    ring_offsets, n_ring_offsets, poly_points_x, poly_points_y,
                                    n_poly_points, (cudaStream_t)stream, out_flags);
+  });
+}
+
+int bsj_quadtree_point_to_nearest_linestring(
+  const uint32_t* pair_linestring, const uint32_t* pair_quad, uint64_t n_pairs,
+  const uint32_t* key, const uint8_t* level, const uint8_t* is_internal_node,
+  const uint32_t* length, const uint32_t* offset, uint64_t num_nodes,
+  const uint32_t* point_indices, const void* point_x, const void* point_y, int dtype,
+  uint64_t n_points, const uint32_t* linestring_offsets, uint64_t n_linestring_offsets,
+  const void* linestring_points_x, const void* linestring_points_y, uint64_t n_linestring_points,
+  bsj_stream_t stream, uint32_t* out_point_index, uint32_t* out_linestring_index,
+  void* out_distance, uint64_t* out_rows)
+{
+  return guarded([&] {
+    (void)key; (void)level; (void)is_internal_node;
+    BSJ_EXPECTS(out_rows != nullptr, "output row count must not be NULL");
+    *out_rows = 0;
+    check_dtype(dtype);
+    // quadtree_point_to_nearest_linestring.cu:161-174 (sizes/types implied by the flat signature)
+    BSJ_EXPECTS(n_pairs == 0 || (pair_linestring && pair_quad),
+                "a quadrant-linestring table must have 2 columns");
+    BSJ_EXPECTS(num_nodes == 0 || (length && offset), "a quadtree table must have 5 columns");
+    BSJ_EXPECTS(n_points == 0 || (point_indices && point_x && point_y),
+                "number of points must be the same for both x and y columns");
+    BSJ_EXPECTS(n_linestring_points == 0 || (linestring_points_x && linestring_points_y),
+                "numbers of vertices must be the same for both x and y columns");
+    quadtree_point_to_nearest_linestring_impl(
+      pair_linestring, pair_quad, n_pairs, length, offset, num_nodes, point_indices, point_x,
+      point_y, dtype, n_points, linestring_offsets, n_linestring_offsets, linestring_points_x,
+      linestring_points_y, n_linestring_points, (cudaStream_t)stream, out_point_index,
+      out_linestring_index, out_distance, out_rows);
+  });
+}
+
+int bsj_linestring_bounding_boxes(const uint32_t* linestring_offsets,
+                                  uint64_t n_linestring_offsets, const void* points_x,
+                                  const void* points_y, int dtype, uint64_t n_points,
+                                  double expansion_radius, bsj_stream_t stream, void* out_x_min,
+                                  void* out_y_min, void* out_x_max, void* out_y_max)
+{
+  return guarded([&] {
+    check_dtype(dtype);
+    // linestring_bounding_boxes.cu:135-141
+    BSJ_EXPECTS(expansion_radius >= 0, "expansion radius must be greater or equal than 0");
+    BSJ_EXPECTS(n_points >= 2 * (n_linestring_offsets ? n_linestring_offsets - 1 : 0),
+                "all linestrings must have at least 2 vertices");
+    linestring_bounding_boxes_impl(linestring_offsets, n_linestring_offsets, points_x, points_y,
+                                   dtype, n_points, expansion_radius, (cudaStream_t)stream,
+                                   out_x_min, out_y_min, out_x_max, out_y_max);
   });
 }
 

@@ -236,6 +236,43 @@ int bsj_pairwise_point_in_polygon(const void* point_x, const void* point_y, int 
                                   bsj_stream_t stream, uint8_t* out_flags);
 
 /*
+ * Replaces cuspatial::quadtree_point_to_nearest_linestring
+ *   (cpp/include/cuspatial/spatial_join.hpp:166-175, cpp/src/join/quadtree_point_to_nearest_linestring.cu:147-196;
+ *    header form cpp/include/cuspatial/detail/join/quadtree_point_to_nearest_linestring.cuh:150-314).
+ * linestring_quad_pairs = (pair_linestring, pair_quad) as returned by
+ * bsj_join_quadtree_and_bounding_boxes on the linestring bounding boxes (rows ordered by quadrant
+ * offset); linestring_offsets has n_linestrings+1 entries into the vertex columns.
+ * Outputs are caller-allocated columns of n_points rows: out_point_index[i] = i (the position in
+ * point_indices), out_linestring_index[i] = nearest linestring among those paired with the
+ * point's quadrant, out_distance[i] (same type as the coordinates). *out_rows = n_points, or 0 when
+ * any input is empty (the reference returns an empty table, :176-184). Rows of points whose
+ * quadrant is in no pair hold distance 0 and index 0 (the reference: distance 0, indices
+ * uninitialised).
+ */
+int bsj_quadtree_point_to_nearest_linestring(
+  const uint32_t* pair_linestring, const uint32_t* pair_quad, uint64_t n_pairs,
+  const uint32_t* key, const uint8_t* level, const uint8_t* is_internal_node,
+  const uint32_t* length, const uint32_t* offset, uint64_t num_nodes,
+  const uint32_t* point_indices, const void* point_x, const void* point_y, int dtype,
+  uint64_t n_points, const uint32_t* linestring_offsets, uint64_t n_linestring_offsets,
+  const void* linestring_points_x, const void* linestring_points_y, uint64_t n_linestring_points,
+  bsj_stream_t stream, uint32_t* out_point_index, uint32_t* out_linestring_index,
+  void* out_distance, uint64_t* out_rows);
+
+/*
+ * Replaces cuspatial::linestring_bounding_boxes
+ *   (cpp/include/cuspatial/bounding_boxes.hpp:52-57, cpp/src/bounding_boxes/linestring_bounding_boxes.cu:127-160;
+ *    header form cpp/include/cuspatial/detail/bounding_boxes.cuh:96-134).
+ * Outputs: 4 caller-allocated columns of n_linestring_offsets-1 rows (x_min, y_min, x_max, y_max),
+ * each expanded by `expansion_radius`.
+ */
+int bsj_linestring_bounding_boxes(const uint32_t* linestring_offsets,
+                                  uint64_t n_linestring_offsets, const void* points_x,
+                                  const void* points_y, int dtype, uint64_t n_points,
+                                  double expansion_radius, bsj_stream_t stream, void* out_x_min,
+                                  void* out_y_min, void* out_x_max, void* out_y_max);
+
+/*
  * Replaces cuspatial::polygon_bounding_boxes
  *   (cpp/include/cuspatial/bounding_boxes.hpp, cpp/src/bounding_boxes/polygon_bounding_boxes.cu:132-161):
  * the producer of the bbox table the join consumes. Outputs: 4 caller-allocated columns of

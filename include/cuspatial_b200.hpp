@@ -7,6 +7,8 @@
 //   cuspatial::quadtree_point_in_polygon         cpp/include/cuspatial/spatial_join.hpp:116-126
 //   cuspatial::point_in_polygon                  cpp/include/cuspatial/point_in_polygon.hpp:75-82
 //   cuspatial::pairwise_point_in_polygon         cpp/include/cuspatial/point_in_polygon.hpp:124-131
+//   cuspatial::quadtree_point_to_nearest_linestring  cpp/include/cuspatial/spatial_join.hpp:166-175
+//   cuspatial::linestring_bounding_boxes         cpp/include/cuspatial/bounding_boxes.hpp:52-57
 //
 // Header only; link against libcuspatial_b200.so.  Errors are rethrown as the reference does:
 // std::logic_error for CUSPATIAL_EXPECTS conditions (cuspatial::logic_error derives from it,
@@ -200,6 +202,57 @@ void pairwise_point_in_polygon(column_view<T> test_points_x, column_view<T> test
     test_points_x.data, test_points_y.data, detail::dtype_of<T>(), test_points_x.size,
     poly_offsets.data, poly_offsets.size, poly_ring_offsets.data, poly_ring_offsets.size,
     poly_points_x.data, poly_points_y.data, poly_points_x.size, stream, out_flags));
+}
+
+/// Result of quadtree_point_to_nearest_linestring: (point_index, linestring_index, distance).
+template <typename T>
+struct nearest_table {
+  column<uint32_t> point_index;
+  column<uint32_t> linestring_index;
+  column<T> distance;
+};
+
+/// cuspatial::quadtree_point_to_nearest_linestring(linestring_quad_pairs, quadtree, point_indices,
+/// point_x, point_y, linestring_offsets, linestring_points_x, linestring_points_y, mr).
+/// The three output columns are caller-allocated (n_points rows each); returns the row count
+/// (n_points, or 0 for empty inputs as the reference returns an empty table).
+template <typename T>
+uint64_t quadtree_point_to_nearest_linestring(
+  const pair_table& linestring_quad_pairs, const quadtree_table& quadtree,
+  column_view<uint32_t> point_indices, column_view<T> point_x, column_view<T> point_y,
+  column_view<uint32_t> linestring_offsets, column_view<T> linestring_points_x,
+  column_view<T> linestring_points_y, uint32_t* out_point_index, uint32_t* out_linestring_index,
+  T* out_distance, bsj_stream_t stream = nullptr)
+{
+  if (point_indices.size != point_x.size || point_x.size != point_y.size)
+    throw std::logic_error("number of points must be the same for both x and y columns");
+  if (linestring_points_x.size != linestring_points_y.size)
+    throw std::logic_error("numbers of vertices must be the same for both x and y columns");
+  uint64_t rows = 0;
+  detail::check(bsj_quadtree_point_to_nearest_linestring(
+    linestring_quad_pairs.first.data(), linestring_quad_pairs.second.data(),
+    linestring_quad_pairs.first.size(), quadtree.key.data(), quadtree.level.data(),
+    quadtree.is_internal_node.data(), quadtree.length.data(), quadtree.offset.data(),
+    quadtree.key.size(), point_indices.data, point_x.data, point_y.data, detail::dtype_of<T>(),
+    point_x.size, linestring_offsets.data, linestring_offsets.size, linestring_points_x.data,
+    linestring_points_y.data, linestring_points_x.size, stream, out_point_index,
+    out_linestring_index, out_distance, &rows));
+  return rows;
+}
+
+/// cuspatial::linestring_bounding_boxes(linestring_offsets, x, y, expansion_radius, mr) ->
+/// (x_min, y_min, x_max, y_max), caller-allocated columns of linestring_offsets.size-1 rows.
+template <typename T>
+void linestring_bounding_boxes(column_view<uint32_t> linestring_offsets, column_view<T> x,
+                               column_view<T> y, double expansion_radius, T* out_x_min,
+                               T* out_y_min, T* out_x_max, T* out_y_max,
+                               bsj_stream_t stream = nullptr)
+{
+  if (x.size != y.size) throw std::logic_error("x and y must be the same size");
+  detail::check(bsj_linestring_bounding_boxes(linestring_offsets.data, linestring_offsets.size,
+                                              x.data, y.data, detail::dtype_of<T>(), x.size,
+                                              expansion_radius, stream, out_x_min, out_y_min,
+                                              out_x_max, out_y_max));
 }
 
 }  // namespace cuspatial_b200

@@ -143,6 +143,38 @@ class CudaRefLib:
         return out, dt
 
 
+    def quadtree_point_to_nearest_linestring(self, pair_line, pair_quad, tree, point_indices, px, py,
+                                             line_offsets, lx, ly):
+        keep, targs = self._tree_args(tree)
+        lo = line_offsets.to(torch.uint32).contiguous()
+        out = (C.c_void_p * 3)()
+        out_n = (C.c_uint64 * 1)()
+        torch.cuda.synchronize(px.device)
+        t0 = time.perf_counter()
+        rc = self._lib.ref_quadtree_point_to_nearest_linestring(
+            _p(pair_line), _p(pair_quad), C.c_uint64(pair_line.numel()), *targs,
+            _p(point_indices), _p(px), _p(py), _dt(px), C.c_uint64(px.numel()), _p(lo),
+            C.c_uint64(lo.numel()), _p(lx), _p(ly), C.c_uint64(lx.numel()), out, out_n)
+        dt = time.perf_counter() - t0
+        self._check(rc)
+        n = out_n[0]
+        d = px.device
+        return (self._take(out[0], n, torch.uint32, d), self._take(out[1], n, torch.uint32, d),
+                self._take(out[2], n, px.dtype, d)), dt
+
+    def linestring_bounding_boxes(self, line_offsets, lx, ly, expansion=0.0):
+        import numpy as np
+
+        lo = line_offsets.to(torch.uint32).contiguous()
+        n = lo.numel() - 1
+        npdt = np.float32 if lx.dtype == torch.float32 else np.float64
+        outs = [np.zeros(n, dtype=npdt) for _ in range(4)]  # host outputs in both flavours
+        rc = self._lib.ref_linestring_bounding_boxes(
+            _p(lo), C.c_uint64(lo.numel()), _p(lx), _p(ly), _dt(lx), C.c_uint64(lx.numel()),
+            C.c_double(expansion), *[o.ctypes.data_as(C.c_void_p) for o in outs])
+        self._check(rc)
+        return tuple(torch.as_tensor(o, device=lx.device) for o in outs)
+
     def polygon_bounding_boxes(self, poly_offsets, ring_offsets, vx, vy, expansion=0.0):
         import numpy as np
 

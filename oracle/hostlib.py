@@ -139,6 +139,36 @@ class HostLib:
             _p(vx), _p(vy), C.c_uint64(len(vx)), _p(out)))
         return out
 
+    def quadtree_point_to_nearest_linestring(self, pair_line, pair_quad, tree, point_indices, px, py,
+                                             line_offsets, lx, ly):
+        px = np.ascontiguousarray(px)
+        py, lx, ly = (np.ascontiguousarray(a, dtype=px.dtype) for a in (py, lx, ly))
+        pair_line = np.ascontiguousarray(pair_line, dtype=np.uint32)
+        pair_quad = np.ascontiguousarray(pair_quad, dtype=np.uint32)
+        point_indices = np.ascontiguousarray(point_indices, dtype=np.uint32)
+        line_offsets = np.ascontiguousarray(line_offsets, dtype=np.uint32)
+        keep, targs = self._tree_args(tree)
+        out = (C.c_void_p * 3)()
+        out_n = (C.c_uint64 * 1)()
+        self._check(self._f("quadtree_point_to_nearest_linestring")(
+            _p(pair_line), _p(pair_quad), C.c_uint64(len(pair_line)), *targs, _p(point_indices),
+            _p(px), _p(py), _dt(px), C.c_uint64(len(px)), _p(line_offsets),
+            C.c_uint64(len(line_offsets)), _p(lx), _p(ly), C.c_uint64(len(lx)), out, out_n))
+        n = out_n[0]
+        return (self._take(out[0], n, np.uint32), self._take(out[1], n, np.uint32),
+                self._take(out[2], n, px.dtype))
+
+    def linestring_bounding_boxes(self, line_offsets, lx, ly, expansion=0.0):
+        lx = np.ascontiguousarray(lx)
+        ly = np.ascontiguousarray(ly, dtype=lx.dtype)
+        line_offsets = np.ascontiguousarray(line_offsets, dtype=np.uint32)
+        n = len(line_offsets) - 1
+        outs = [np.zeros(n, dtype=lx.dtype) for _ in range(4)]
+        self._check(self._f("linestring_bounding_boxes")(
+            _p(line_offsets), C.c_uint64(len(line_offsets)), _p(lx), _p(ly), _dt(lx),
+            C.c_uint64(len(lx)), C.c_double(expansion), *[_p(o) for o in outs]))
+        return tuple(outs)
+
     def polygon_bounding_boxes(self, poly_offsets, ring_offsets, vx, vy, expansion=0.0):
         vx = np.ascontiguousarray(vx)
         vy = np.ascontiguousarray(vy, dtype=vx.dtype)

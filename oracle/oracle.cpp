@@ -535,6 +535,128 @@ int pairwise_pip_t(T const* px, T const* py, uint64_t n_points, int32_t const* p
   return 0;
 }
 
+// vec_2d.hpp:166-170 dot(a,b) = a.x*b.x + a.y*b.y.  nvcc (default -fmad=true) contracts it to
+// fma(a.x, b.x, a.y*b.y) -- checked in the SASS of oracle/_ref/libcuspatial_ref_cuda.so
+// (FMUL/DMUL of the y terms first, then one FFMA/DFMA); restated explicitly because this file is
+// compiled with -ffp-contract=off.
+template <typename T>
+inline T dot2(T ax, T ay, T bx, T by)
+{
+  return std::fma(ax, bx, ay * by);
+}
+
+// detail/algorithm/point_linestring_distance.cuh:33-53
+template <typename T>
+inline T point_linestring_distance(T px, T py, T const* lx, T const* ly, uint32_t v0, uint32_t v1)
+{
+  T distance_squared = std::numeric_limits<T>::max();
+  for (uint32_t i = v0; i + 1 < v1; ++i) {  // linestring_ref: segments (v[i], v[i+1])
+    T const ax = lx[i], ay = ly[i], bx = lx[i + 1], by = ly[i + 1];
+    T const v1px = px - ax, v1py = py - ay, v2px = px - bx, v2py = py - by;
+    T const d0 = dot2(v1px, v1py, v1px, v1py);
+    T const d1 = dot2(v2px, v2py, v2px, v2py);
+    T const ex = bx - ax, ey = by - ay;
+    T const d2 = dot2(ex, ey, ex, ey);        // segment::length2
+    T const d3 = dot2(v1px, v1py, ex, ey);    // proj2
+    T const r  = d3 * d3 / d2;
+    T const d  = (d3 <= 0 || r >= d2) ? std::fmin(d0, d1) : d0 - r;
+    distance_squared = std::fmin(distance_squared, d);
+  }
+  return std::sqrt(distance_squared);
+}
+
+// detail/join/quadtree_point_to_nearest_linestring.cuh:150-314, literally: the candidate list is
+// enumerated in the reference's "transposed" order (:64-92) so that the candidates of one point
+// are consecutive, reduced by key with the reference's selection rule (:283-300: a zero distance
+// loses to anything, ties go to the smaller linestring id), then scattered to the point's sorted
+// position (:309-316).  Points that belong to no candidate quadrant keep distance 0 (:264); the
+// reference leaves their two index columns uninitialised -- here they are 0.
+template <typename T>
+int nearest_linestring_t(uint32_t const* pair_line, uint32_t const* pair_quad, uint64_t n_pairs,
+                         uint32_t const* length, uint32_t const* offset, uint64_t q,
+                         uint32_t const* point_indices, T const* px, T const* py,
+                         uint64_t n_points, uint32_t const* line_offsets, uint64_t n_line_offsets,
+                         T const* lx, T const* ly, void** out, uint64_t* out_n)
+{
+  out[0] = out[1] = out[2] = nullptr;
+  out_n[0]                 = 0;
+  // cpp/src/join/quadtree_point_to_nearest_linestring.cu:176-184
+  if (n_pairs == 0 || q == 0 || n_points == 0 || n_line_offsets == 0) return 0;
+  std::vector<uint32_t> quad_len(n_pairs), quad_off(n_pairs), local(n_pairs + 1, 0);
+  for (uint64_t j = 0; j < n_pairs; ++j) {
+    quad_len[j]  = length[pair_quad[j]];
+    quad_off[j]  = offset[pair_quad[j]];
+    local[j + 1] = local[j] + quad_len[j];  // :176-183 (uint32 arithmetic like IndexType)
+  }
+  uint32_t const total = local[n_pairs];
+  std::vector<uint32_t> out_point(n_points, 0), out_line(n_points, 0);
+  std::vector<T> out_dist(n_points, (T)0);
+
+  struct cand { uint32_t point, line; T d; };
+  auto candidate = [&](uint32_t g) {
+    // get_quad_and_local_point_indices.cuh:37-44
+    uint32_t const j  = (uint32_t)(std::upper_bound(local.begin(), local.end(), g) - local.begin()) - 1;
+    uint32_t const lp = g - local[j];
+    // :44-60 run of pairs with the same quadrant offset around j
+    uint32_t const lhs = (uint32_t)(std::lower_bound(quad_off.begin(), quad_off.begin() + j, quad_off[j]) - quad_off.begin());
+    uint32_t const rhs = (uint32_t)(std::upper_bound(quad_off.begin() + j, quad_off.end(), quad_off[j]) - quad_off.begin());
+    uint32_t const local_line = j - lhs, n_lines = rhs - lhs;
+    // :76-91
+    uint32_t const t     = local_line * quad_len[j] + lp;
+    uint32_t const point = t / n_lines + quad_off[j];
+    uint32_t const pj    = t % n_lines + (j - local_line);
+    uint32_t const line  = pair_line[pj];
+    uint32_t const pi    = point_indices[point];
+    return cand{point, line,
+                point_linestring_distance<T>(px[pi], py[pi], lx, ly, line_offsets[line],
+                                             line_offsets[line + 1])};
+  };
+  auto select = [](cand const& l, cand const& r) {  // :283-300
+    if (l.d == (T)0) return r;
+    if (r.d == (T)0) return l;
+    if (l.d == r.d) return l.line < r.line ? l : r;
+    return l.d < r.d ? l : r;
+  };
+  uint32_t g = 0;
+  while (g < total) {  // reduce_by_key over equal consecutive point ids, then scatter
+    cand acc = candidate(g++);
+    while (g < total) {
+      cand const c = candidate(g);
+      if (c.point != acc.point) break;
+      cand sel  = select(acc, c);
+      sel.point = acc.point;
+      acc       = sel;
+      ++g;
+    }
+    if (acc.point < n_points) {
+      out_point[acc.point] = acc.point;
+      out_line[acc.point]  = acc.line;
+      out_dist[acc.point]  = acc.d;
+    }
+  }
+  out[0] = to_buf(out_point, &out_n[0]);
+  out[1] = to_buf(out_line, &out_n[0]);
+  out[2] = to_buf(out_dist, &out_n[0]);
+  return 0;
+}
+
+// detail/bounding_boxes.cuh:96-134  per-linestring min/max of (v - r, v + r)
+template <typename T>
+int line_bbox_t(uint32_t const* line_offsets, uint64_t n_line_offsets, T const* lx, T const* ly,
+                uint64_t n_verts, T r, T* x0, T* y0, T* x1, T* y1)
+{
+  if (n_line_offsets < 2 || n_verts == 0) return 0;
+  for (uint64_t p = 0; p + 1 < n_line_offsets; ++p) {
+    T ax = std::numeric_limits<T>::infinity(), ay = ax, bx = -ax, by = -ax;
+    for (uint64_t i = line_offsets[p]; i < line_offsets[p + 1] && i < n_verts; ++i) {
+      ax = std::fmin(ax, lx[i] - r); ay = std::fmin(ay, ly[i] - r);
+      bx = std::fmax(bx, lx[i] + r); by = std::fmax(by, ly[i] + r);
+    }
+    x0[p] = ax; y0[p] = ay; x1[p] = bx; y1[p] = by;
+  }
+  return 0;
+}
+
 // detail/bounding_boxes.cuh:36-60,136-184  per-polygon min/max of (v - r, v + r)
 template <typename T>
 int poly_bbox_t(uint32_t const* poly_offsets, uint64_t n_poly_offsets,
@@ -647,6 +769,37 @@ int orc_pairwise_point_in_polygon(void const* px, void const* py, int dtype, uin
                     : pairwise_pip_t<double>((double const*)px, (double const*)py, n_points,
                                              poly_offsets, n_poly_offsets, ring_offsets,
                                              (double const*)vx, (double const*)vy, out);
+}
+
+int orc_quadtree_point_to_nearest_linestring(
+  uint32_t const* pair_line, uint32_t const* pair_quad, uint64_t n_pairs, uint32_t const* key,
+  uint8_t const* level, uint8_t const* internal, uint32_t const* length, uint32_t const* offset,
+  uint64_t q, uint32_t const* point_indices, void const* px, void const* py, int dtype,
+  uint64_t n_points, uint32_t const* line_offsets, uint64_t n_line_offsets, void const* lx,
+  void const* ly, uint64_t n_verts, void** out, uint64_t* out_n)
+{
+  (void)key; (void)level; (void)internal; (void)n_verts;
+  return dtype == 0
+           ? nearest_linestring_t<float>(pair_line, pair_quad, n_pairs, length, offset, q,
+                                         point_indices, (float const*)px, (float const*)py,
+                                         n_points, line_offsets, n_line_offsets, (float const*)lx,
+                                         (float const*)ly, out, out_n)
+           : nearest_linestring_t<double>(pair_line, pair_quad, n_pairs, length, offset, q,
+                                          point_indices, (double const*)px, (double const*)py,
+                                          n_points, line_offsets, n_line_offsets,
+                                          (double const*)lx, (double const*)ly, out, out_n);
+}
+
+int orc_linestring_bounding_boxes(uint32_t const* line_offsets, uint64_t n_line_offsets,
+                                  void const* lx, void const* ly, int dtype, uint64_t n_verts,
+                                  double expansion, void* x0, void* y0, void* x1, void* y1)
+{
+  return dtype == 0 ? line_bbox_t<float>(line_offsets, n_line_offsets, (float const*)lx,
+                                         (float const*)ly, n_verts, (float)expansion, (float*)x0,
+                                         (float*)y0, (float*)x1, (float*)y1)
+                    : line_bbox_t<double>(line_offsets, n_line_offsets, (double const*)lx,
+                                          (double const*)ly, n_verts, expansion, (double*)x0,
+                                          (double*)y0, (double*)x1, (double*)y1);
 }
 
 int orc_polygon_bounding_boxes(uint32_t const* poly_offsets, uint64_t n_poly_offsets,

@@ -9,6 +9,8 @@
 //   - point_in_polygon (bitmask): cpp/src/point_in_polygon/point_in_polygon.cu:52-98
 //   - pairwise_point_in_polygon : cpp/src/point_in_polygon/point_in_polygon.cu:52-98,172-190
 //   - polygon_bounding_boxes    : cpp/src/bounding_boxes/polygon_bounding_boxes.cu:132-161
+//   - linestring_bounding_boxes : cpp/src/bounding_boxes/linestring_bounding_boxes.cu:60-120
+//   - quadtree_point_to_nearest_linestring : cpp/src/join/quadtree_point_to_nearest_linestring.cu:47-112
 // i.e. cast the double parameters to T, wrap raw columns into the reference's iterators,
 // call the header-only entry point, hand the result arrays back.
 //
@@ -32,6 +34,7 @@
 #include <cuspatial/iterator_factory.cuh>
 #include <cuspatial/point_in_polygon.cuh>
 #include <cuspatial/point_quadtree.cuh>
+#include <cuspatial/range/multilinestring_range.cuh>
 #include <cuspatial/range/multipoint_range.cuh>
 #include <cuspatial/range/multipolygon_range.cuh>
 
@@ -218,6 +221,55 @@ int poly_bbox_t(uint32_t const* poly_offsets, uint64_t n_poly_offsets, uint32_t 
   return 0;
 }
 
+template <typename T>
+int nearest_linestring_t(uint32_t const* pair_line, uint32_t const* pair_quad, uint64_t n_pairs,
+                         uint32_t const* key, uint8_t const* level, bool const* internal,
+                         uint32_t const* length, uint32_t const* offset, uint64_t q,
+                         uint32_t const* point_indices, T const* px, T const* py,
+                         uint64_t n_points, uint32_t const* line_offsets, uint64_t n_line_offsets,
+                         T const* lx, T const* ly, uint64_t n_verts, void** out, uint64_t* out_n)
+{
+  rmm::cuda_stream_view stream{};
+  cuspatial::point_quadtree_ref tree(key, key + q, level, internal, length, offset);
+  // same construction as cpp/src/join/quadtree_point_to_nearest_linestring.cu:70-76
+  auto linestrings = cuspatial::multilinestring_range(
+    thrust::make_counting_iterator(0), thrust::make_counting_iterator((int)n_line_offsets),
+    line_offsets, line_offsets + n_line_offsets, cuspatial::make_vec_2d_iterator(lx, ly),
+    cuspatial::make_vec_2d_iterator(lx + n_verts, ly + n_verts));
+  auto [point_idx, line_idx, dist] = cuspatial::quadtree_point_to_nearest_linestring(
+    pair_line, pair_line + n_pairs, pair_quad, tree, point_indices, point_indices + n_points,
+    cuspatial::make_vec_2d_iterator(px, py), linestrings, stream,
+    rmm::mr::get_current_device_resource());
+  stream.synchronize();
+  out[0] = release(point_idx, &out_n[0]);
+  out[1] = release(line_idx, &out_n[0]);
+  out[2] = release(dist, &out_n[0]);
+  return 0;
+}
+
+template <typename T>
+int line_bbox_t(uint32_t const* line_offsets, uint64_t n_line_offsets, T const* lx, T const* ly,
+                uint64_t n_verts, T expansion, T* x0, T* y0, T* x1, T* y1)
+{
+  rmm::cuda_stream_view stream{};
+  uint64_t n_lines = n_line_offsets - 1;
+  rmm::device_uvector<cuspatial::box<T>> boxes(n_lines, stream);
+  auto pts = cuspatial::make_vec_2d_iterator(lx, ly);
+  cuspatial::linestring_bounding_boxes(line_offsets, line_offsets + n_line_offsets, pts,
+                                       pts + n_verts, boxes.begin(), expansion, stream);
+  stream.synchronize();
+  std::vector<cuspatial::box<T>> h(n_lines);
+#if defined(__CUDACC__)
+  cudaMemcpy(h.data(), boxes.data(), n_lines * sizeof(cuspatial::box<T>), cudaMemcpyDeviceToHost);
+#else
+  std::memcpy(h.data(), boxes.data(), n_lines * sizeof(cuspatial::box<T>));
+#endif
+  for (uint64_t i = 0; i < n_lines; ++i) {
+    x0[i] = h[i].v1.x; y0[i] = h[i].v1.y; x1[i] = h[i].v2.x; y1[i] = h[i].v2.y;
+  }
+  return 0;
+}
+
 template <typename F>
 int guarded(F&& f)
 {
@@ -336,6 +388,45 @@ int ref_pairwise_point_in_polygon(void const* px, void const* py, int dtype, uin
              : pairwise_pip_t<double>((double const*)px, (double const*)py, n_points, poly_offsets,
                                       n_poly_offsets, ring_offsets, n_ring_offsets,
                                       (double const*)vx, (double const*)vy, n_verts, out);
+  });
+}
+
+// out[3] = {point_index u32, linestring_index u32, distance T}; out_n[1] = {n_points}
+int ref_quadtree_point_to_nearest_linestring(
+  uint32_t const* pair_line, uint32_t const* pair_quad, uint64_t n_pairs, uint32_t const* key,
+  uint8_t const* level, uint8_t const* internal, uint32_t const* length, uint32_t const* offset,
+  uint64_t q, uint32_t const* point_indices, void const* px, void const* py, int dtype,
+  uint64_t n_points, uint32_t const* line_offsets, uint64_t n_line_offsets, void const* lx,
+  void const* ly, uint64_t n_verts, void** out, uint64_t* out_n)
+{
+  return guarded([&] {
+    return dtype == 0
+             ? nearest_linestring_t<float>(pair_line, pair_quad, n_pairs, key, level,
+                                           (bool const*)internal, length, offset, q, point_indices,
+                                           (float const*)px, (float const*)py, n_points,
+                                           line_offsets, n_line_offsets, (float const*)lx,
+                                           (float const*)ly, n_verts, out, out_n)
+             : nearest_linestring_t<double>(pair_line, pair_quad, n_pairs, key, level,
+                                            (bool const*)internal, length, offset, q,
+                                            point_indices, (double const*)px, (double const*)py,
+                                            n_points, line_offsets, n_line_offsets,
+                                            (double const*)lx, (double const*)ly, n_verts, out,
+                                            out_n);
+  });
+}
+
+// x0..y1 are HOST output arrays of n_line_offsets-1 elements of T.
+int ref_linestring_bounding_boxes(uint32_t const* line_offsets, uint64_t n_line_offsets,
+                                  void const* lx, void const* ly, int dtype, uint64_t n_verts,
+                                  double expansion, void* x0, void* y0, void* x1, void* y1)
+{
+  return guarded([&] {
+    return dtype == 0 ? line_bbox_t<float>(line_offsets, n_line_offsets, (float const*)lx,
+                                           (float const*)ly, n_verts, (float)expansion,
+                                           (float*)x0, (float*)y0, (float*)x1, (float*)y1)
+                      : line_bbox_t<double>(line_offsets, n_line_offsets, (double const*)lx,
+                                            (double const*)ly, n_verts, expansion, (double*)x0,
+                                            (double*)y0, (double*)x1, (double*)y1);
   });
 }
 

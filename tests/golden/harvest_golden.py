@@ -10,6 +10,7 @@ Sources (rapidsai/cuspatial 25.06):
   cpp/tests/join/quadtree_point_in_polygon_test_small.cu   71 points, 4 polygons, pairs, PIP rows
   cpp/tests/point_in_polygon/point_in_polygon_test.cu      predicate edge cases (planar)
   cpp/tests/point_in_polygon/pairwise_point_in_polygon_test.cu:75-325  pairwise known answers
+  cpp/tests/join/quadtree_point_to_nearest_linestring_test_small.cu:36-210  nearest linestring
   python/.../tests/spatial/join/test_spatial_join.py:321-432  linestring bbox join (21 pairs)
 
 Run:  python tests/golden/harvest_golden.py
@@ -238,6 +239,36 @@ def harvest_pairwise_tests():
     return cases
 
 
+def harvest_nearest_linestring():
+    path = os.path.join(REF, "cpp/tests/join/quadtree_point_to_nearest_linestring_test_small.cu")
+    src = strip_comments(open(path).read())
+    i = src.index("make_device_vector<vec_2d<T>>(")
+    pts = brace_to_py(balanced(src, src.index("{", i)))
+    j = src.index("make_multilinestring_array<T>(")
+    geom, part, verts = [brace_to_py(a)
+                         for a in split_top_level_args(balanced(src, src.index("(", j))[1:-1])]
+
+    def vec_after(marker, k=0):
+        pos = -1
+        for _ in range(k + 1):
+            pos = src.index(marker, pos + 1)
+        return brace_to_py(balanced(src, src.index("{", pos)))
+
+    return {
+        "source": "cpp/tests/join/quadtree_point_to_nearest_linestring_test_small.cu:36-210",
+        "bbox": [0.0, 8.0, 0.0, 8.0], "scale": 1.0, "max_depth": 3, "max_size": 12,
+        "expansion_radius": 2.0,
+        "points": pts, "geometry_offsets": geom, "line_offsets": part, "vertices": verts,
+        "pair_line": vec_after("expected_linestring_indices =\n      make_device_vector<uint32_t>("),
+        "pair_quad": vec_after("expected_quad_indices = make_device_vector<uint32_t>("),
+        "distance_f32": vec_after("return make_device_vector<T>(", 0),
+        "distance_f64": vec_after("return make_device_vector<T>(", 1),
+        "point_index": vec_after("expected_point_indices = make_device_vector<std::uint32_t>("),
+        "linestring_index": vec_after(
+            "expected_linestring_indices = make_device_vector<std::uint32_t>("),
+    }
+
+
 def harvest_linestring_join():
     path = os.path.join(
         REF, "python/cuspatial/cuspatial/tests/spatial/join/test_spatial_join.py"
@@ -267,6 +298,7 @@ def main():
         "quadtree_cases": harvest_quadtree_tests(),
         "pip_cases": harvest_pip_tests(),
         "pairwise_cases": harvest_pairwise_tests(),
+        "nearest_linestring": harvest_nearest_linestring(),
         "linestring_join": harvest_linestring_join(),
     }
     with open(OUT, "w") as f:

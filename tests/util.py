@@ -54,6 +54,113 @@ def pairwise_case(n, dtype, seed, degenerate=False):
     return px, py, po, ro, vx, vy
 
 
+def make_linestrings(n_lines, ext, seed, dtype=np.float64, median_vertices=12):
+    """Random-walk polylines inside the extent -> (part_offset u32[n+1], x, y)."""
+    rng = np.random.default_rng(seed)
+    w, h = ext[1] - ext[0], ext[3] - ext[2]
+    counts = np.clip(rng.lognormal(np.log(median_vertices), 0.6, n_lines).astype(np.int64), 2, 400)
+    lo = np.zeros(n_lines + 1, dtype=np.uint32)
+    lo[1:] = np.cumsum(counts)
+    xs, ys = np.empty(lo[-1], dtype), np.empty(lo[-1], dtype)
+    for i in range(n_lines):
+        n = int(counts[i])
+        step = 0.02 * min(w, h)
+        x0, y0 = rng.uniform(ext[0], ext[1]), rng.uniform(ext[2], ext[3])
+        dx = np.cumsum(rng.normal(0, step, n))
+        dy = np.cumsum(rng.normal(0, step, n))
+        xs[lo[i]:lo[i + 1]] = np.clip(x0 + dx, ext[0], ext[1])
+        ys[lo[i]:lo[i + 1]] = np.clip(y0 + dy, ext[2], ext[3])
+        if i % 7 == 3 and n > 3:      # a zero-length segment
+            xs[lo[i] + 2], ys[lo[i] + 2] = xs[lo[i] + 1], ys[lo[i] + 1]
+    return lo, xs, ys
+
+
+def covered_positions(tree, pair_quad, n_points):
+    """Sorted positions of the points whose quadrant appears in the pair table."""
+    m = np.zeros(n_points, dtype=bool)
+    off, ln = np.asarray(tree["offset"]), np.asarray(tree["length"])
+    for q in np.unique(np.asarray(pair_quad)):
+        m[off[q]:off[q] + ln[q]] = True
+    return m
+
+
+def run_host_nearest(lib, c, lines, max_size, radius):
+    ext = c["ext"]
+    lo, lx, ly = lines
+    tree = lib.quadtree_on_points(c["x"], c["y"], ext[0], ext[1], ext[2], ext[3], c["scale"],
+                                  c["depth"], max_size)
+    bb = lib.linestring_bounding_boxes(lo, lx, ly, radius)
+    pairs = lib.join_quadtree_and_bounding_boxes(tree, *bb, ext[0], ext[2], c["scale"], c["depth"])
+    out = lib.quadtree_point_to_nearest_linestring(pairs[0], pairs[1], tree, tree["point_indices"],
+                                                   c["x"], c["y"], lo, lx, ly)
+    return dict(tree=tree, bbox=bb, pairs=pairs, nearest=out)
+
+
+def run_gpu_nearest(c, lines, max_size, radius):
+    import torch
+
+    import cuspatial_b200 as cs
+
+    dev = "cuda"
+    ext = c["ext"]
+    x, y = torch.as_tensor(c["x"], device=dev), torch.as_tensor(c["y"], device=dev)
+    ls = tuple(torch.as_tensor(a, device=dev) for a in lines)
+    pidx, tree = cs.quadtree_on_points((x, y), ext[0], ext[1], ext[2], ext[3], c["scale"],
+                                       c["depth"], max_size)
+    bb = cs.linestring_bounding_boxes(ls, radius)
+    pairs = cs.join_quadtree_and_bounding_boxes(tree, bb, ext[0], ext[1], ext[2], ext[3],
+                                                c["scale"], c["depth"])
+    out = cs.quadtree_point_to_nearest_linestring(pairs, tree, pidx, (x, y), ls)
+    assert out.columns == ["point_index", "linestring_index", "distance"]
+    t = {k: tree[k].cpu().numpy().astype(np.uint8 if k in ("level", "is_internal_node")
+                                         else np.uint32) for k in TREE_COLS}
+    t["point_indices"] = pidx.cpu().numpy()
+    return dict(tree=t, bbox=tuple(bb[k].cpu().numpy() for k in ("minx", "miny", "maxx", "maxy")),
+                pairs=(pairs["bbox_offset"].cpu().numpy(), pairs["quad_offset"].cpu().numpy()),
+                nearest=tuple(out[k].cpu().numpy() for k in out.columns))
+
+
+def run_ref_cuda_nearest(c, lines, max_size, radius):
+    """The same flow on the reference's own CUDA build (oracle/_ref/libcuspatial_ref_cuda.so)."""
+    import torch
+
+    from oracle import cudalib
+
+    lib = cudalib.reference_cuda()
+    dev = "cuda"
+    ext = c["ext"]
+    x, y = torch.as_tensor(c["x"], device=dev), torch.as_tensor(c["y"], device=dev)
+    lo, lx, ly = (torch.as_tensor(a, device=dev) for a in lines)
+    tree, _ = lib.quadtree_on_points(x, y, ext[0], ext[1], ext[2], ext[3], c["scale"], c["depth"],
+                                     max_size)
+    bb = lib.linestring_bounding_boxes(lo, lx, ly, radius)
+    pairs, _ = lib.join_quadtree_and_bounding_boxes(tree, *bb, ext[0], ext[2], c["scale"],
+                                                    c["depth"])
+    out, _ = lib.quadtree_point_to_nearest_linestring(pairs[0], pairs[1], tree,
+                                                      tree["point_indices"], x, y, lo, lx, ly)
+    return dict(tree={k: v.cpu().numpy() for k, v in tree.items()},
+                bbox=tuple(b.cpu().numpy() for b in bb),
+                pairs=tuple(p.cpu().numpy() for p in pairs),
+                nearest=tuple(o.cpu().numpy() for o in out))
+
+
+def assert_same_nearest(a, b, what="", covered_only=False):
+    for k in TREE_COLS + ("point_indices",):
+        np.testing.assert_array_equal(a["tree"][k], b["tree"][k], err_msg="%s tree.%s" % (what, k))
+    for i in range(4):
+        np.testing.assert_array_equal(a["bbox"][i], b["bbox"][i], err_msg="%s bbox[%d]" % (what, i))
+    for i in range(2):
+        np.testing.assert_array_equal(a["pairs"][i], b["pairs"][i], err_msg="%s pairs[%d]" % (what, i))
+    m = slice(None)
+    if covered_only:  # the reference leaves the index columns of uncovered points uninitialised
+        m = covered_positions(a["tree"], a["pairs"][1], len(a["tree"]["point_indices"]))
+        np.testing.assert_array_equal(a["nearest"][2][~m], 0, err_msg=what + " uncovered distance")
+        np.testing.assert_array_equal(b["nearest"][2][~m], 0, err_msg=what + " uncovered distance")
+    for i, name in enumerate(("point_index", "linestring_index", "distance")):
+        np.testing.assert_array_equal(a["nearest"][i][m], b["nearest"][i][m],
+                                      err_msg="%s nearest.%s" % (what, name))
+
+
 def run_host(lib, c, max_size):
     """Full path on a HostLib (oracle or reference host build)."""
     ext = c["ext"]
