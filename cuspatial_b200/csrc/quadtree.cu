@@ -57,32 +57,39 @@ struct fp<double> {
 // than the cheap product a * (1/scale): both are within `guard` of the exact quotient, so when the
 // product's fractional part is farther than `guard` from 0 and 1 (and the quotient is in range)
 // the truncations agree.  Otherwise (probability ~2^-29 for fp64, ~6 % for fp32; NaN; huge
-// values) the true division is evaluated.
+// values) the true division is evaluated, out of line so the hot loop stays short.
+// static_cast<uint16_t>(T) compiles to cvt.rzi.u32 (saturating, NaN -> 0) followed by & 0xFFFF,
+// restated explicitly; IEEE division (the reference builds with the default -prec-div=true).
 template <typename T>
-__device__ __forceinline__ u32 cell_index(T a, T scale, T inv_scale)
+__device__ __noinline__ u32 cell_index_exact(T a, T scale, T coord, u32* point_flags)
 {
-  T const q = fp<T>::mul(a, inv_scale);
-  T const t = fp<T>::trunc_(q);
-  T const f = q - t;
-  if (q >= (T)0 && q < (T)65536 && f > fp<T>::guard() && f < (T)1 - fp<T>::guard())
-    return (u32)(int)t;
+  if (coord != coord && !(*(volatile u32*)point_flags & 2u)) atomicOr(point_flags, 2u);  // a NaN
   return fp<T>::to_u32(fp<T>::div(a, scale)) & 0xFFFFu;
 }
 
-// phase_1.cuh:78-85.  static_cast<uint16_t>(T) compiles to cvt.rzi.u32 (saturating, NaN -> 0)
-// followed by & 0xFFFF, restated explicitly.  IEEE division (the reference builds with the default
-// -prec-div=true), no reciprocal multiply.
+template <typename T>
+__device__ __forceinline__ u32 cell_index(T coord, T lo, T scale, T inv_scale, u32* point_flags)
+{
+  T const a = fp<T>::sub(coord, lo);
+  T const q = fp<T>::mul(a, inv_scale);
+  T const t = fp<T>::trunc_(q);
+  T const f = q - t;
+  // (q < 65536 and f > guard imply q >= 0: a negative q has f <= 0)
+  if (q < (T)65536 && f > fp<T>::guard() && f < (T)1 - fp<T>::guard()) return (u32)(int)t;
+  return cell_index_exact<T>(a, scale, coord, point_flags);
+}
+
+// phase_1.cuh:78-85
 template <typename T>
 __device__ __forceinline__ u32 point_key(T x, T y, T min_x, T min_y, T max_x, T max_y, T scale,
-                                         T inv_scale, u32 oob_key, u32& flags)
+                                         T inv_scale, u32 oob_key, u32& flags, u32* point_flags)
 {
   if (x < min_x || x > max_x || y < min_y || y > max_y) {
     flags |= 1u;
     return oob_key;
   }
-  if (x != x || y != y) flags |= 2u;
-  u32 const ix = cell_index<T>(fp<T>::sub(x, min_x), scale, inv_scale);
-  u32 const iy = cell_index<T>(fp<T>::sub(y, min_y), scale, inv_scale);
+  u32 const ix = cell_index<T>(x, min_x, scale, inv_scale, point_flags);
+  u32 const iy = cell_index<T>(y, min_y, scale, inv_scale, point_flags);
   return (dilate16(iy) << 1) | dilate16(ix);
 }
 
@@ -90,18 +97,20 @@ __device__ __forceinline__ u32 point_key(T x, T y, T min_x, T min_y, T max_x, T 
 // K1: Morton encode fused with the radix digit histograms of all sort passes.
 // 128-bit coordinate loads, 128/64-bit key stores, shared-memory histograms.
 // Algorithmic bytes per point: 2*sizeof(T) read + 4 written.
+// The pass count is a template parameter: the tally unrolls to one shift/mask + one shared
+// atomic with an immediate offset per pass.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int PASSES>
 __global__ void __launch_bounds__(512)
 encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T min_x, T min_y,
-                   T max_x, T max_y, T scale, u32 oob_key, int passes, u32* __restrict__ keys,
+                   T max_x, T max_y, T scale, u32 oob_key, u32* __restrict__ keys,
                    u32* __restrict__ hist, u32* __restrict__ point_flags)
 {
-  u32 flags = 0;  // bit 0: a point outside the box, bit 1: a NaN coordinate
+  u32 flags = 0;  // bit 0: a point outside the box (bit 1, a NaN coordinate, is set out of line)
   T const inv_scale = (T)1 / scale;
   constexpr int V = 16 / sizeof(T);  // points per 128-bit load
-  __shared__ u32 s_hist[kMaxPasses * kRadixDigits];
-  for (int i = threadIdx.x; i < kMaxPasses * kRadixDigits; i += blockDim.x) s_hist[i] = 0;
+  __shared__ u32 s_hist[(PASSES ? PASSES : 1) * kRadixDigits];  // PASSES == 0: keys only
+  for (int i = threadIdx.x; i < PASSES * kRadixDigits; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
 
   u64 const nvec   = n / V;
@@ -111,8 +120,13 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
     (reinterpret_cast<uintptr_t>(keys) & (4 * V - 1)) == 0;
 
   auto tally = [&](u32 k) {
-    for (int p = 0; p < passes; ++p)
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p)
       atomicAdd(&s_hist[p * kRadixDigits + ((k >> (p * kRadixBits)) & 0xFFu)], 1u);
+  };
+  auto key_of = [&](T px, T py) {
+    return point_key<T>(px, py, min_x, min_y, max_x, max_y, scale, inv_scale, oob_key, flags,
+                        point_flags);
   };
 
   if (aligned) {
@@ -123,7 +137,7 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
       u32 ks[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        ks[j] = point_key<T>(xs[j], ys[j], min_x, min_y, max_x, max_y, scale, inv_scale, oob_key, flags);
+        ks[j] = key_of(xs[j], ys[j]);
         tally(ks[j]);
       }
       if constexpr (V == 2)
@@ -133,19 +147,19 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
     }
     // tail
     for (u64 i = nvec * V + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, inv_scale, oob_key, flags);
+      u32 const k = key_of(x[i], y[i]);
       tally(k);
       keys[i] = k;
     }
   } else {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      u32 const k = point_key<T>(x[i], y[i], min_x, min_y, max_x, max_y, scale, inv_scale, oob_key, flags);
+      u32 const k = key_of(x[i], y[i]);
       tally(k);
       keys[i] = k;
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < passes * kRadixDigits; i += blockDim.x)
+  for (int i = threadIdx.x; i < PASSES * kRadixDigits; i += blockDim.x)
     if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
   if (flags) atomicOr(point_flags, flags);
 }
@@ -474,9 +488,19 @@ void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_m
   u32 const oob_key = (u32)((1 << (2 * max_depth)) - 1);
   int const V       = 16 / sizeof(T);
   int const nblk    = (int)std::min<u64>((u64)kNumSMs * 4, (u64)div_up(div_up(n, V), 512));
-  encode_hist_kernel<T><<<std::max(nblk, 1), 512, 0, s>>>(
-    (const T*)x, (const T*)y, n, min_x, min_y, max_x, max_y, scale, oob_key, passes, keys, hist,
-    point_flags);
+  auto launch = [&](auto pass_tag) {
+    constexpr int P = decltype(pass_tag)::value;
+    encode_hist_kernel<T, P><<<std::max(nblk, 1), 512, 0, s>>>(
+      (const T*)x, (const T*)y, n, min_x, min_y, max_x, max_y, scale, oob_key, keys, hist,
+      point_flags);
+  };
+  switch (passes) {
+    case 0: launch(std::integral_constant<int, 0>{}); break;
+    case 1: launch(std::integral_constant<int, 1>{}); break;
+    case 2: launch(std::integral_constant<int, 2>{}); break;
+    case 3: launch(std::integral_constant<int, 3>{}); break;
+    default: launch(std::integral_constant<int, 4>{}); break;
+  }
   BSJ_CHECK_LAUNCH();
   grid->valid     = 1;
   grid->max_depth = max_depth;

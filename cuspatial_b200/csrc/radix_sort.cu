@@ -127,7 +127,11 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
   u32 const incl = warp_inclusive_scan(total);
   if (lane == 31) sm.warp_sums[warp] = incl;
   __syncthreads();
+  // The tile's digit totals are PUBLISHED before the in-tile permutation and the look-back is
+  // resolved after it: successors see this tile's aggregate as early as possible and this tile
+  // hides its own wait for its predecessors behind the shared-memory placement.
   if (tid < kRadixDigits) {
+    u64* const col = lookback + tid;
     u32 base = 0;
     for (int w = 0; w < warp; ++w) base += sm.warp_sums[w];
     u32 const bin_start = base + incl - total;
@@ -136,30 +140,11 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
     // padding keys (0xFFFFFFFF) of the last tile land at the end of digit 255: not counted
     u32 my_total = total;
     if (tid == kRadixDigits - 1) my_total -= ((u32)kSortTile - valid);
-
-    // ---- decoupled look-back on this digit's column of tile descriptors
-    u64* const col = lookback + tid;
-    u32 excl       = 0;
-    if (tile == 0) {
+    sm.gbase[tid] = my_total;  // parked here until the look-back below
+    if (tile == 0)
       st_relaxed_u64(col, lb_pack(tag_pre, my_total));
-    } else {
+    else
       st_relaxed_u64(col + (u64)tile * kRadixDigits, lb_pack(tag_agg, my_total));
-      i64 t = (i64)tile - 1;
-      while (true) {
-        u64 const v    = ld_relaxed_u64(col + (u64)t * kRadixDigits);
-        u32 const flag = (u32)(v >> 32);
-        if (flag == tag_pre) {
-          excl += (u32)v;
-          break;
-        }
-        if (flag == tag_agg) {
-          excl += (u32)v;
-          --t;
-        }
-      }
-      st_relaxed_u64(col + (u64)tile * kRadixDigits, lb_pack(tag_pre, excl + my_total));
-    }
-    sm.gbase[tid] = digit_offsets[tid] + excl - bin_start;
     // fold the digit's tile offset into every warp's offset: one random lookup per element
     // in the placement below instead of two
 #pragma unroll
@@ -188,6 +173,30 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
       u32 const pos = wh[d].x + rank[i];
       sm.kv[pos]    = make_uint2(key[i], v[i]);
     }
+  }
+
+  // ---- decoupled look-back on this digit's column of tile descriptors
+  if (tid < kRadixDigits) {
+    u64* const col     = lookback + tid;
+    u32 const my_total = sm.gbase[tid];
+    u32 excl           = 0;
+    if (tile != 0) {
+      i64 t = (i64)tile - 1;
+      while (true) {
+        u64 const v    = ld_relaxed_u64(col + (u64)t * kRadixDigits);
+        u32 const flag = (u32)(v >> 32);
+        if (flag == tag_pre) {
+          excl += (u32)v;
+          break;
+        }
+        if (flag == tag_agg) {
+          excl += (u32)v;
+          --t;
+        }
+      }
+      st_relaxed_u64(col + (u64)tile * kRadixDigits, lb_pack(tag_pre, excl + my_total));
+    }
+    sm.gbase[tid] = digit_offsets[tid] + excl - sm.bin_start[tid];
   }
   __syncthreads();
 

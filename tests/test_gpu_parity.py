@@ -123,6 +123,32 @@ def test_random_inputs_equal_oracle(oracle_lib, case, dtype):
     assert_same(run_gpu(c, max_size, use_grid_hint="no_keys"), want, "gpu (no keys) vs oracle")
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_small_configurations_equal_oracle(oracle_lib, seed):
+    """Randomised shapes (point count, polygon count and size, depth, max_size, distribution,
+    dtype, out-of-bbox points, duplicates): small inputs walk through the code paths that big
+    benchmarks never touch (few tiles, tiny levels, warp-kernel tree levels, empty quadrants)."""
+    rng = np.random.default_rng(1000 + seed)
+    for it in range(8):
+        n = int(rng.choice([1, 2, 33, 257, 1000, 4097, 20000, 60000]))
+        n_poly = int(rng.choice([1, 2, 7, 31, 64]))
+        depth = int(rng.integers(1, 16))
+        max_size = int(rng.choice([1, 2, 5, 32, 64, 200, 512]))
+        dtype = [np.float32, np.float64][int(rng.integers(0, 2))]
+        kind = "uc"[int(rng.integers(0, 2))]
+        oob = int(rng.integers(0, min(n, 20) + 1)) if rng.random() < 0.5 else 0
+        dups = int(rng.integers(0, min(n - oob, 300) + 1)) if rng.random() < 0.5 else 0
+        mv = int(rng.choice([4, 12, 40, 150]))
+        c = make_case(n, n_poly, depth, kind, dtype, seed=int(rng.integers(1, 10**6)),
+                      median_vertices=mv, oob=oob, dups=dups)
+        want = run_host(oracle_lib, c, max_size)
+        tag = "fuzz seed=%d it=%d n=%d polys=%d depth=%d max_size=%d %s %s oob=%d dups=%d mv=%d" % (
+            seed, it, n, n_poly, depth, max_size, dtype.__name__, kind, oob, dups, mv)
+        assert_same(run_gpu(c, max_size), want, tag)
+        if it % 2 == 0:
+            assert_same(run_gpu(c, max_size, use_grid_hint=False), want, tag + " (no hint)")
+
+
 def test_config1_1M_uniform_263_polygons_equals_oracle_and_reference(oracle_lib):
     """BASELINE.json configs[0]: 1M uniform fp64 points x 263 taxi-zone-like polygons."""
     from oracle import hostlib
@@ -396,6 +422,59 @@ def test_nearest_linestring_empty_and_errors():
         cs.linestring_bounding_boxes(ls, -1.0)
     with pytest.raises(RuntimeError, match="at least 2 vertices"):
         cs.linestring_bounding_boxes((_t(np.array([0, 1, 2], np.uint32)), ls[1], ls[2]), 0.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_sharding_kernels_on_one_gpu(dtype):
+    """The multi-GPU helpers, with every destination bucket in local memory: keys equal the
+    quadtree builder's keys, histograms equal bincounts, the partition is stable and complete."""
+    import ctypes as C
+
+    import torch
+
+    import cuspatial_b200 as cs
+    from cuspatial_b200 import _lib, multi_gpu as mg
+    from cuspatial_b200.api import _DTYPE_CODE, _ptr, _stream
+
+    c = make_case(300_000, 5, 15, "c", dtype, seed=5, oob=100, dups=1000)
+    x, y = _t(c["x"]), _t(c["y"])
+    ext = c["ext"]
+    pidx, tree = cs.quadtree_on_points((x, y), ext[0], ext[1], ext[2], ext[3], c["scale"], 15, 64)
+    shift = mg.hist_shift_for(15)
+    n_bins = 1 << mg.HIST_BITS
+    keys, bins = mg.cuda_keys_and_histogram(x, y, ext, c["scale"], 15, shift, n_bins)
+    k = keys.cpu().numpy().view(np.uint32)
+    np.testing.assert_array_equal(np.sort(k, kind="stable"), tree._sorted_keys.cpu().numpy())
+    np.testing.assert_array_equal(np.argsort(k, kind="stable").astype(np.uint32), pidx.cpu().numpy())
+    np.testing.assert_array_equal(bins.cpu().numpy(), np.bincount(k >> shift, minlength=n_bins))
+    # sub-histogram of the two heaviest first-level bins
+    targets = np.argsort(bins.cpu().numpy())[-2:].astype(np.uint32)
+    shift2, n_sub = max(shift - 10, 0), 1 << min(10, shift)
+    sub = mg.cuda_sub_histogram(keys, shift, targets, shift2, n_sub).cpu().numpy()
+    for t, b in enumerate(targets):
+        sel = k[(k >> shift) == b]
+        np.testing.assert_array_equal(sub[t], np.bincount((sel >> shift2) & (n_sub - 1),
+                                                          minlength=n_sub))
+    # partition into 3 local buckets
+    q = np.quantile(k, [0.3, 0.8]).astype(np.uint32)
+    dest = np.searchsorted(q, k, side="right")
+    counts = np.bincount(dest, minlength=3)
+    outs = [(torch.empty(int(n), dtype=x.dtype, device="cuda"),
+             torch.empty(int(n), dtype=x.dtype, device="cuda"),
+             torch.empty(int(n), dtype=torch.int32, device="cuda")) for n in counts]
+    px, py, pg = (C.c_void_p * 3)(), (C.c_void_p * 3)(), (C.c_void_p * 3)()
+    for d in range(3):
+        px[d], py[d], pg[d] = (outs[d][i].data_ptr() for i in range(3))
+    sp = np.ascontiguousarray(q, dtype=np.uint32)
+    _lib.check(_lib.lib().bsj_partition_points(
+        _ptr(keys), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], 7,
+        sp.ctypes.data_as(C.c_void_p), 3, px, py, pg, _stream(x.device)))
+    torch.cuda.synchronize()
+    for d in range(3):
+        ids = np.nonzero(dest == d)[0]
+        np.testing.assert_array_equal(outs[d][2].cpu().numpy(), ids.astype(np.int32) + 7)
+        np.testing.assert_array_equal(outs[d][0].cpu().numpy(), c["x"][ids])
+        np.testing.assert_array_equal(outs[d][1].cpu().numpy(), c["y"][ids])
 
 
 def test_error_conditions_match_reference():
