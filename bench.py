@@ -266,6 +266,86 @@ def run_bitmask(args):
     }))
 
 
+def run_nearest(args):
+    """SURVEY 8f row 2 (informational): quadtree_point_to_nearest_linestring.  `--points` uniform
+    fp64 points against the 263 polygon outlines taken as linestrings; the bounding boxes are
+    grown by the whole extent so that every point is a candidate of every linestring (the regime
+    where the reference's result is defined for every row).  A step = linestring boxes + bbox join
+    + nearest-linestring refinement on a prebuilt quadtree; the reference's CUDA build runs the
+    same three calls on the same inputs when it is present."""
+    import torch
+
+    import cuspatial_b200 as cs
+    from cuspatial_b200 import _lib
+    from cuspatial_b200 import datagen as D
+
+    dev = torch.device("cuda", 0)
+    (po, ro, vx, vy), ext, scale = make_polygons()
+    lo = ro[po]                      # one linestring per polygon: its rings' vertices in order
+    lines = (torch.as_tensor(lo.astype("uint32"), device=dev), torch.as_tensor(vx, device=dev),
+             torch.as_tensor(vy, device=dev))
+    n = args.points
+    x, y = D.uniform_points_torch(n, ext, SEED, torch.float64, dev)
+    radius = (ext[1] - ext[0]) + (ext[3] - ext[2])
+    pidx, tree = cs.quadtree_on_points((x, y), ext[0], ext[1], ext[2], ext[3], scale, MAX_DEPTH,
+                                       MAX_SIZE)
+
+    def step():
+        bb = cs.linestring_bounding_boxes(lines, radius)
+        pairs = cs.join_quadtree_and_bounding_boxes(tree, bb, ext[0], ext[1], ext[2], ext[3],
+                                                    scale, MAX_DEPTH)
+        return pairs, cs.quadtree_point_to_nearest_linestring(pairs, tree, pidx, (x, y), lines)
+
+    for _ in range(max(args.warmup, 1)):
+        pairs, out = step()
+    n_pairs = len(pairs)
+    segs = int(lo[-1]) - (len(lo) - 1)
+    checksum = float(out["distance"].sum())
+    torch.cuda.synchronize()
+    l0 = _lib.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = int(_lib.kernel_launch_count() - l0)
+
+    ref = None
+    from oracle import cudalib
+    if cudalib.available() and not args.no_gpu_reference:
+        lib = cudalib.reference_cuda()
+        rt, _ = lib.quadtree_on_points(x, y, ext[0], ext[1], ext[2], ext[3], scale, MAX_DEPTH,
+                                       MAX_SIZE)
+        ts = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            bb = lib.linestring_bounding_boxes(lines[0], lines[1], lines[2], radius)
+            t_bb = time.perf_counter() - t0
+            rp, t1 = lib.join_quadtree_and_bounding_boxes(rt, *bb, ext[0], ext[2], scale, MAX_DEPTH)
+            ro_, t2 = lib.quadtree_point_to_nearest_linestring(rp[0], rp[1], rt,
+                                                               rt["point_indices"], x, y, *lines)
+            ts.append((t_bb + t1 + t2) * 1e3)
+        same = bool(torch.equal(ro_[1], out["linestring_index"]) and
+                    torch.equal(ro_[2], out["distance"]))
+        ref = {"ms_per_step": min(ts[1:]), "points_per_s": n / (min(ts[1:]) / 1e3),
+               "identical_rows": same}
+    print(json.dumps({
+        "metric": "quadtree nearest-linestring points/sec", "value": n / (ms / 1e3),
+        "unit": "points/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%d uniform fp64 points x %d linestrings (%d segments), every "
+                               "point a candidate of every linestring, prebuilt quadtree "
+                               "max_depth=%d max_size=%d" % (n, len(lo) - 1, segs, MAX_DEPTH,
+                                                             MAX_SIZE),
+                   "pairs": n_pairs, "point_segment_distances_per_step": n * segs,
+                   "distance_checksum": checksum},
+        "gpu_launches": launches, "gpu_reference": ref,
+    }))
+
+
 def run_sharded(args, dist, dev, rank, world, x, y, polys, ext, scale):
     """N > 1: the distributed join (cuspatial_b200/multi_gpu.py).  Every rank holds an arbitrary
     shard of `--points` points; a step = keys + histogram all-reduce, Morton-range partition +
@@ -344,7 +424,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
-    ap.add_argument("--workload", default="join", choices=["join", "bitmask"],
+    ap.add_argument("--workload", default="join", choices=["join", "bitmask", "nearest"],
                     help="join = configs[1] (the headline); bitmask = configs[2], the non-indexed "
                          "point_in_polygon API on 31 polygons (informational)")
     args = ap.parse_args()
@@ -354,6 +434,8 @@ def main():
         return run_reference_cuda(args)
     if args.workload == "bitmask":
         return run_bitmask(args)
+    if args.workload == "nearest":
+        return run_nearest(args)
 
     import numpy as np
     import torch

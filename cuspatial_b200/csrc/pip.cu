@@ -840,19 +840,23 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                   double const eby = (double)__shfl_sync(0xffffffffu, by, src);
                   double const run = ebx - eax, rise = eby - eay;
                   double const d   = eps * fmax(fmax(fabs(eax), fabs(ebx)), fmax(fabs(eay), fabs(eby)));
-                  double const lx = fmin(eax, ebx) - d, hx = fmax(eax, ebx) + d;
-                  double const ly = fmin(eay, eby) - d, hy = fmax(eay, eby) + d;
-                  double const reach = fabs(rise) * hw + fabs(run) * hh;
+                  // per-edge constants (warp-uniform): the edge's extent widened by its tolerance
+                  // AND by the cell half-size, and the |f| threshold.  The rounding allowance of f
+                  // uses the largest |ddx|, |ddy| any cell centre of this tile can have.
+                  double const lx = fmin(eax, ebx) - d - hw, hx = fmax(eax, ebx) + d + hw;
+                  double const ly = fmin(eay, eby) - d - hh, hy = fmax(eay, eby) + d + hh;
+                  double const mdx = fmax(fabs(tx0 - eax), fabs(tx1 - eax));
+                  double const mdy = fmax(fabs(ty0 - eay), fabs(ty1 - eay));
+                  double const thr = (fabs(rise) * hw + fabs(run) * hh) * 1.000001 +
+                                     1e-9 * (mdx * fabs(rise) + fabs(run) * mdy);
 #pragma unroll
                   for (int i = 0; i < kCellPPL; ++i) {
                     double const ddx = cx[i] - eax, ddy = cy[i] - eay;
                     double const f   = ddx * rise - run * ddy;  // (v - u) of the reference
                     // the edge's line passes through the widened cell square, within the edge's
                     // own (tolerance-widened) extent?
-                    double const tol = 1e-9 * (fabs(ddx * rise) + fabs(run * ddy));
-                    bool const touch = fabs(f) <= reach * 1.000001 + tol &&
-                                       cx[i] + hw >= lx && cx[i] - hw <= hx &&
-                                       cy[i] + hh >= ly && cy[i] - hh <= hy;
+                    bool const touch = fabs(f) <= thr && cx[i] >= lx && cx[i] <= hx &&
+                                       cy[i] >= ly && cy[i] <= hy;
                     near |= (u32)touch << i;
                     bool const y1 = eay > cy[i], y0 = eby > cy[i];
                     cross ^= (u32)((y1 != y0) && ((f < 0.0) != y1)) << i;
