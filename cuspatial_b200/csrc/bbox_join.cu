@@ -50,7 +50,7 @@ struct join_state {
   u32 n_top;     // number of level-0 nodes (quadtree_bbox_filtering.cuh:53-56)
   u32 n_hits;    // leaf hits found by the traversal
   u32 overflow;  // work-list overflow (malformed tree)
-  u32 pad;
+  u32 n_seeds;   // (box, node) sub-traversals queued by the seeding pass
 };
 
 // SoA tree -> one 16-byte record per node; counts level-0 nodes on the way.
@@ -79,7 +79,9 @@ traverse_kernel(const uint4* __restrict__ nodes, const T* __restrict__ bx0,
                 const T* __restrict__ by0, const T* __restrict__ bx1, const T* __restrict__ by1,
                 u32 n_boxes, T vmin_x, T vmin_y, T scale, int max_depth,
                 u32* __restrict__ out_box, u32* __restrict__ out_node, u32 capacity,
-                join_state* st)
+                join_state* st, const u32* __restrict__ seed_box,
+                const u32* __restrict__ seed_node, int stop_level, u32* __restrict__ q_box,
+                u32* __restrict__ q_node, u32 q_capacity)
 {
   extern __shared__ u32 s_stack_all[];
   int const warp      = threadIdx.x >> 5;
@@ -89,15 +91,19 @@ traverse_kernel(const uint4* __restrict__ nodes, const T* __restrict__ bx0,
   u32 const n_top     = min(st->n_top, (u32)kJoinStackCap);
   u32 const num_warps = gridDim.x * kJoinWarps;
 
-  // one warp per (bounding box, level-0 node): 4x the parallelism of a warp per box, and the
-  // four sub-traversals of a box are independent
-  u64 const n_units = (u64)n_boxes * max(n_top, 1u);
+  // Two launches of this kernel.  Seeding pass (seed_box == nullptr): one warp per (bounding
+  // box, level-0 node) descends to `stop_level`; internal nodes hit there are not expanded but
+  // queued as (box, node) seeds.  Main pass: one warp per seed traverses that subtree.  A box then
+  // spreads over as many warps as it overlaps level-`stop_level` cells instead of serialising its
+  // whole (latency-bound) traversal in one warp.  stop_level < 0: single pass, no queue.
+  bool const seeded = seed_box != nullptr;
+  u64 const n_units = seeded ? (u64)min(st->n_seeds, q_capacity) : (u64)n_boxes * max(n_top, 1u);
   for (u64 unit = (u64)blockIdx.x * kJoinWarps + warp; unit < n_units; unit += num_warps) {
-    u32 const box = (u32)(unit / max(n_top, 1u));
+    u32 const box = seeded ? __ldg(seed_box + unit) : (u32)(unit / max(n_top, 1u));
     T const qx0 = __ldg(bx0 + box), qy0 = __ldg(by0 + box);
     T const qx1 = __ldg(bx1 + box), qy1 = __ldg(by1 + box);
-    if (lane == 0) stack[0] = (u32)(unit % max(n_top, 1u));
-    u32 sp = n_top ? 1u : 0u;
+    if (lane == 0) stack[0] = seeded ? __ldg(seed_node + unit) : (u32)(unit % max(n_top, 1u));
+    u32 sp = (seeded || n_top) ? 1u : 0u;
     __syncwarp();
     while (sp > 0) {
       u32 const take  = min(sp, 32u);
@@ -107,7 +113,7 @@ traverse_kernel(const uint4* __restrict__ nodes, const T* __restrict__ bx0,
       sp              = base;
       __syncwarp();
 
-      bool leaf_hit = false;
+      bool leaf_hit = false, seed_hit = false;
       u32 nchild = 0, child0 = 0;
       if (have) {
         uint4 const nd   = __ldg(nodes + node);
@@ -128,8 +134,12 @@ traverse_kernel(const uint4* __restrict__ nodes, const T* __restrict__ bx0,
           if (!inner) {
             leaf_hit = true;
           } else if ((int)lv + 1 < max_depth) {  // quadtree_bbox_filtering.cuh:116 loop bound
-            nchild = nd.z;
-            child0 = nd.w;
+            if (!seeded && (int)lv == stop_level) {
+              seed_hit = true;
+            } else {
+              nchild = nd.z;
+              child0 = nd.w;
+            }
           }
         }
       }
@@ -144,6 +154,22 @@ traverse_kernel(const uint4* __restrict__ nodes, const T* __restrict__ bx0,
           if (o < capacity) {
             out_box[o]  = box;
             out_node[o] = node;
+          }
+        }
+      }
+      // ---- seeds for the main pass
+      u32 const sm_ = __ballot_sync(0xffffffffu, seed_hit);
+      if (sm_) {
+        u32 qbase = 0;
+        if (lane == 0) qbase = atomicAdd(&st->n_seeds, (u32)__popc(sm_));
+        qbase = __shfl_sync(0xffffffffu, qbase, 0);
+        if (seed_hit) {
+          u32 const o = qbase + __popc(sm_ & lt);
+          if (o < q_capacity) {
+            q_box[o]  = box;
+            q_node[o] = node;
+          } else {
+            st->overflow = 1;  // more level-k nodes than 4^(k+1) per box: malformed tree
           }
         }
       }
@@ -223,14 +249,26 @@ void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32*
   dev_buf<u32> hit_box, hit_node;
   join_state h{};
   int const grid = (int)std::min<u64>((u64)kNumSMs * 3, (u64)div_up(n_boxes * 4, kJoinWarps));
+  // seeding level k: at most 4^(k+1) level-k nodes per box; keep the queue below 2^24 entries
+  int stop_level = n_boxes <= (1u << 16) ? 3 : n_boxes <= (1u << 18) ? 2 : 1;
+  if (stop_level + 2 >= max_depth) stop_level = -1;  // shallow tree: one pass does it all
+  u64 const q_cap = stop_level >= 0 ? n_boxes << (2 * (stop_level + 1)) : 0;
+  dev_buf<u32> q_box(std::max<u64>(q_cap, 1), s), q_node(std::max<u64>(q_cap, 1), s);
   for (int attempt = 0; attempt < 2; ++attempt) {
     hit_box.alloc(capacity, s);
     hit_node.alloc(capacity, s);
     traverse_kernel<T><<<grid, kJoinWarps * 32, kJoinWarps * kJoinStackCap * 4, s>>>(
       nodes.get(), (const T*)bx0, (const T*)by0, (const T*)bx1, (const T*)by1, (u32)n_boxes,
       (T)x_min, (T)y_min, (T)scale, max_depth, hit_box.get(), hit_node.get(), (u32)capacity,
-      st.get());
+      st.get(), nullptr, nullptr, stop_level, q_box.get(), q_node.get(), (u32)q_cap);
     BSJ_CHECK_LAUNCH();
+    if (stop_level >= 0) {
+      traverse_kernel<T><<<kNumSMs * 3, kJoinWarps * 32, kJoinWarps * kJoinStackCap * 4, s>>>(
+        nodes.get(), (const T*)bx0, (const T*)by0, (const T*)bx1, (const T*)by1, (u32)n_boxes,
+        (T)x_min, (T)y_min, (T)scale, max_depth, hit_box.get(), hit_node.get(), (u32)capacity,
+        st.get(), q_box.get(), q_node.get(), -1, nullptr, nullptr, (u32)q_cap);
+      BSJ_CHECK_LAUNCH();
+    }
     BSJ_CUDA_TRY(cudaMemcpyAsync(&h, st.get(), sizeof(h), cudaMemcpyDeviceToHost, s));
     BSJ_CUDA_TRY(cudaStreamSynchronize(s));
     if (h.overflow)
@@ -239,6 +277,7 @@ void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32*
     if (h.n_hits <= capacity) break;
     capacity = h.n_hits;
     BSJ_CUDA_TRY(cudaMemsetAsync(&st.get()->n_hits, 0, sizeof(u32), s));
+    BSJ_CUDA_TRY(cudaMemsetAsync(&st.get()->n_seeds, 0, sizeof(u32), s));
   }
   tm.mark("traverse");
   u64 const p = h.n_hits;

@@ -261,11 +261,13 @@ poly_scan_kernel(poly_meta<T>* __restrict__ meta, u32 n_poly, u32* __restrict__ 
   if (tid == 0) { totals[0] = carry_a; totals[1] = carry_b; }
 }
 
-// Edge records + y-slab index, one warp per polygon.  FILL = false: write edge records, count
+// Edge records + y-slab index, one CTA per polygon (a 4096-vertex polygon would otherwise keep one
+// warp busy long after the 200-vertex ones are done).  FILL = false: write edge records, count
 // slab entries and list vertical edges; FILL = true: write the entries (order inside a slab is
 // arbitrary -- crossings XOR and on-edge ORs commute, the result does not depend on it).
+constexpr int kSlabBlock = 256;
 template <typename T, bool FILL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kSlabBlock)
 slab_build_kernel(const poly_meta<T>* __restrict__ meta, u32 n_poly,
                   const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
                   const T* __restrict__ vy, edge_rec<T>* __restrict__ edges,
@@ -273,14 +275,13 @@ slab_build_kernel(const poly_meta<T>* __restrict__ meta, u32 n_poly,
                   u32* __restrict__ entries, u32* __restrict__ vert_edges,
                   u32* __restrict__ vert_cursor)
 {
-  u32 const p    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  u32 const lane = lane_id();
+  u32 const p = blockIdx.x;
   if (p >= n_poly) return;
   poly_meta<T> const m = meta[p];
   if (m.n_slabs == 0) return;
   for (u32 r = m.ring_begin; r < m.ring_end; ++r) {
     u32 const v0 = ring_offsets[r], v1 = ring_offsets[r + 1];
-    for (u32 i = v0 + lane; i < v1; i += 32) {
+    for (u32 i = v0 + threadIdx.x; i < v1; i += kSlabBlock) {
       u32 const pr = i == v0 ? v1 - 1 : i - 1;
       T const ax = vx[i], ay = vy[i], bx = vx[pr], by = vy[pr];
       if (!FILL) edges[i] = edge_rec<T>{ax, ay, bx, by};
@@ -1253,7 +1254,7 @@ struct polygon_index {
     entry_total.alloc(1, s);
     slab_start.alloc(total_slabs + 1, s);
     BSJ_CUDA_TRY(cudaMemsetAsync(slab_count.get(), 0, slab_count.size() * sizeof(u32), s));
-    slab_build_kernel<T, false><<<poly_grid, 128, 0, s>>>(
+    slab_build_kernel<T, false><<<std::max<u32>(n_poly, 1), kSlabBlock, 0, s>>>(
       meta.get(), n_poly, ring_offsets, vx, vy, edges.get(), slab_count.get(), nullptr, nullptr,
       vert_edges.get(), vert_cursor.get());
     BSJ_CHECK_LAUNCH();
@@ -1272,7 +1273,7 @@ struct polygon_index {
                                                                    total_slabs + 1);
     BSJ_CHECK_LAUNCH();
     BSJ_CUDA_TRY(cudaMemsetAsync(slab_count.get(), 0, slab_count.size() * sizeof(u32), s));
-    slab_build_kernel<T, true><<<poly_grid, 128, 0, s>>>(
+    slab_build_kernel<T, true><<<std::max<u32>(n_poly, 1), kSlabBlock, 0, s>>>(
       meta.get(), n_poly, ring_offsets, vx, vy, edges.get(), slab_count.get(), slab_start.get(),
       entries.get(), vert_edges.get(), vert_cursor.get());
     BSJ_CHECK_LAUNCH();
