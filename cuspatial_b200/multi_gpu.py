@@ -211,9 +211,15 @@ def cuda_partition_exchange(keys, x, y, gid_base, splitters, counts_matrix, rank
         _lib.check(_lib.lib().bsj_partition_points(
             _ptr(keys), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], int(gid_base),
             sp.ctypes.data_as(C.c_void_p), R, ptr_x, ptr_y, ptr_g, _stream(dev)))
-    # every rank's stores must have landed before anyone reads its receive buffers
-    torch.cuda.synchronize(dev)
-    dist.barrier(group=group)
+    # every rank's stores must have landed before anyone reads its receive buffers: a device-side
+    # barrier over the symmetric-memory signal pads, enqueued after the partition kernel on the
+    # same stream (kernel completion makes its peer stores visible system-wide) -- no host
+    # synchronisation and no NCCL round trip.  BSJ_MG_HOST_BARRIER=1 restores the host barrier.
+    if os.environ.get("BSJ_MG_HOST_BARRIER") == "1":
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+    else:
+        ent["hdls"][0].barrier(channel=0)
     n_recv = recv_tot[rank]
     rx, ry, rg = (b[:n_recv] for b in ent["bufs"])
     return rx, ry, rg
@@ -298,36 +304,48 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     scale = max(scale, min_scale)
 
     prof = _Prof(dev)
-    # 1. replicate the polygon table (sizes first, then payload) -- NCCL broadcast
+    # 1. replicate the polygon table -- two NCCL broadcasts: the four sizes, then ONE packed byte
+    # buffer (each array padded to 16 bytes) that the receivers slice into typed views
+    src0 = dist.get_global_rank(group, 0) if group else 0
     meta = torch.tensor([t.shape[0] for t in polygons], dtype=torch.int64, device=dev)
-    dist.broadcast(meta, src=dist.get_global_rank(group, 0) if group else 0, group=group)
-    polys = []
-    for t, n in zip(polygons, meta.tolist()):
-        if rank != 0:
-            t = torch.empty(n, dtype=t.dtype, device=dev)
-        t = t.contiguous()
-        view = t.view(torch.int32) if t.dtype == torch.uint32 else t
-        dist.broadcast(view, src=dist.get_global_rank(group, 0) if group else 0, group=group)
-        polys.append(t)
+    dist.broadcast(meta, src=src0, group=group)
+    sizes = meta.tolist()
+    nbytes = [n * t.element_size() for n, t in zip(sizes, polygons)]
+    padded = [b + (-b) % 16 for b in nbytes]
+    if rank == 0:
+        parts = []
+        for t, b, pb in zip(polygons, nbytes, padded):
+            parts.append(t.contiguous().view(torch.uint8))
+            if pb > b:
+                parts.append(torch.zeros(pb - b, dtype=torch.uint8, device=dev))
+        packed_polys = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=dev)
+    else:
+        packed_polys = torch.empty(sum(padded), dtype=torch.uint8, device=dev)
+    if packed_polys.numel():
+        dist.broadcast(packed_polys, src=src0, group=group)
+    polys, o = [], 0
+    for t, n, b, pb in zip(polygons, sizes, nbytes, padded):
+        polys.append(packed_polys[o: o + b].view(t.dtype) if n else
+                     torch.empty(0, dtype=t.dtype, device=dev))
+        o += pb
     polys = tuple(polys)
 
     prof.mark("broadcast_polygons")
-    # global ids are rank-major
-    n_local = torch.tensor([x.shape[0]], dtype=torch.int64, device=dev)
-    all_n = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(all_n, n_local, group=group)
-    all_n = [int(v.item()) for v in all_n]
-    gid_base = sum(all_n[:rank])
-
-    # 2. keys + leading-bit histogram, one all-reduce, identical splitters everywhere
+    # 2. keys + leading-bit histogram, one all-reduce, identical splitters everywhere.  The
+    # per-rank point counts (global ids are rank-major) ride in `world` extra slots of the same
+    # all-reduce, and local + global histogram come back to the host in one copy.
     shift = hist_shift_for(max_depth)
     n_bins = 1 << min(HIST_BITS, 32 - shift) if shift < 32 else 1
-    prof.mark("gid_bases")
     keys, hist = keys_hist(x, y, bbox, scale, max_depth, shift, n_bins)
     prof.mark("keys_hist")
-    local_hist = hist.detach().clone().cpu().numpy()
-    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
-    hist_h = hist.cpu().numpy()
+    slots = torch.zeros(world, dtype=hist.dtype, device=dev)
+    slots[rank] = x.shape[0]
+    both = torch.stack([torch.cat([hist, slots])] * 2)   # row 0 stays local, row 1 is reduced
+    dist.all_reduce(both[1], op=dist.ReduceOp.SUM, group=group)
+    both_h = both.cpu().numpy()
+    local_hist, hist_h = both_h[0, :n_bins].copy(), both_h[1, :n_bins].copy()
+    all_n = [int(v) for v in both_h[1, n_bins:]]
+    gid_base = sum(all_n[:rank])
     # two-level splitters: a first-level bin can hold a whole cluster, so the boundary is placed
     # inside it with a second histogram of the next SUB_BITS key bits (one more all-reduce)
     sub_hist = steps.get("sub_hist", cuda_sub_histogram)
@@ -336,9 +354,11 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     targets, bounds = refine_splitters(hist_h, world, shift)
     if n_sub > 1 and targets:
         sub = sub_hist(keys, shift, targets, shift2, n_sub)
-        sub_local = sub.detach().clone().cpu().numpy()
-        dist.all_reduce(sub, op=dist.ReduceOp.SUM, group=group)
-        splitters = splitters_from_subhist(bounds, targets, sub.cpu().numpy(), shift, shift2)
+        sub_both = torch.stack([sub, sub])
+        dist.all_reduce(sub_both[1], op=dist.ReduceOp.SUM, group=group)
+        sub_h = sub_both.cpu().numpy()
+        sub_local = sub_h[0].copy()
+        splitters = splitters_from_subhist(bounds, targets, sub_h[1], shift, shift2)
     else:
         targets, sub_local = [], np.zeros((0, 1), dtype=np.int64)
         splitters = choose_splitters(hist_h, world, shift)
