@@ -61,3 +61,53 @@ def test_product_package_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert "liboracle" not in txt and "libcuspatial_ref" not in txt, f
+
+
+def test_cpp_header_compiles_against_the_c_abi(tmp_path):
+    """include/cuspatial_b200.hpp: the reference's C++ signatures over raw device spans."""
+    import shutil
+    import subprocess
+
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if cxx is None:
+        pytest.skip("no host C++ compiler")
+    src = tmp_path / "use_header.cpp"
+    src.write_text(
+        '#include "cuspatial_b200.hpp"\n'
+        "using namespace cuspatial_b200;\n"
+        "int main() {\n"
+        "  column_view<double> d; column_view<uint32_t> u; column_view<int32_t> i;\n"
+        "  pair_table p; quadtree_table q;\n"
+        "  if (d.size) {\n"
+        "    auto t = quadtree_on_points<double>(d, d, 0, 1, 0, 1, 1, 15, 512);\n"
+        "    auto j = join_quadtree_and_bounding_boxes<double>(t.second, d, d, d, d, 0, 1, 0, 1, 1,"
+        " 15);\n"
+        "    auto h = quadtree_point_in_polygon<double>(j, t.second, u, d, d, u, u, d, d);\n"
+        "    point_in_polygon<double>(d, d, i, i, d, d, nullptr);\n"
+        "    pairwise_point_in_polygon<double>(d, d, i, i, d, d, nullptr);\n"
+        "    quadtree_point_to_nearest_linestring<double>(p, q, u, d, d, u, d, d, nullptr, nullptr,"
+        " nullptr);\n"
+        "    linestring_bounding_boxes<double>(u, d, d, 0.0, nullptr, nullptr, nullptr, nullptr);\n"
+        "  }\n"
+        "  return 0;\n"
+        "}\n")
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run([cxx, "-std=c++17", "-fsyntax-only", "-I", inc, "-I",
+                        "/usr/local/cuda/include", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU reference on the host cores) needs no GPU."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "points/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
