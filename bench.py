@@ -458,6 +458,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="coordinate type of the join workload (the headline is f64)")
     ap.add_argument("--workload", default="join", choices=["join", "bitmask", "nearest"],
                     help="join = configs[1] (the headline); bitmask = configs[2], the non-indexed "
                          "point_in_polygon API on 31 polygons (informational)")
@@ -495,7 +497,11 @@ def main():
     polys = tuple(torch.as_tensor(a, device=dev) for a in (po, ro, vx, vy))
     # (for N > 1 the polygon table is replicated from rank 0 by an NCCL broadcast inside the
     #  sharded join itself, every step)
-    x, y = D.uniform_points_torch(n, ext, SEED + rank, torch.float64, dev)
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    T = 8 if args.dtype == "f64" else 4
+    if args.dtype == "f32":  # polygons in the same coordinate type (points/polygons must agree)
+        polys = (polys[0], polys[1], polys[2].float(), polys[3].float())
+    x, y = D.uniform_points_torch(n, ext, SEED + rank, tdt, dev)
     bb = cs.polygon_bounding_boxes(polys)
 
     def step():
@@ -572,14 +578,14 @@ def main():
     # algorithmic bytes per launch of the candidate dominant kernels
     alg_bytes = {
         "onesweep_pass": n * (12 + 16 * (passes - 1)) / passes,
-        "encode_hist": n * (2 * 8 + 4),
-        "pip_eval": n * c * (4 + 2 * 8),   # index + gathered coords per candidate
+        "encode_hist": n * (2 * T + 4),
+        "pip_eval": n * c * (4 + 2 * T),   # index + gathered coords per candidate
         "pip_emit": n * h * 8,
     }
     dom = max(alg_bytes, key=lambda k: stage_per_step.get(k, 0.0))
     dom_ms = stage_avg.get(dom, float("nan"))
     achieved = alg_bytes[dom] / (dom_ms / 1e3) / 1e9
-    b_alg = (2 * 8 + 4) + (12 + 16 * (passes - 1)) + 4 + c * (4 + 2 * 8) + 8 * h
+    b_alg = (2 * T + 4) + (12 + 16 * (passes - 1)) + 4 + c * (4 + 2 * T) + 8 * h
     traffic = None
     try:  # per-launch DRAM bytes of that kernel from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
@@ -603,8 +609,8 @@ def main():
     # ---- end to end through the public API with host buffers
     e2e = None
     if not args.no_e2e:
-        hx = torch.empty(n, dtype=torch.float64).pin_memory()
-        hy = torch.empty(n, dtype=torch.float64).pin_memory()
+        hx = torch.empty(n, dtype=tdt).pin_memory()
+        hy = torch.empty(n, dtype=tdt).pin_memory()
         hx.copy_(x)
         hy.copy_(y)
         torch.cuda.synchronize(dev)
@@ -639,7 +645,7 @@ def main():
         if dist is not None:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n / float(dt.item()), "unit": "points/s",
-               "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": int(d2h),
+               "h2d_bytes_per_step": 2 * n * T, "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * float(dt.item()),
                "note": "pinned host x,y -> device, 3 API calls, full (polygon_index, point_index) "
                        "table read back to host"}
@@ -660,13 +666,13 @@ def main():
         print(json.dumps({
             "metric": "quadtree PIP join points/sec", "value": value, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
-            "config": {"workload": "configs[1]: %d uniform fp64 points x %d taxi-zone-like "
+            "config": {"workload": "configs[1]: %d uniform %s points x %d taxi-zone-like "
                                    "polygons per GPU, quadtree max_depth=%d max_size=%d"
-                                   % (n, N_POLY, MAX_DEPTH, MAX_SIZE),
+                                   % (n, "fp64" if T == 8 else "fp32", N_POLY, MAX_DEPTH, MAX_SIZE),
                        "l2": "inputs (%.1f GB) and every intermediate exceed the 126 MB L2"
-                             % (2 * n * 8 / 1e9),
+                             % (2 * n * T / 1e9),
                        "nodes": n_nodes, "pairs": n_pairs, "candidates": n_cand, "hits": n_hits,
                        "parallelism": "replicated polygons, independent point shards"
                        if world > 1 else "single GPU"},

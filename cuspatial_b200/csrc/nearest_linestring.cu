@@ -67,7 +67,7 @@ __device__ __forceinline__ T dot2(T ax, T ay, T bx, T by)
 constexpr int kNlBlock = 128;
 
 template <typename T>
-__global__ void __launch_bounds__(kNlBlock)
+__global__ void __launch_bounds__(kNlBlock, 6)
 nearest_linestring_kernel(const u32* __restrict__ pair_line, const u32* __restrict__ pair_quad,
                           u64 n_pairs, const u32* __restrict__ length,
                           const u32* __restrict__ offset, const u32* __restrict__ point_indices,
@@ -115,9 +115,25 @@ nearest_linestring_kernel(const u32* __restrict__ pair_line, const u32* __restri
             T const ex = fpl<T>::sub(bx, ax), ey = fpl<T>::sub(by, ay);
             T const d2 = dot2<T>(ex, ey, ex, ey);
             T const d3 = dot2<T>(v1px, v1py, ex, ey);
-            T const r  = fpl<T>::div(fpl<T>::mul(d3, d3), d2);
-            T const d  = (d3 <= (T)0 || r >= d2) ? fmin(d0, d1) : fpl<T>::sub(d0, r);
-            dsq        = fmin(dsq, d);
+            // reference: r = d3*d3/d2; d = (d3 <= 0 || r >= d2) ? min(d0, d1) : d0 - r.
+            // The IEEE division is the most expensive operation here and its result only
+            // matters when the projection falls inside the segment: d3 <= 0 decides without it,
+            // and d3*d3 > d2*d2 (with a margin far above the rounding of the two products)
+            // implies r >= d2 -- rounding is monotone and d2 is representable.  NaN, overflow
+            // and underflow fail the comparison and take the literal path.
+            T d;
+            if (d3 <= (T)0) {
+              d = fmin(d0, d1);
+            } else {
+              T const m = fpl<T>::mul(d3, d3);
+              if (m > fpl<T>::mul(fpl<T>::mul(d2, d2), (T)1.00001)) {
+                d = fmin(d0, d1);
+              } else {
+                T const r = fpl<T>::div(m, d2);
+                d         = (r >= d2) ? fmin(d0, d1) : fpl<T>::sub(d0, r);
+              }
+            }
+            dsq = fmin(dsq, d);
             ax = bx; ay = by; v1px = v2px; v1py = v2py; d0 = d1;
           }
         }

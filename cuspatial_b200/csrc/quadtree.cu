@@ -71,6 +71,12 @@ template <typename T>
 __device__ __forceinline__ u32 cell_index(T coord, T lo, T scale, T inv_scale, u32* point_flags)
 {
   T const a = fp<T>::sub(coord, lo);
+  if constexpr (sizeof(T) == 4) {
+    // fp32: the guard band would be 2^-5 wide (6 % of the coordinates, i.e. some lane of nearly
+    // every warp), and the IEEE fp32 division is only ~10 instructions: always divide.
+    if (coord != coord && !(*(volatile u32*)point_flags & 2u)) atomicOr(point_flags, 2u);
+    return fp<T>::to_u32(fp<T>::div(a, scale)) & 0xFFFFu;
+  }
   T const q = fp<T>::mul(a, inv_scale);
   T const t = fp<T>::trunc_(q);
   T const f = q - t;
