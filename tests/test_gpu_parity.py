@@ -149,6 +149,17 @@ def test_fuzz_small_configurations_equal_oracle(oracle_lib, seed):
             assert_same(run_gpu(c, max_size, use_grid_hint=False), want, tag + " (no hint)")
 
 
+@pytest.mark.parametrize("n_poly,n,dtype,kind", [(10_000, 1_000_000, np.float64, "c"),
+                                                 (50_000, 500_000, np.float32, "u")])
+def test_many_polygons_equal_oracle(oracle_lib, n_poly, n, dtype, kind):
+    """The polygon counts of BASELINE.json configs[3] and configs[4] (10 k and 50 k polygons):
+    per-polygon index build, seeded traversal queue and pair bookkeeping at that scale."""
+    c = make_case(n, n_poly, 15, kind, dtype, seed=123, median_vertices=24, oob=50)
+    want = run_host(oracle_lib, c, 128)
+    assert len(want["pairs"][0]) > n_poly
+    assert_same(run_gpu(c, 128), want, "gpu vs oracle (%d polygons)" % n_poly)
+
+
 def test_config1_1M_uniform_263_polygons_equals_oracle_and_reference(oracle_lib):
     """BASELINE.json configs[0]: 1M uniform fp64 points x 263 taxi-zone-like polygons."""
     from oracle import hostlib
