@@ -3,7 +3,7 @@
 the merged pair set and the global point_indices must equal a single-process CPU-oracle run.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-      --master-port 29511 scripts/check_multi_gpu.py
+      --master-port 29511 tests/multi_gpu_parity.py
 """
 import os
 import sys
@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from cuspatial_b200 import multi_gpu as mg  # noqa: E402
 from util import make_case, run_host  # noqa: E402
