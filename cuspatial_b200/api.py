@@ -64,10 +64,28 @@ def _as_cuda(t, dtype=None, name="input"):
     return t.contiguous()
 
 
+def _accessor(obj, kind):
+    """A geoarrow.GeoArrowSeries -> its .points / .polygons / .lines accessor; anything else as is."""
+    from .geoarrow import GeoArrowSeries
+
+    return obj._get(kind) if isinstance(obj, GeoArrowSeries) else obj
+
+
+def _reject_multi(obj, what):
+    from .geoarrow import GeoArrowSeries, is_multi
+
+    if isinstance(obj, GeoArrowSeries) and is_multi(obj):
+        raise ValueError("GeoSeries cannot contain %s." % what)  # join.py:75-78, 323-326
+
+
 def _split_points(points):
-    """(x, y) | (N,2) | flat interleaved xy  ->  contiguous x, y (reference: geoseries .x/.y
-    make strided copies of the interleaved buffer, core/geoseries.py:238-243)."""
-    if isinstance(points, (tuple, list)) and len(points) == 2:
+    """(x, y) | (N,2) | flat interleaved xy | GeoArrowSeries of points  ->  contiguous x, y
+    (reference: geoseries .x/.y make strided copies of the interleaved buffer,
+    core/geoseries.py:238-243)."""
+    points = _accessor(points, "points")
+    if hasattr(points, "xy") and hasattr(points, "x"):
+        x, y = _as_cuda(points.x, name="points.x"), _as_cuda(points.y, name="points.y")
+    elif isinstance(points, (tuple, list)) and len(points) == 2:
         x, y = _as_cuda(points[0], name="points.x"), _as_cuda(points[1], name="points.y")
     else:
         p = _as_cuda(points, name="points")
@@ -85,6 +103,7 @@ def _split_points(points):
 
 
 def _split_polygons(polygons):
+    polygons = _accessor(polygons, "polygons")
     if hasattr(polygons, "part_offset"):
         polygons = (polygons.part_offset, polygons.ring_offset, polygons.x, polygons.y)
     if not (isinstance(polygons, (tuple, list)) and len(polygons) == 4):
@@ -326,6 +345,7 @@ def point_in_polygon(points, polygons):
     Returns a Frame with one bool column per polygon (column i <-> polygon i), reference:
     join.py:23-102 (bitmask unpacked as utils/join_utils.py:12-46 does).
     """
+    _reject_multi(polygons, "multipolygon")
     po = polygons[0] if isinstance(polygons, (tuple, list)) else polygons.part_offset
     n_poly = max(int(po.shape[0]) - 1, 0)
     if n_poly == 0:
@@ -337,6 +357,7 @@ def point_in_polygon(points, polygons):
 def _split_linestrings(linestrings):
     """(part_offset, x, y) arrays in GeoArrow layout, or an object with .part_offset/.x/.y
     (the reference takes a GeoSeries and reads linestrings.lines.part_offset/x/y)."""
+    linestrings = _accessor(linestrings, "linestrings")
     if hasattr(linestrings, "part_offset"):
         linestrings = (linestrings.part_offset, linestrings.x, linestrings.y)
     if not (isinstance(linestrings, (tuple, list)) and len(linestrings) == 3):
@@ -350,7 +371,12 @@ def _split_linestrings(linestrings):
 def linestring_bounding_boxes(linestrings, expansion_radius):
     """Axis-aligned bounding box of every linestring, grown by `expansion_radius`
     -> Frame[minx, miny, maxx, maxy] (reference: core/spatial/bounding.py:83-140)."""
+    acc = _accessor(linestrings, "linestrings")
     lo, lx, ly = _split_linestrings(linestrings)
+    if getattr(acc, "geometry_offset", None) is not None:
+        # bounding.py:123-125: one box per geometry, over all of its parts
+        go = _as_cuda(acc.geometry_offset, torch.int64)
+        lo = lo.view(torch.int32)[go].view(lo.dtype) if lo.dtype == torch.uint32 else lo[go]
     if lx.dtype != ly.dtype:
         raise RuntimeError("Data type mismatch")
     if lx.shape[0] != ly.shape[0]:
@@ -372,6 +398,7 @@ def quadtree_point_to_nearest_linestring(linestring_quad_pairs, quadtree, point_
     Returns Frame[point_index u32, linestring_index u32, distance T], one row per point in
     quadtree order; point_index indexes `point_indices` -- reference: join.py:265-352.
     """
+    _reject_multi(linestrings, "multilinestrings")
     x, y = _split_points(points)
     lo, lx, ly = _split_linestrings(linestrings)
     if lx.dtype != ly.dtype:
