@@ -216,3 +216,39 @@ def test_oracle_nearest_linestring_partial_coverage_is_zero_filled(oracle_lib):
     assert (a["nearest"][2][~m] == 0).all() and (a["nearest"][0][~m] == 0).all()
     np.testing.assert_array_equal(a["nearest"][0][m], np.nonzero(m)[0])
     assert (a["nearest"][2][m] > 0).all()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_lattice_polygons_oracle_equals_reference(oracle_lib, reference_lib, dtype):
+    """Adversarial exact-arithmetic territory: integer-lattice polygons (collinear runs, repeated
+    vertices, self-intersections, unclosed rings, a hole touching the shell) against every lattice
+    and half-lattice point -- most points sit exactly on an edge, a vertex or an edge's line."""
+    rng = np.random.default_rng(2024)
+    rings, po, ro = [], [0], [0]
+    for p in range(31):
+        k = int(rng.integers(3, 9))
+        v = rng.integers(0, 9, size=(k, 2)).astype(np.float64)
+        if p % 5 == 0:
+            v = np.repeat(v, 2, axis=0)[: k + 2]          # repeated vertices (zero-length segments)
+        if p % 3 == 0:
+            v = np.vstack([v, v[:1]])                      # closed ring; the others stay unclosed
+        rings.append(v)
+        ro.append(ro[-1] + len(v))
+        if p % 7 == 0:                                     # a hole sharing a vertex with the shell
+            h = np.array([v[0], v[0] + [1, 0], v[0] + [0, 1], v[0]])
+            rings.append(h)
+            ro.append(ro[-1] + len(h))
+        po.append(len(ro) - 1)
+    vv = np.vstack(rings).astype(dtype)
+    gx, gy = np.meshgrid(np.arange(-1, 19) / 2.0, np.arange(-1, 19) / 2.0)
+    px, py = gx.reshape(-1).astype(dtype), gy.reshape(-1).astype(dtype)
+    po, ro = np.array(po, np.int32), np.array(ro, np.int32)
+    a = oracle_lib.point_in_polygon(px, py, po, ro, vv[:, 0].copy(), vv[:, 1].copy())
+    b = reference_lib.point_in_polygon(px, py, po, ro, vv[:, 0].copy(), vv[:, 1].copy())
+    np.testing.assert_array_equal(a, b)
+    assert 0 < np.count_nonzero(a) < len(a)
+    # the same polygons pairwise against a point each
+    qx, qy = px[:31].copy(), py[200:231].copy()
+    np.testing.assert_array_equal(
+        oracle_lib.pairwise_point_in_polygon(qx, qy, po, ro, vv[:, 0].copy(), vv[:, 1].copy()),
+        reference_lib.pairwise_point_in_polygon(qx, qy, po, ro, vv[:, 0].copy(), vv[:, 1].copy()))
