@@ -43,6 +43,8 @@ N_POLY = 263
 MAX_DEPTH = 15
 MAX_SIZE = 512
 SEED = 20251017
+# CPU legs: a bounded sample of the same workload, ~10 s on the GPU box's 16 host cores
+CPU_SAMPLE = 20_000_000
 
 
 def read_peaks():
@@ -165,7 +167,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 2_000_000
+    sample = CPU_SAMPLE
     vals = []
     info = None
     for i in range(args.warmup + args.steps):
@@ -653,7 +655,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(2_000_000)
+        cpu = cpu_baseline(CPU_SAMPLE)
         cpu.pop("seconds", None)
 
     gpu_ref = None
