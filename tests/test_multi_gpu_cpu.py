@@ -77,7 +77,7 @@ def _host_steps(oracle):
             "expand": expand, "sub_hist": sub_hist}
 
 
-def _worker(rank, world, port, kind, dtype_name, q):
+def _worker(rank, world, port, kind, dtype_name, q, gather=True):
     import torch
     import torch.distributed as dist
 
@@ -101,7 +101,7 @@ def _worker(rank, world, port, kind, dtype_name, q):
         ext = c["ext"]
         out = mg.sharded_quadtree_point_in_polygon(
             (x, y), polys, ext[0], ext[1], ext[2], ext[3], c["scale"], c["depth"], 32,
-            gather_pairs=True, gather_point_indices=True, steps=_host_steps(hostlib.oracle()))
+            gather_pairs=gather, gather_point_indices=True, steps=_host_steps(hostlib.oracle()))
         q.put((rank, out["polygon_index"].numpy(), out["point_index"].numpy(),
                out["point_indices"].numpy(), out["counts"]))
     finally:
@@ -146,6 +146,40 @@ def test_sharded_join_world2_equals_single_process_oracle(oracle_lib, kind, dtyp
         np.testing.assert_array_equal(pidx.view(np.uint32), ref["tree"]["point_indices"])
         # two-level splitters: the ranks are balanced to within a sub-bin even for clustered data
         assert sum(counts) == len(c["x"]) and min(counts) > 0.9 * len(c["x"]) / world
+
+
+def test_sharded_join_world3_partitioned_rows_union_equals_oracle(oracle_lib):
+    """Odd world size and gather_pairs=False: every rank keeps only the rows of its own key range
+    (with GLOBAL point_index); their disjoint union is the single-process pair set."""
+    import torch.multiprocessing as mp
+
+    from util import make_case, run_host
+
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, "c", "float64", q, False))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    c = make_case(30000, 25, 10, "c", np.float64, seed=77, oob=20, dups=200, median_vertices=24)
+    ref = run_host(oracle_lib, c, 32)
+    want = np.stack([ref["hits"][0].astype(np.int64), ref["hits"][1].astype(np.int64)], 1)
+    want = want[np.lexsort((want[:, 1], want[:, 0]))]
+    parts = [np.stack([hp.view(np.uint32).astype(np.int64), hq.view(np.uint32).astype(np.int64)], 1)
+             for _, hp, hq, _, _ in results]
+    assert sum(len(p) for p in parts) == len(want)            # disjoint: no row twice
+    got = np.concatenate(parts)
+    got = got[np.lexsort((got[:, 1], got[:, 0]))]
+    np.testing.assert_array_equal(got, want)
+    for _, _, _, pidx, counts in results:
+        np.testing.assert_array_equal(pidx.view(np.uint32), ref["tree"]["point_indices"])
+        assert sum(counts) == len(c["x"]) and min(counts) > 0.85 * len(c["x"]) / world
 
 
 def test_two_level_splitters_balance_a_heavy_bin():
