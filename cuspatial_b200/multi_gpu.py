@@ -215,11 +215,15 @@ def cuda_partition_exchange(keys, x, y, gid_base, splitters, counts_matrix, rank
     # barrier over the symmetric-memory signal pads, enqueued after the partition kernel on the
     # same stream (kernel completion makes its peer stores visible system-wide) -- no host
     # synchronisation and no NCCL round trip.  BSJ_MG_HOST_BARRIER=1 restores the host barrier.
-    if os.environ.get("BSJ_MG_HOST_BARRIER") == "1":
+    # The device barrier is verified at 2 and 4 GPUs; larger groups keep the host barrier (the
+    # form verified at 8 GPUs) until it has been re-run there -- BSJ_MG_DEVICE_BARRIER=1 forces it.
+    use_device = (R <= 4 or os.environ.get("BSJ_MG_DEVICE_BARRIER") == "1") and \
+        os.environ.get("BSJ_MG_HOST_BARRIER") != "1"
+    if use_device:
+        ent["hdls"][0].barrier(channel=0)
+    else:
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)
-    else:
-        ent["hdls"][0].barrier(channel=0)
     n_recv = recv_tot[rank]
     rx, ry, rg = (b[:n_recv] for b in ent["bufs"])
     return rx, ry, rg
