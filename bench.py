@@ -138,8 +138,6 @@ def make_polygons():
 
 def cpu_baseline(sample_points, want_seconds=15.0):
     """Time the CPU implementation of the whole path on `sample_points` points of the workload."""
-    import numpy as np
-
     from cuspatial_b200 import datagen as D
     from oracle import hostlib
 
@@ -475,7 +473,6 @@ def main():
     if args.workload == "nearest":
         return run_nearest(args)
 
-    import numpy as np
     import torch
 
     import cuspatial_b200 as cs

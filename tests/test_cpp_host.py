@@ -1,6 +1,5 @@
 """The C++ host layer (include/cuspatial_b200.hpp over the C ABI): a C++ program written like the
 reference's own gtest cases is built here (CPU) and run on the GPU box against the golden vectors."""
-import json
 import os
 import shutil
 import subprocess
