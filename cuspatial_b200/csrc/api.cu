@@ -79,7 +79,37 @@ std::atomic<int> g_profiling{0};
 thread_local stage_timer* t_timer = nullptr;
 std::mutex g_pool_mutex;
 bool g_pool_done[64] = {};
+constexpr int kMaxDevices = 64, kConfigSlots = 8;
+std::mutex g_config_mutex;
+std::atomic<bool> g_config_done[kConfigSlots][kMaxDevices];
+std::atomic<int> g_sm_count[kMaxDevices];
 }  // namespace
+
+int num_sms()
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  int n = g_sm_count[dev].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = 148;
+  }
+  g_sm_count[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+
+void configure_once_per_device(int slot, void (*configure)())
+{
+  int dev = 0;
+  BSJ_CUDA_TRY(cudaGetDevice(&dev));
+  bool const tracked = dev >= 0 && dev < kMaxDevices && slot >= 0 && slot < kConfigSlots;
+  if (tracked && g_config_done[slot][dev].load(std::memory_order_acquire)) return;
+  std::lock_guard<std::mutex> lk(g_config_mutex);
+  if (tracked && g_config_done[slot][dev].load(std::memory_order_relaxed)) return;
+  configure();  // untracked device ordinals are simply configured on every call
+  if (tracked) g_config_done[slot][dev].store(true, std::memory_order_release);
+}
 
 void ensure_pool_configured()
 {

@@ -219,8 +219,6 @@ int bits_for(u64 max_value)
   return b;
 }
 
-bool g_attr_set = false;
-
 template <typename T>
 void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32* length,
                  const u32* offset, u64 q, const void* bx0, const void* by0, const void* bx1,
@@ -228,15 +226,14 @@ void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32*
                  int max_depth, const bsj_allocator* mr, cudaStream_t s, bsj_pairs* out)
 {
   stage_timer tm(s);
-  if (!g_attr_set) {
+  configure_once_per_device(1, [] {  // per device, not per process
     BSJ_CUDA_TRY(cudaFuncSetAttribute(traverse_kernel<float>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kJoinWarps * kJoinStackCap * 4));
     BSJ_CUDA_TRY(cudaFuncSetAttribute(traverse_kernel<double>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kJoinWarps * kJoinStackCap * 4));
-    g_attr_set = true;
-  }
+  });
   dev_buf<uint4> nodes(q, s);
   dev_buf<join_state> st(1, s);
   BSJ_CUDA_TRY(cudaMemsetAsync(st.get(), 0, sizeof(join_state), s));
@@ -248,7 +245,7 @@ void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32*
   u64 capacity = std::max<u64>(1u << 20, n_boxes * 64);
   dev_buf<u32> hit_box, hit_node;
   join_state h{};
-  int const grid = (int)std::min<u64>((u64)kNumSMs * 3, (u64)div_up(n_boxes * 4, kJoinWarps));
+  int const grid = (int)std::min<u64>((u64)num_sms() * 3, (u64)div_up(n_boxes * 4, kJoinWarps));
   // seeding level k: at most 4^(k+1) level-k nodes per box; keep the queue below 2^24 entries
   int stop_level = n_boxes <= (1u << 16) ? 3 : n_boxes <= (1u << 18) ? 2 : 1;
   if (stop_level + 2 >= max_depth) stop_level = -1;  // shallow tree: one pass does it all
@@ -263,7 +260,7 @@ void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32*
       st.get(), nullptr, nullptr, stop_level, q_box.get(), q_node.get(), (u32)q_cap);
     BSJ_CHECK_LAUNCH();
     if (stop_level >= 0) {
-      traverse_kernel<T><<<kNumSMs * 3, kJoinWarps * 32, kJoinWarps * kJoinStackCap * 4, s>>>(
+      traverse_kernel<T><<<num_sms() * 3, kJoinWarps * 32, kJoinWarps * kJoinStackCap * 4, s>>>(
         nodes.get(), (const T*)bx0, (const T*)by0, (const T*)bx1, (const T*)by1, (u32)n_boxes,
         (T)x_min, (T)y_min, (T)scale, max_depth, hit_box.get(), hit_node.get(), (u32)capacity,
         st.get(), q_box.get(), q_node.get(), -1, nullptr, nullptr, (u32)q_cap);

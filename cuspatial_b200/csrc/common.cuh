@@ -22,7 +22,13 @@ using u64 = uint64_t;
 using i32 = int32_t;
 using i64 = int64_t;
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+// SM count of the current device (148 on a B200: 2 dies x 74 SMs), queried once per device.
+int num_sms();
+
+// One-time per-DEVICE kernel configuration (cudaFuncSetAttribute applies to the current device
+// only): runs `configure` the first time it is called with `slot` on each device, thread-safe.
+// Slots: 0 radix sort, 1 bbox join, 2 partition, 3 pip.
+void configure_once_per_device(int slot, void (*configure)());
 
 // ---------------------------------------------------------------------------------------------
 // Errors.  logic_error wording follows the reference (cpp/include/cuspatial/error.hpp:76-79):

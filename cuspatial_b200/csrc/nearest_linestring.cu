@@ -202,7 +202,7 @@ void nearest_t(const u32* pair_line, const u32* pair_quad, u64 n_pairs, const u3
   BSJ_CUDA_TRY(cudaMemsetAsync(out_point, 0, n_points * sizeof(u32), s));
   BSJ_CUDA_TRY(cudaMemsetAsync(out_line, 0, n_points * sizeof(u32), s));
   BSJ_CUDA_TRY(cudaMemsetAsync(out_dist, 0, n_points * sizeof(T), s));
-  int const grid = (int)std::min<u64>((u64)kNumSMs * 16, div_up(n_pairs * 32, (u64)kNlBlock));
+  int const grid = (int)std::min<u64>((u64)num_sms() * 16, div_up(n_pairs * 32, (u64)kNlBlock));
   nearest_linestring_kernel<T><<<std::max(grid, 1), kNlBlock, 0, s>>>(
     pair_line, pair_quad, n_pairs, length, offset, point_indices, (const T*)px, (const T*)py,
     n_points, line_offsets, (const T*)lx, (const T*)ly, out_point, out_line, (T*)out_dist);

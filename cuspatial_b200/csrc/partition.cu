@@ -240,16 +240,14 @@ void partition_t(const u32* keys, const void* x, const void* y, u64 n, u32 gid_b
   dev_buf<u32> ticket(1, s);
   BSJ_CUDA_TRY(cudaMemsetAsync(desc.get(), 0, desc.size() * sizeof(u64), s));
   BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
-  static bool attr_set = false;
-  if (!attr_set) {
+  configure_once_per_device(2, [] {  // per device, not per process
     BSJ_CUDA_TRY(cudaFuncSetAttribute(partition_kernel<float>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(part_smem<float>)));
     BSJ_CUDA_TRY(cudaFuncSetAttribute(partition_kernel<double>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(part_smem<double>)));
-    attr_set = true;
-  }
+  });
   partition_kernel<T><<<tiles, kPartBlock, sizeof(part_smem<T>), s>>>(
     keys, (const T*)x, (const T*)y, (u32)n, gid_base, sp, dst, desc.get(), ticket.get());
   BSJ_CHECK_LAUNCH();
@@ -272,7 +270,7 @@ void point_keys_histogram_impl(const void* x, const void* y, int dtype, u64 n, d
   if (bins) {
     BSJ_EXPECTS(hist_shift >= 0 && hist_shift < 32 && (0xFFFFFFFFull >> hist_shift) < n_bins,
                 "histogram does not cover the key range");
-    int const grid = (int)std::min<u64>((u64)kNumSMs * 2, (u64)div_up(n, 2048));
+    int const grid = (int)std::min<u64>((u64)num_sms() * 2, (u64)div_up(n, 2048));
     key_histogram_kernel<<<std::max(grid, 1), 512, 0, s>>>(keys, n, hist_shift, (u32)n_bins, bins);
     BSJ_CHECK_LAUNCH();
   }
@@ -290,7 +288,7 @@ void key_subhistogram_impl(const u32* keys, u64 n, int shift1, const u32* h_targ
   targets_t tg{};
   tg.n = n_targets;
   for (int t = 0; t < n_targets; ++t) tg.bin[t] = h_targets[t];
-  int const grid = (int)std::min<u64>((u64)kNumSMs * 2, (u64)div_up(n, 2048));
+  int const grid = (int)std::min<u64>((u64)num_sms() * 2, (u64)div_up(n, 2048));
   key_subhistogram_kernel<<<std::max(grid, 1), 512, (size_t)n_targets * n_sub * sizeof(u32), s>>>(
     keys, n, shift1, tg, shift2, n_sub, bins);
   BSJ_CHECK_LAUNCH();

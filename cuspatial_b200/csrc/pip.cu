@@ -1384,7 +1384,7 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
     dev_buf<u32> run_flag(n_runs + 1, s), run_list(n_runs + 1, s), run_count(1, s);
     BSJ_CUDA_TRY(cudaMemsetAsync(run_flag.get(), 0, (n_runs + 1) * sizeof(u32), s));
     BSJ_CUDA_TRY(cudaMemsetAsync(run_count.get(), 0, sizeof(u32), s));
-    int const cgrid = (int)std::min<u64>((u64)kNumSMs * 16, (u64)div_up(n_pairs * 32, 256));
+    int const cgrid = (int)std::min<u64>((u64)num_sms() * 16, (u64)div_up(n_pairs * 32, 256));
     pip_classify_kernel<T><<<std::max(cgrid, 1), 256, 0, s>>>(
       pair_poly, pair_quad, (u32)n_pairs, heads.get(), run_idx.get(), length, offset,
       (u32)num_nodes, (u32)n_points, meta.get(), n_poly, force_reference_mode(), node_key,
@@ -1393,7 +1393,7 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
     BSJ_CHECK_LAUNCH();
     prof_mark("pip_classify");
     if (force_reference_mode() == 0 && gi.valid && gi.sorted_keys) {
-      int const grid_dim = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_runs, kPipWarps));
+      int const grid_dim = (int)std::min<u64>((u64)num_sms() * 8, (u64)div_up(n_runs, kPipWarps));
       pip_eval_cells_kernel<T><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
         pair_poly, pair_quad, run_start.get(), run_list.get(), run_count.get(), length, offset,
         point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly,
@@ -1401,7 +1401,7 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
         ticket.get(), c->pair_class, ix, gi, gi.sorted_keys);
       BSJ_CHECK_LAUNCH();
     } else if (force_reference_mode() != 2) {  // 2: timing experiment, classification only
-      int const grid_dim = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_runs, kPipWarps));
+      int const grid_dim = (int)std::min<u64>((u64)num_sms() * 8, (u64)div_up(n_runs, kPipWarps));
       pip_eval_kernel<T><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
         pair_poly, pair_quad, run_start.get(), run_list.get(), run_count.get(), length, offset,
         point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly,
@@ -1422,7 +1422,7 @@ void expand_compact(const u32* pair_poly, const bsj_pip_compact* c, u32 position
                     u32* out_poly, u32* out_point, cudaStream_t s)
 {
   if (c->n_hits == 0 || c->n_pairs == 0) return;
-  int const grid_dim = (int)std::min<u64>((u64)kNumSMs * BSJ_EMIT_GRID_MULT, (u64)div_up(c->n_pairs * 32, 256));
+  int const grid_dim = (int)std::min<u64>((u64)num_sms() * BSJ_EMIT_GRID_MULT, (u64)div_up(c->n_pairs * 32, 256));
   pip_emit_kernel<<<std::max(grid_dim, 1), 256, 0, s>>>(
     pair_poly, c->pair_offset, c->pair_length, (u32)c->n_pairs, c->pair_word_base,
     c->pair_row_base, c->pair_hits, c->mask_words, c->pair_class, position_base, out_poly,
@@ -1443,7 +1443,7 @@ void pip_bitmask_t(const void* px, const void* py, u64 n_points, const u32* poly
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
   edge_index<T> ix = pidx.finish(s);
   prof_mark("polygon_index");
-  int const grid = (int)std::min<u64>((u64)kNumSMs * 16, (u64)div_up(n_points, 256));
+  int const grid = (int)std::min<u64>((u64)num_sms() * 16, (u64)div_up(n_points, 256));
   pip_bitmask_kernel<T><<<std::max(grid, 1), 256, 0, s>>>(
     (const T*)px, (const T*)py, n_points, pidx.meta.get(), n_poly, ring_offsets, (const T*)vx,
     (const T*)vy, out, force_reference_mode(), ix);
@@ -1576,7 +1576,7 @@ void pairwise_point_in_polygon_impl(const void* px, const void* py, int dtype, u
   if (n_points == 0) return;
   (void)n_ring_offsets;
   (void)n_verts;
-  int const grid = (int)std::min<u64>((u64)kNumSMs * 8, (u64)div_up(n_points * 32, 256));
+  int const grid = (int)std::min<u64>((u64)num_sms() * 8, (u64)div_up(n_points * 32, 256));
   // offsets are non-negative int32: reinterpreting as uint32 is value preserving
   if (dtype == BSJ_FLOAT32)
     pip_pairwise_kernel<float><<<std::max(grid, 1), 256, 0, s>>>(

@@ -493,7 +493,7 @@ void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_m
                                          (T)((1 << max_depth) + 2));
   u32 const oob_key = (u32)((1 << (2 * max_depth)) - 1);
   int const V       = 16 / sizeof(T);
-  int const nblk    = (int)std::min<u64>((u64)kNumSMs * 4, (u64)div_up(div_up(n, V), 512));
+  int const nblk    = (int)std::min<u64>((u64)num_sms() * 4, (u64)div_up(div_up(n, V), 512));
   auto launch = [&](auto pass_tag) {
     constexpr int P = decltype(pass_tag)::value;
     encode_hist_kernel<T, P><<<std::max(nblk, 1), 512, 0, s>>>(
@@ -616,7 +616,7 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
   for (int L = 0; L + 1 < d; ++L) {
     // level L holds at most min(cap, (2^(L+1)+3)^2) nodes; size the grid for that
     u64 const geo  = ((2ull << L) + 3) * ((2ull << L) + 3);
-    int const grid = (int)std::min<u64>((u64)kNumSMs * 8,
+    int const grid = (int)std::min<u64>((u64)num_sms() * 8,
                                         std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandBlock)));
     if (geo <= kWarpLevelNodes) {  // few, huge nodes: warp-cooperative child search
       int const wgrid = (int)std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandWarpNodes));

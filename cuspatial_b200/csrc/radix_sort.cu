@@ -1,6 +1,16 @@
 // radix_sort.cu -- onesweep LSD radix sort (u32 key, u32 value), sm_100a.  See radix_sort.cuh.
 #include "radix_sort.cuh"
 
+// Ranking scheme of the per-warp stable ranking (the shared-memory-pipe cost of the kernel):
+//   0  match word (atomicOr of the lane bit) packed next to the running count, one 64-bit entry
+//      per (warp, digit)                                       [round-1 form, kept for A/B runs]
+//   1  same, count and match word in separate 32-bit arrays (all 32 banks instead of 16 pairs)
+//   2  peers found with eight warp votes (no shared-memory traffic, no atomics); only the
+//      running count lives in shared memory (one 32-bit load + one leader store per round)
+#ifndef BSJ_SORT_RANK
+#define BSJ_SORT_RANK 2
+#endif
+
 namespace bsj {
 
 namespace {
@@ -10,12 +20,20 @@ constexpr int kWarps = kSortBlock / 32;
 // shared-memory layout of one onesweep CTA (dynamic)
 struct sort_smem {
   uint2 kv[kSortTile];  // tile-sorted {key, value} slots: one 64-bit store / load per element
+#if BSJ_SORT_RANK == 0
   // per-warp, per-digit {x: running count -> exclusive warp offset, y: match mask of the
   // current round}
   uint2 whist[kWarps * kRadixDigits];
+#else
+  u32 wcnt[kWarps * kRadixDigits];   // running count -> exclusive warp offset (+ bin start)
+#if BSJ_SORT_RANK == 1
+  u32 wmask[kWarps * kRadixDigits];  // match mask of the current round
+#endif
+#endif
   u32 bin_start[kRadixDigits];       // exclusive scan of the tile's digit totals
   u32 gbase[kRadixDigits];           // global destination of (digit, slot j): gbase[d] + j
   u32 warp_sums[kWarps];
+  u32 gsums[kWarps];
   u32 tile;
 };
 
@@ -40,30 +58,16 @@ __global__ void __launch_bounds__(512) histogram_kernel(const u32* __restrict__ 
     if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
 }
 
-// counts -> exclusive digit offsets, one 256-thread group per pass
-__global__ void __launch_bounds__(kMaxPasses * kRadixDigits) scan_hist_kernel(u32* hist)
-{
-  __shared__ u32 s_ws[kMaxPasses * 8];
-  int const t      = threadIdx.x;
-  u32 const c      = hist[t];
-  u32 const incl   = warp_inclusive_scan(c);
-  int const warp   = t >> 5;
-  if ((t & 31) == 31) s_ws[warp] = incl;
-  __syncthreads();
-  u32 base       = 0;
-  int const w0   = (warp >> 3) << 3;  // first warp of this pass's 256-thread group
-  for (int w = w0; w < warp; ++w) base += s_ws[w];
-  hist[t] = base + incl - c;
-}
-
 // ---------------------------------------------------------------------------------------------
 // one onesweep pass: rank -> look-back -> scatter
+// `digit_counts` are the RAW digit counts of this pass (the histogram row): every CTA turns them
+// into exclusive offsets itself (256 loads that hit L2), which removed the separate scan launch.
 // ---------------------------------------------------------------------------------------------
 template <bool IOTA>
 __global__ void __launch_bounds__(kSortBlock, BSJ_SORT_MINBLOCKS)
 onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in,
                 u32* __restrict__ keys_out, u32* __restrict__ vals_out, u32 n, int shift,
-                const u32* __restrict__ digit_offsets, u64* __restrict__ lookback,
+                const u32* __restrict__ digit_counts, u64* __restrict__ lookback,
                 u32* __restrict__ ticket, u32 tag_agg, u32 tag_pre)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -74,7 +78,16 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
   int const warp = tid >> 5;
 
   if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+#if BSJ_SORT_RANK == 0
   for (int i = tid; i < kWarps * kRadixDigits; i += kSortBlock) sm.whist[i] = make_uint2(0u, 0u);
+#else
+  for (int i = tid; i < kWarps * kRadixDigits; i += kSortBlock) {
+    sm.wcnt[i] = 0u;
+#if BSJ_SORT_RANK == 1
+    sm.wmask[i] = 0u;
+#endif
+  }
+#endif
   __syncthreads();
   u32 const tile      = sm.tile;
   u32 const tile_base = tile * (u32)kSortTile;
@@ -88,16 +101,21 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
     u32 const idx = warp_base + i * 32 + lane;
     key[i]        = idx < n ? ld_stream(keys_in + idx) : 0xFFFFFFFFu;
   }
+  // this pass's global digit count (turned into an exclusive offset below)
+  u32 gcount = 0;
+  if (tid < kRadixDigits) gcount = __ldg(digit_counts + tid);
 
-  // ---- per-warp stable ranking.  Lanes holding the same digit find each other through a
-  // shared-memory match word (atomicOr of the lane bit), which took the place of match.any (the
-  // top stall on B200) and of an 8-ballot vote (3x the instructions): the word sits next to the
-  // digit's running count, so ONE 64-bit load gives a lane both its peer mask and the count of
-  // earlier items; the lowest peer then bumps the count and clears the mask for the next round.
-  uint2* const wh = sm.whist + warp * kRadixDigits;
-  u32 const lt    = lanemask_lt();
-  u32 const mybit = 1u << lane;
+  // ---- per-warp stable ranking: rank[i] = number of keys with the same digit that precede
+  // item i inside this warp's 16 x 32 items
+  u32 const lt = lanemask_lt();
   unsigned short rank[kSortIPT];
+#if BSJ_SORT_RANK == 0
+  // Lanes holding the same digit find each other through a shared-memory match word (atomicOr of
+  // the lane bit): the word sits next to the digit's running count, so ONE 64-bit load gives a
+  // lane both its peer mask and the count of earlier items; the lowest peer then bumps the count
+  // and clears the mask for the next round.
+  uint2* const wh = sm.whist + warp * kRadixDigits;
+  u32 const mybit = 1u << lane;
 #pragma unroll
   for (int i = 0; i < kSortIPT; ++i) {
     u32 const d = (key[i] >> shift) & 0xFFu;
@@ -110,31 +128,89 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
     rank[i] = (unsigned short)(cm.x + __popc(below));
     __syncwarp();
   }
+#elif BSJ_SORT_RANK == 1
+  u32* const wc = sm.wcnt + warp * kRadixDigits;
+  u32* const wm = sm.wmask + warp * kRadixDigits;
+  u32 const mybit = 1u << lane;
+#pragma unroll
+  for (int i = 0; i < kSortIPT; ++i) {
+    u32 const d = (key[i] >> shift) & 0xFFu;
+    atomicOr(&wm[d], mybit);
+    __syncwarp();
+    u32 const peers = wm[d];
+    u32 const cnt   = wc[d];
+    __syncwarp();
+    u32 const below = peers & lt;
+    if (below == 0) {
+      wc[d] = cnt + __popc(peers);
+      wm[d] = 0u;
+    }
+    rank[i] = (unsigned short)(cnt + __popc(below));
+    __syncwarp();
+  }
+#else
+  // Peers by eight votes: after bit b the mask keeps the lanes whose digit agrees with mine on
+  // bits 0..b.  No shared-memory traffic and no atomics for the match; the running count costs
+  // one 32-bit load (peers read the same word: broadcast) and one store by the lowest peer.
+  u32* const wc = sm.wcnt + warp * kRadixDigits;
+#pragma unroll
+  for (int i = 0; i < kSortIPT; ++i) {
+    u32 const d = (key[i] >> shift) & 0xFFu;
+    u32 peers   = 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = 0; b < kRadixBits; ++b) {
+      bool const bit = (d >> b) & 1u;
+      u32 const m    = __ballot_sync(0xFFFFFFFFu, bit);
+      peers &= bit ? m : ~m;
+    }
+    u32 const below = peers & lt;
+    u32 const cnt   = wc[d];
+    __syncwarp();
+    if (below == 0) wc[d] = cnt + __popc(peers);
+    rank[i] = (unsigned short)(cnt + __popc(below));
+    __syncwarp();
+  }
+#endif
   __syncthreads();
 
-  // ---- digit totals over warps (thread d < 256 owns digit d), exclusive scan over digits
+  // ---- digit totals over warps (thread d < 256 owns digit d), exclusive scan over digits;
+  // the global digit counts are scanned in the same sweep
+#if BSJ_SORT_RANK == 0
+#define BSJ_WCNT(w, d) sm.whist[(w) * kRadixDigits + (d)].x
+#else
+#define BSJ_WCNT(w, d) sm.wcnt[(w) * kRadixDigits + (d)]
+#endif
   u32 total = 0;
   if (tid < kRadixDigits) {
     u32 sum = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
-      u32 const c                        = sm.whist[w * kRadixDigits + tid].x;
-      sm.whist[w * kRadixDigits + tid].x = sum;
+      u32 const c      = BSJ_WCNT(w, tid);
+      BSJ_WCNT(w, tid) = sum;
       sum += c;
     }
     total = sum;
   }
-  u32 const incl = warp_inclusive_scan(total);
-  if (lane == 31) sm.warp_sums[warp] = incl;
+  u32 const incl  = warp_inclusive_scan(total);
+  u32 const gincl = warp_inclusive_scan(gcount);
+  if (lane == 31) {
+    sm.warp_sums[warp] = incl;
+    sm.gsums[warp]     = gincl;
+  }
   __syncthreads();
   // The tile's digit totals are PUBLISHED before the in-tile permutation and the look-back is
   // resolved after it: successors see this tile's aggregate as early as possible and this tile
   // hides its own wait for its predecessors behind the shared-memory placement.
+  u32 goffset = 0;  // exclusive global offset of digit `tid`
   if (tid < kRadixDigits) {
     u64* const col = lookback + tid;
-    u32 base = 0;
-    for (int w = 0; w < warp; ++w) base += sm.warp_sums[w];
+    u32 base = 0, gb = 0;
+    for (int w = 0; w < warp; ++w) {
+      base += sm.warp_sums[w];
+      gb += sm.gsums[w];
+    }
     u32 const bin_start = base + incl - total;
+    goffset             = gb + gincl - gcount;
     sm.bin_start[tid]   = bin_start;
 
     // padding keys (0xFFFFFFFF) of the last tile land at the end of digit 255: not counted
@@ -148,7 +224,7 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
     // fold the digit's tile offset into every warp's offset: one random lookup per element
     // in the placement below instead of two
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) sm.whist[w * kRadixDigits + tid].x += bin_start;
+    for (int w = 0; w < kWarps; ++w) BSJ_WCNT(w, tid) += bin_start;
   }
   __syncthreads();
 
@@ -157,7 +233,7 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
 #pragma unroll
     for (int i = 0; i < kSortIPT; ++i) {
       u32 const d   = (key[i] >> shift) & 0xFFu;
-      u32 const pos = wh[d].x + rank[i];
+      u32 const pos = BSJ_WCNT(warp, d) + rank[i];
       sm.kv[pos]    = make_uint2(key[i], warp_base + i * 32 + lane);
     }
   } else {
@@ -170,10 +246,11 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
 #pragma unroll
     for (int i = 0; i < kSortIPT; ++i) {
       u32 const d   = (key[i] >> shift) & 0xFFu;
-      u32 const pos = wh[d].x + rank[i];
+      u32 const pos = BSJ_WCNT(warp, d) + rank[i];
       sm.kv[pos]    = make_uint2(key[i], v[i]);
     }
   }
+#undef BSJ_WCNT
 
   // ---- decoupled look-back on this digit's column of tile descriptors
   if (tid < kRadixDigits) {
@@ -196,7 +273,7 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
       }
       st_relaxed_u64(col + (u64)tile * kRadixDigits, lb_pack(tag_pre, excl + my_total));
     }
-    sm.gbase[tid] = digit_offsets[tid] + excl - sm.bin_start[tid];
+    sm.gbase[tid] = goffset + excl - sm.bin_start[tid];
   }
   __syncthreads();
 
@@ -213,17 +290,17 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
   }
 }
 
-bool g_attr_set = false;
+// cudaFuncSetAttribute applies to the current device only: configured once per device
 void set_kernel_attrs()
 {
-  if (g_attr_set) return;
-  BSJ_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<true>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(sort_smem)));
-  BSJ_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<false>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(sort_smem)));
-  g_attr_set = true;
+  configure_once_per_device(0, [] {
+    BSJ_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(sort_smem)));
+    BSJ_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(sort_smem)));
+  });
 }
 
 }  // namespace
@@ -247,7 +324,7 @@ void sort_histogram(const u32* keys, u64 n, int begin_bit, int end_bit, sort_wor
                     cudaStream_t s)
 {
   int const passes = passes_for_bits(begin_bit, end_bit);
-  int const grid   = (int)std::min<u64>((u64)kNumSMs * 4, (u64)div_up(n, 512));
+  int const grid   = (int)std::min<u64>((u64)num_sms() * 4, (u64)div_up(n, 512));
   histogram_kernel<<<grid, 512, 0, s>>>(keys, n, begin_bit, passes, ws.hist.get());
   BSJ_CHECK_LAUNCH();
 }
@@ -258,9 +335,6 @@ void sort_passes(u32* keys_a, u32* vals_a, bool iota_values, u32* keys_b, u32* v
 {
   set_kernel_attrs();
   int const passes = passes_for_bits(begin_bit, end_bit);
-  scan_hist_kernel<<<1, kMaxPasses * kRadixDigits, 0, s>>>(ws.hist.get());
-  BSJ_CHECK_LAUNCH();
-  prof_mark("scan_hist");
   bool in_a = true;
   for (int p = 0; p < passes; ++p) {
     u32* kin  = in_a ? keys_a : keys_b;

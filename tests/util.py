@@ -6,14 +6,38 @@ from cuspatial_b200 import datagen as D
 TREE_COLS = ("key", "level", "is_internal_node", "length", "offset")
 
 
+def in_contract(x, y, ext, scale, depth, dtype):
+    """Mask of the points whose cell index, computed the way the reference does in `dtype`
+    (phase_1.cuh:78-85: subtract, IEEE divide, truncate), stays below 2^depth -- the regime in
+    which the reference's tree construction is well defined.  Out-of-bbox points
+    (which take the fixed key 4^depth - 1) are in contract."""
+    T = dtype
+    x0, x1, y0, y1 = (T(v) for v in ext)
+    lo_x, hi_x, lo_y, hi_y = min(x0, x1), max(x0, x1), min(y0, y1), max(y0, y1)
+    s = max(T(scale), max(hi_x - lo_x, hi_y - lo_y) / T((1 << depth) + 2))
+    inside = ~((x < lo_x) | (x > hi_x) | (y < lo_y) | (y > hi_y))
+    with np.errstate(invalid="ignore"):
+        ix = np.nan_to_num(((x - lo_x) / s).astype(T), nan=0.0)
+        iy = np.nan_to_num(((y - lo_y) / s).astype(T), nan=0.0)
+    lim = T(1 << depth)
+    return ~inside | ((ix < lim) & (iy < lim))
+
+
 def make_case(n, n_poly, depth, kind="u", dtype=np.float64, seed=0, median_vertices=40,
-              oob=0, dups=0):
+              oob=0, dups=0, extent=None):
+    """`extent` = (x0, x1, y0, y1) places polygons and points there (default: the unit square);
+    points that the cast to `dtype` pushes out of the reference's well-defined key range are
+    dropped (only happens for coordinates far from the origin in float32)."""
     po, ro, vx, vy = D.taxi_zone_like_polygons(n_poly, seed=seed + 11, dtype=dtype,
-                                               median_vertices=median_vertices)
+                                               median_vertices=median_vertices,
+                                               **({"extent": extent} if extent else {}))
     ext = D.polygon_extent(vx, vy)
     scale = D.quadtree_params(ext, depth)
     gen = D.uniform_points if kind == "u" else D.clustered_points
     x, y = gen(n, ext, seed=seed + 5, dtype=dtype)
+    if extent is not None:
+        keep = in_contract(x, y, ext, scale, depth, dtype)
+        x, y = x[keep], y[keep]
     if oob:
         x[:oob] = dtype(ext[1] + (ext[1] - ext[0]))  # outside the area of interest
     if dups:
