@@ -8,7 +8,7 @@
 //   2  peers found with eight warp votes (no shared-memory traffic, no atomics); only the
 //      running count lives in shared memory (one 32-bit load + one leader store per round)
 #ifndef BSJ_SORT_RANK
-#define BSJ_SORT_RANK 2
+#define BSJ_SORT_RANK 1
 #endif
 
 namespace bsj {
