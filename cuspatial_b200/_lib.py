@@ -46,6 +46,30 @@ class bsj_pip_compact(C.Structure):
     ]
 
 
+BSJ_MAX_RANKS = 32
+
+
+class bsj_shard_plan(C.Structure):
+    """Mirror of the device-resident sharding plan (include/cuspatial_b200.h)."""
+    _fields_ = [
+        ("n_ranks", C.c_uint32), ("rank", C.c_uint32), ("hist_shift", C.c_uint32),
+        ("sub_shift", C.c_uint32), ("n_sub", C.c_uint32), ("n_targets", C.c_uint32),
+        ("status", C.c_uint32), ("reserved", C.c_uint32),
+        ("gid_base", C.c_uint32 * (BSJ_MAX_RANKS + 1)),
+        ("bound_bin", C.c_uint32 * BSJ_MAX_RANKS), ("bound_missing", C.c_uint32 * BSJ_MAX_RANKS),
+        ("target_bin", C.c_uint32 * BSJ_MAX_RANKS), ("splitter", C.c_uint32 * BSJ_MAX_RANKS),
+        ("send_count", C.c_uint32 * BSJ_MAX_RANKS), ("send_offset", C.c_uint32 * BSJ_MAX_RANKS),
+        ("recv_total", C.c_uint32 * BSJ_MAX_RANKS),
+    ]
+
+
+class bsj_coord_segments(C.Structure):
+    _fields_ = [
+        ("n_segments", C.c_int32), ("first_id", C.c_uint32 * (BSJ_MAX_RANKS + 1)),
+        ("x", C.c_void_p * BSJ_MAX_RANKS), ("y", C.c_void_p * BSJ_MAX_RANKS),
+    ]
+
+
 class bsj_pairs(C.Structure):
     _fields_ = [("first", C.c_void_p), ("second", C.c_void_p), ("size", C.c_uint64)]
 
@@ -57,7 +81,9 @@ EXPORTED_SYMBOLS = [
     "bsj_expand_pip_compact", "bsj_point_in_polygon", "bsj_pairwise_point_in_polygon",
     "bsj_polygon_bounding_boxes", "bsj_quadtree_point_to_nearest_linestring",
     "bsj_linestring_bounding_boxes",
-    "bsj_point_keys_histogram", "bsj_key_subhistogram", "bsj_partition_points", "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
+    "bsj_point_keys_histogram", "bsj_shard_plan_level1", "bsj_shard_subhistogram",
+    "bsj_shard_plan_level2", "bsj_shard_plan_finalize", "bsj_partition_keys",
+    "bsj_quadtree_on_keys", "bsj_quadtree_point_in_polygon_compact_seg", "bsj_free", "bsj_free_quadtree", "bsj_free_pairs", "bsj_last_error", "bsj_version",
     "bsj_kernel_launch_count", "bsj_set_profiling", "bsj_get_profile",
 ]
 
@@ -105,10 +131,19 @@ def lib():
     L.bsj_polygon_bounding_boxes.argtypes = [vp, u64, vp, u64, vp, vp, C.c_int, u64, dbl, vp,
                                              vp, vp, vp, vp]
     L.bsj_point_keys_histogram.argtypes = [vp, vp, C.c_int, u64, dbl, dbl, dbl, dbl, dbl, C.c_int8,
-                                           C.c_int, vp, vp, u64, vp]
-    L.bsj_key_subhistogram.argtypes = [vp, u64, C.c_int, vp, C.c_int, C.c_int, C.c_uint32, vp, vp]
-    L.bsj_partition_points.argtypes = [vp, vp, vp, C.c_int, u64, C.c_uint32, vp, C.c_int, vp, vp,
-                                       vp, vp]
+                                           C.c_int, vp, vp, u64, vp, vp]
+    L.bsj_shard_plan_level1.argtypes = [vp, u64, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_uint32, vp, vp]
+    L.bsj_shard_subhistogram.argtypes = [vp, u64, vp, C.c_int, C.c_uint32, vp, vp]
+    L.bsj_shard_plan_level2.argtypes = [vp, u64, vp, vp, vp, vp]
+    L.bsj_shard_plan_finalize.argtypes = [vp, u64, vp, vp]
+    L.bsj_partition_keys.argtypes = [vp, u64, vp, C.c_int, vp, vp, C.c_int, vp]
+    L.bsj_quadtree_on_keys.argtypes = [vp, vp, u64, C.POINTER(bsj_grid), i32,
+                                       C.POINTER(bsj_allocator), vp, C.POINTER(bsj_quadtree)]
+    L.bsj_quadtree_point_in_polygon_compact_seg.argtypes = [
+        vp, vp, u64, vp, vp, vp, vp, vp, u64, vp, C.POINTER(bsj_coord_segments), C.c_int, u64, vp,
+        u64, vp, u64, vp, vp, u64, C.POINTER(bsj_grid), C.POINTER(bsj_allocator), vp,
+        C.POINTER(bsj_pip_compact)]
     L.bsj_free.argtypes = [vp, vp]
     L.bsj_last_error.restype = C.c_char_p
     L.bsj_version.restype = C.c_char_p

@@ -36,8 +36,8 @@ void quadtree_point_in_polygon_compact_impl(
   const u8* internal, const u32* length, const u32* offset, u64 num_nodes,
   const u32* point_indices, const void* px, const void* py, int dtype, u64 n_points,
   const u32* poly_offsets, u64 n_poly_offsets, const u32* ring_offsets, u64 n_ring_offsets,
-  const void* vx, const void* vy, u64 n_verts, const bsj_grid* grid, const bsj_allocator* mr,
-  cudaStream_t s, bsj_pip_compact* c);
+  const void* vx, const void* vy, u64 n_verts, const bsj_grid* grid,
+  const bsj_coord_segments* segs, const bsj_allocator* mr, cudaStream_t s, bsj_pip_compact* c);
 void expand_pip_compact_impl(const u32* pair_poly, const bsj_pip_compact* c, u32 position_base,
                              u32* out_poly, u32* out_point, cudaStream_t s);
 void point_in_polygon_impl(const void* px, const void* py, int dtype, u64 n_points,
@@ -64,13 +64,21 @@ void polygon_bounding_boxes_impl(const u32* poly_offsets, u64 n_poly_offsets,
 void point_keys_histogram_impl(const void* x, const void* y, int dtype, u64 n, double x_min,
                                double x_max, double y_min, double y_max, double scale,
                                int max_depth, int hist_shift, u32* keys, u32* bins, u64 n_bins,
-                               cudaStream_t s);
-void key_subhistogram_impl(const u32* keys, u64 n, int shift1, const u32* h_targets, int n_targets,
-                           int shift2, u32 n_sub, u32* bins, cudaStream_t s);
-void partition_points_impl(const u32* keys, const void* x, const void* y, int dtype, u64 n,
-                           u32 gid_base, const u32* h_splitters, int n_ranks,
-                           void* const* dst_x, void* const* dst_y, u32* const* dst_gid,
-                           cudaStream_t s);
+                               u32* point_flags, cudaStream_t s);
+void shard_plan_level1_impl(const u32* global_hist, u64 n_bins, const u32* h_rank_sizes,
+                            int n_ranks, int rank, int hist_shift, int sub_shift, u32 n_sub,
+                            bsj_shard_plan* plan, cudaStream_t s);
+void shard_subhistogram_impl(const u32* keys, u64 n, const bsj_shard_plan* plan, int n_ranks,
+                             u32 n_sub, u32* bins, cudaStream_t s);
+void shard_plan_level2_impl(const u32* local_hist, u64 n_bins, const u32* local_sub,
+                            const u32* global_sub, bsj_shard_plan* plan, cudaStream_t s);
+void shard_plan_finalize_impl(const u32* counts_matrix, u64 capacity, bsj_shard_plan* plan,
+                              cudaStream_t s);
+void partition_keys_impl(const u32* keys, u64 n, const bsj_shard_plan* plan, int n_ranks,
+                         u32* const* dst_key, u32* const* dst_gid, int use_bulk_copy,
+                         cudaStream_t s);
+void quadtree_on_keys_impl(u32* keys, u32* values, u64 n, const bsj_grid* g, int max_size,
+                           const bsj_allocator* mr, cudaStream_t s, bsj_quadtree* out);
 
 namespace {
 thread_local std::string t_err;
@@ -317,7 +325,35 @@ int bsj_quadtree_point_in_polygon_compact(
     quadtree_point_in_polygon_compact_impl(
       pair_poly, pair_quad, n_pairs, key, level, is_internal_node, length, offset, num_nodes,
       point_indices, point_x, point_y, dtype, n_points, poly_offsets, n_poly_offsets,
-      ring_offsets, n_ring_offsets, poly_points_x, poly_points_y, n_poly_points, grid, mr,
+      ring_offsets, n_ring_offsets, poly_points_x, poly_points_y, n_poly_points, grid, nullptr, mr,
+      (cudaStream_t)stream, out);
+  });
+}
+
+int bsj_quadtree_point_in_polygon_compact_seg(
+  const uint32_t* pair_poly, const uint32_t* pair_quad, uint64_t n_pairs, const uint32_t* key,
+  const uint8_t* level, const uint8_t* is_internal_node, const uint32_t* length,
+  const uint32_t* offset, uint64_t num_nodes, const uint32_t* point_indices,
+  const bsj_coord_segments* segments, int dtype, uint64_t n_points, const uint32_t* poly_offsets,
+  uint64_t n_poly_offsets, const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+  const void* poly_points_x, const void* poly_points_y, uint64_t n_poly_points,
+  const bsj_grid* grid, const bsj_allocator* mr, bsj_stream_t stream, bsj_pip_compact* out)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
+    *out = bsj_pip_compact{};
+    check_dtype(dtype);
+    BSJ_EXPECTS(n_pairs == 0 || (pair_poly && pair_quad),
+                "a quadrant-polygon table must have 2 columns");
+    BSJ_EXPECTS(num_nodes == 0 || (length && offset), "a quadtree table must have 5 columns");
+    BSJ_EXPECTS(segments != nullptr && segments->n_segments >= 1 &&
+                  segments->n_segments <= BSJ_MAX_RANKS,
+                "coordinate segments must be given");
+    BSJ_EXPECTS(n_points == 0 || point_indices, "point indices must not be NULL");
+    quadtree_point_in_polygon_compact_impl(
+      pair_poly, pair_quad, n_pairs, key, level, is_internal_node, length, offset, num_nodes,
+      point_indices, nullptr, nullptr, dtype, n_points, poly_offsets, n_poly_offsets, ring_offsets,
+      n_ring_offsets, poly_points_x, poly_points_y, n_poly_points, grid, segments, mr,
       (cudaStream_t)stream, out);
   });
 }
@@ -440,37 +476,77 @@ int bsj_polygon_bounding_boxes(const uint32_t* poly_offsets, uint64_t n_poly_off
 int bsj_point_keys_histogram(const void* x, const void* y, int dtype, uint64_t n, double x_min,
                              double x_max, double y_min, double y_max, double scale,
                              int8_t max_depth, int hist_shift, uint32_t* keys, uint32_t* bins,
-                             uint64_t n_bins, bsj_stream_t stream)
+                             uint64_t n_bins, uint32_t* point_flags, bsj_stream_t stream)
 {
   return guarded([&] {
     check_dtype(dtype);
     BSJ_EXPECTS(n == 0 || (x && y && keys), "x and y columns must have the same length");
     point_keys_histogram_impl(x, y, dtype, n, x_min, x_max, y_min, y_max, scale, max_depth,
-                              hist_shift, keys, bins, n_bins, (cudaStream_t)stream);
+                              hist_shift, keys, bins, n_bins, point_flags, (cudaStream_t)stream);
   });
 }
 
-int bsj_key_subhistogram(const uint32_t* keys, uint64_t n, int shift1,
-                         const uint32_t* host_target_bins, int n_targets, int shift2,
-                         uint32_t n_sub, uint32_t* bins, bsj_stream_t stream)
+int bsj_shard_plan_level1(const uint32_t* global_hist, uint64_t n_bins,
+                          const uint32_t* host_rank_sizes, int n_ranks, int rank, int hist_shift,
+                          int sub_shift, uint32_t n_sub, bsj_shard_plan* plan, bsj_stream_t stream)
 {
   return guarded([&] {
-    BSJ_EXPECTS(n == 0 || (keys && bins), "keys and bins must not be NULL");
-    key_subhistogram_impl(keys, n, shift1, host_target_bins, n_targets, shift2, n_sub, bins,
-                          (cudaStream_t)stream);
+    BSJ_EXPECTS(global_hist && host_rank_sizes && plan, "plan inputs must not be NULL");
+    shard_plan_level1_impl(global_hist, n_bins, host_rank_sizes, n_ranks, rank, hist_shift,
+                           sub_shift, n_sub, plan, (cudaStream_t)stream);
   });
 }
 
-int bsj_partition_points(const uint32_t* keys, const void* x, const void* y, int dtype, uint64_t n,
-                         uint32_t gid_base, const uint32_t* host_splitters, int n_ranks,
-                         void* const* dst_x, void* const* dst_y, uint32_t* const* dst_gid,
-                         bsj_stream_t stream)
+int bsj_shard_subhistogram(const uint32_t* keys, uint64_t n, const bsj_shard_plan* plan,
+                           int n_ranks, uint32_t n_sub, uint32_t* bins, bsj_stream_t stream)
 {
   return guarded([&] {
-    check_dtype(dtype);
-    BSJ_EXPECTS(dst_x && dst_y && dst_gid, "destination pointer tables must not be NULL");
-    partition_points_impl(keys, x, y, dtype, n, gid_base, host_splitters, n_ranks, dst_x, dst_y,
-                          dst_gid, (cudaStream_t)stream);
+    BSJ_EXPECTS(n == 0 || (keys && bins && plan), "keys, bins and plan must not be NULL");
+    BSJ_EXPECTS(n_ranks >= 1 && n_ranks <= BSJ_MAX_RANKS && n_sub >= 1 &&
+                  (uint64_t)(n_ranks > 1 ? n_ranks - 1 : 1) * n_sub <= 12288,
+                "sub-histogram does not fit shared memory");
+    shard_subhistogram_impl(keys, n, plan, n_ranks, n_sub, bins, (cudaStream_t)stream);
+  });
+}
+
+int bsj_shard_plan_level2(const uint32_t* local_hist, uint64_t n_bins, const uint32_t* local_sub,
+                          const uint32_t* global_sub, bsj_shard_plan* plan, bsj_stream_t stream)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(local_hist && local_sub && global_sub && plan, "plan inputs must not be NULL");
+    shard_plan_level2_impl(local_hist, n_bins, local_sub, global_sub, plan, (cudaStream_t)stream);
+  });
+}
+
+int bsj_shard_plan_finalize(const uint32_t* counts_matrix, uint64_t capacity, bsj_shard_plan* plan,
+                            bsj_stream_t stream)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(counts_matrix && plan, "plan inputs must not be NULL");
+    shard_plan_finalize_impl(counts_matrix, capacity, plan, (cudaStream_t)stream);
+  });
+}
+
+int bsj_partition_keys(const uint32_t* keys, uint64_t n, const bsj_shard_plan* plan, int n_ranks,
+                       uint32_t* const* dst_key, uint32_t* const* dst_gid, int use_bulk_copy,
+                       bsj_stream_t stream)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(plan && dst_key && dst_gid, "destination pointer tables must not be NULL");
+    partition_keys_impl(keys, n, plan, n_ranks, dst_key, dst_gid, use_bulk_copy,
+                        (cudaStream_t)stream);
+  });
+}
+
+int bsj_quadtree_on_keys(uint32_t* keys, uint32_t* values, uint64_t n, const bsj_grid* grid,
+                         int32_t max_size, const bsj_allocator* mr, bsj_stream_t stream,
+                         bsj_quadtree* out)
+{
+  return guarded([&] {
+    BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
+    *out = bsj_quadtree{};
+    BSJ_EXPECTS(n == 0 || (keys && values), "keys and values must not be NULL");
+    quadtree_on_keys_impl(keys, values, n, grid, max_size, mr, (cudaStream_t)stream, out);
   });
 }
 

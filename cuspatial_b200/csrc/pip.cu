@@ -314,6 +314,35 @@ struct edge_index {  // device view of the per-call polygon edge index
   const u32* vert_edges;
 };
 
+// Where the coordinates of point `id` live.  Single GPU: two columns.  Multi-GPU: the points of a
+// key range stay on the ranks that own them and only (key, id) pairs were exchanged; `id` is then
+// a GLOBAL id and the coordinates are read from the owning rank's columns through peer pointers
+// (NVLink) -- only for the few points that need the exact predicate.
+template <typename T>
+struct coord_source {
+  const T* x;
+  const T* y;
+  u32 n_ids;   // ids are valid below this
+  int n_seg;   // 0: x/y above; otherwise ids first_id[s] .. first_id[s+1]-1 live in segment s
+  u32 first_id[BSJ_MAX_RANKS + 1];
+  const T* sx[BSJ_MAX_RANKS];
+  const T* sy[BSJ_MAX_RANKS];
+
+  __device__ __forceinline__ void load(u32 id, T& ox, T& oy) const
+  {
+    if (n_seg == 0) {
+      ox = __ldg(x + id);
+      oy = __ldg(y + id);
+    } else {
+      int sgm = 0;
+      while (sgm + 1 < n_seg && id >= first_id[sgm + 1]) ++sgm;
+      u32 const j = id - first_id[sgm];
+      ox = sx[sgm][j];
+      oy = sy[sgm][j];
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Whole-quadrant classification from the cell rectangle (optional bsj_grid hint).
 //
@@ -498,7 +527,7 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
                 const u32* __restrict__ run_start, const u32* __restrict__ run_list,
                 const u32* __restrict__ run_count, const u32* __restrict__ length,
                 const u32* __restrict__ offset, const u32* __restrict__ point_indices,
-                u32 n_points, const T* __restrict__ px, const T* __restrict__ py,
+                u32 n_points, coord_source<T> const pts,
                 const poly_meta<T>* __restrict__ meta, u32 n_poly,
                 const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
                 const T* __restrict__ vy, const u64* __restrict__ wbase,
@@ -533,10 +562,11 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
       T x[kPPL], y[kPPL];
 #pragma unroll
       for (int i = 0; i < kPPL; ++i) {
-        bool const ok = idx[i] < n_points;
+        bool const ok = idx[i] < pts.n_ids;
         if (!ok) valid &= ~(1u << i);
-        x[i] = ok ? __ldg(px + idx[i]) : (T)0;
-        y[i] = ok ? __ldg(py + idx[i]) : (T)0;
+        x[i] = (T)0;
+        y[i] = (T)0;
+        if (ok) pts.load(idx[i], x[i], y[i]);
       }
       // invalid slots mirror the tile's first point so they neither widen the bbox nor trap
       T const fx = __shfl_sync(0xffffffffu, x[0], 0), fy = __shfl_sync(0xffffffffu, y[0], 0);
@@ -711,7 +741,7 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                       const u32* __restrict__ run_start, const u32* __restrict__ run_list,
                       const u32* __restrict__ run_count, const u32* __restrict__ length,
                       const u32* __restrict__ offset, const u32* __restrict__ point_indices,
-                      u32 n_points, const T* __restrict__ px, const T* __restrict__ py,
+                      u32 n_points, coord_source<T> const pts,
                       const poly_meta<T>* __restrict__ meta, u32 n_poly,
                       const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
                       const T* __restrict__ vy, const u64* __restrict__ wbase,
@@ -773,9 +803,8 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
         for (int i = 0; i < kCellPPL; ++i)
           if ((want >> i) & 1u) {
             u32 const id = __ldg(point_indices + off + base + i * 32 + lane);
-            if (id < n_points) {
-              xr[i] = __ldg(px + id);
-              yr[i] = __ldg(py + id);
+            if (id < pts.n_ids) {
+              pts.load(id, xr[i], yr[i]);
               if (!(comfy(xr[i]) && comfy(yr[i]))) unsafe_pt |= 1u << i;
             } else {
               valid &= ~(1u << i);
@@ -1314,9 +1343,25 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
                     const void* py, u64 n_points, const u32* poly_offsets, u64 n_poly_offsets,
                     const u32* ring_offsets, u64 n_ring_offsets, const void* vx, const void* vy,
                     u64 n_verts, const u32* node_key, const u8* node_level, const bsj_grid* grid,
-                    out_alloc& oa, cudaStream_t s, bsj_pip_compact* c)
+                    const bsj_coord_segments* segs, out_alloc& oa, cudaStream_t s,
+                    bsj_pip_compact* c)
 {
   u32 const n_poly = (u32)(n_poly_offsets - 1);
+  coord_source<T> pts{};
+  pts.x = (const T*)px;
+  pts.y = (const T*)py;
+  pts.n_ids = (u32)n_points;
+  if (segs && segs->n_segments > 0) {
+    BSJ_EXPECTS(segs->n_segments <= BSJ_MAX_RANKS, "too many coordinate segments");
+    pts.n_seg = segs->n_segments;
+    for (int i = 0; i < segs->n_segments; ++i) {
+      pts.first_id[i] = segs->first_id[i];
+      pts.sx[i]       = (const T*)segs->x[i];
+      pts.sy[i]       = (const T*)segs->y[i];
+    }
+    pts.first_id[segs->n_segments] = segs->first_id[segs->n_segments];
+    pts.n_ids                      = segs->first_id[segs->n_segments];
+  }
   grid_info gi{};
   {
     static int no_grid = -1;
@@ -1396,7 +1441,7 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
       int const grid_dim = (int)std::min<u64>((u64)num_sms() * 8, (u64)div_up(n_runs, kPipWarps));
       pip_eval_cells_kernel<T><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
         pair_poly, pair_quad, run_start.get(), run_list.get(), run_count.get(), length, offset,
-        point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly,
+        point_indices, (u32)n_points, pts, meta.get(), n_poly,
         ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words, c->pair_hits,
         ticket.get(), c->pair_class, ix, gi, gi.sorted_keys);
       BSJ_CHECK_LAUNCH();
@@ -1404,7 +1449,7 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
       int const grid_dim = (int)std::min<u64>((u64)num_sms() * 8, (u64)div_up(n_runs, kPipWarps));
       pip_eval_kernel<T><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
         pair_poly, pair_quad, run_start.get(), run_list.get(), run_count.get(), length, offset,
-        point_indices, (u32)n_points, (const T*)px, (const T*)py, meta.get(), n_poly,
+        point_indices, (u32)n_points, pts, meta.get(), n_poly,
         ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words, c->pair_hits,
         ticket.get(), force_reference_mode(), c->pair_class, ix);
       BSJ_CHECK_LAUNCH();
@@ -1474,8 +1519,8 @@ void quadtree_point_in_polygon_compact_impl(
   const u8* internal, const u32* length, const u32* offset, u64 num_nodes,
   const u32* point_indices, const void* px, const void* py, int dtype, u64 n_points,
   const u32* poly_offsets, u64 n_poly_offsets, const u32* ring_offsets, u64 n_ring_offsets,
-  const void* vx, const void* vy, u64 n_verts, const bsj_grid* grid, const bsj_allocator* mr,
-  cudaStream_t s, bsj_pip_compact* c)
+  const void* vx, const void* vy, u64 n_verts, const bsj_grid* grid,
+  const bsj_coord_segments* segs, const bsj_allocator* mr, cudaStream_t s, bsj_pip_compact* c)
 {
   (void)internal;
   *c = bsj_pip_compact{};
@@ -1489,12 +1534,12 @@ void quadtree_point_in_polygon_compact_impl(
   if (dtype == BSJ_FLOAT32)
     qpip_compact_t<float>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes, point_indices,
                           px, py, n_points, poly_offsets, n_poly_offsets, ring_offsets,
-                          n_ring_offsets, vx, vy, n_verts, key, level, grid, oa, s, c);
+                          n_ring_offsets, vx, vy, n_verts, key, level, grid, segs, oa, s, c);
   else
     qpip_compact_t<double>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes,
                            point_indices, px, py, n_points, poly_offsets, n_poly_offsets,
-                           ring_offsets, n_ring_offsets, vx, vy, n_verts, key, level, grid, oa, s,
-                           c);
+                           ring_offsets, n_ring_offsets, vx, vy, n_verts, key, level, grid, segs,
+                           oa, s, c);
   tm.finish();
   oa.commit();
 }
@@ -1530,12 +1575,13 @@ void quadtree_point_in_polygon_impl(const u32* pair_poly, const u32* pair_quad, 
   if (dtype == BSJ_FLOAT32)
     qpip_compact_t<float>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes, point_indices,
                           px, py, n_points, poly_offsets, n_poly_offsets, ring_offsets,
-                          n_ring_offsets, vx, vy, n_verts, key, level, grid, scratch, s, &c);
+                          n_ring_offsets, vx, vy, n_verts, key, level, grid, nullptr, scratch, s,
+                          &c);
   else
     qpip_compact_t<double>(pair_poly, pair_quad, n_pairs, length, offset, num_nodes,
                            point_indices, px, py, n_points, poly_offsets, n_poly_offsets,
                            ring_offsets, n_ring_offsets, vx, vy, n_verts, key, level, grid,
-                           scratch, s, &c);
+                           nullptr, scratch, s, &c);
   out_alloc oa(mr, s);
   out->size = c.n_hits;
   if (c.n_hits) {

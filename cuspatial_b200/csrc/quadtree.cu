@@ -517,21 +517,113 @@ void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_m
 }  // namespace
 
 // Keys only (no histograms): used by the multi-GPU partitioner (partition.cu).
+// `point_flags` (device, may be NULL): bit 0 is OR-ed in when a point lies outside the box, bit 1
+// when a coordinate is NaN.
 template <typename T>
 void launch_point_keys(const void* x, const void* y, u64 n, double x_min, double x_max,
                        double y_min, double y_max, double scale, int max_depth, u32* keys,
-                       cudaStream_t s)
+                       u32* point_flags, cudaStream_t s)
 {
-  dev_buf<u32> flags(1, s);
-  BSJ_CUDA_TRY(cudaMemsetAsync(flags.get(), 0, sizeof(u32), s));
+  dev_buf<u32> flags;
+  if (!point_flags) {
+    flags.alloc(1, s);
+    BSJ_CUDA_TRY(cudaMemsetAsync(flags.get(), 0, sizeof(u32), s));
+    point_flags = flags.get();
+  }
   bsj_grid g{};
   launch_encode<T>(x, y, n, x_min, x_max, y_min, y_max, scale, max_depth, /*passes=*/0, keys,
-                   nullptr, flags.get(), &g, s);
+                   nullptr, point_flags, &g, s);
 }
 template void launch_point_keys<float>(const void*, const void*, u64, double, double, double,
-                                       double, double, int, u32*, cudaStream_t);
+                                       double, double, int, u32*, u32*, cudaStream_t);
 template void launch_point_keys<double>(const void*, const void*, u64, double, double, double,
-                                        double, double, int, u32*, cudaStream_t);
+                                        double, double, int, u32*, u32*, cudaStream_t);
+
+namespace {
+// Tree rows from the sorted keys, then the exact-size copy-out.  `st->point_flags` carries the
+// out-of-box / NaN flags of the encode (or of the caller, quadtree_on_keys).
+void finish_tree(const u32* sorted_keys, u32* out_keys, u32* out_idx, u64 n, int d, u32 max_size,
+                 tree_state* st_dev, bsj_grid grid, out_alloc& oa, stage_timer& tm, cudaStream_t s,
+                 bsj_quadtree* out)
+{
+  // ---- tree rows. Capacity: every node below level 0 has a parent with > max_size points, so a
+  // level holds at most 4*floor(N/(max_size+1)) nodes, and never more than N or (2^(L+1)+3)^2
+  // cells (cell indices reach 2^d + 2 under the reference's scale clamp, SURVEY.md A.1).
+  u64 cap = 64;
+  {
+    u64 const per_level = std::min<u64>(n, 4 * (n / ((u64)max_size + 1)));
+    for (int L = 1; L < d; ++L) {
+      u64 const side = (2ull << L) + 3;
+      cap += std::min(per_level, side * side);
+    }
+  }
+  dev_buf<u32> tkey(cap, s), tlen(cap, s), toff(cap, s);
+  dev_buf<u8> tlevel(cap, s), tint(cap, s);
+  // one look-back descriptor per tile of the largest level: 256-node tiles in the thread kernel,
+  // 8-node tiles in the warp kernel (which only runs on levels with <= kWarpLevelNodes nodes)
+  u32 const max_tiles = (u32)std::max<u64>(div_up(cap, kExpandBlock),
+                                           div_up(std::min<u64>(cap, kWarpLevelNodes), kExpandWarpNodes)) + 1;
+  dev_buf<u64> lb(max_tiles, s);
+  dev_buf<u32> tickets(16, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(lb.get(), 0, max_tiles * sizeof(u64), s));
+  BSJ_CUDA_TRY(cudaMemsetAsync(tickets.get(), 0, 16 * sizeof(u32), s));
+
+  int const shift0 = d >= 1 ? 2 * (d - 1) : 0;
+  level0_kernel<<<1, 32, 0, s>>>(sorted_keys, (u32)n, shift0, (u32)cap, tkey.get(), tlevel.get(),
+                                 tint.get(), tlen.get(), toff.get(), st_dev);
+  BSJ_CHECK_LAUNCH();
+  for (int L = 0; L + 1 < d; ++L) {
+    // level L holds at most min(cap, (2^(L+1)+3)^2) nodes; size the grid for that
+    u64 const geo  = ((2ull << L) + 3) * ((2ull << L) + 3);
+    int const grid = (int)std::min<u64>((u64)num_sms() * 8,
+                                        std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandBlock)));
+    if (geo <= kWarpLevelNodes) {  // few, huge nodes: warp-cooperative child search
+      int const wgrid = (int)std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandWarpNodes));
+      expand_level_warp_kernel<<<wgrid, kExpandBlock, 0, s>>>(
+        sorted_keys, L, d, max_size, (u32)cap, tkey.get(), tlevel.get(), tint.get(), tlen.get(),
+        toff.get(), st_dev, lb.get(), tickets.get() + L);
+    } else {
+      expand_level_kernel<<<grid, kExpandBlock, 0, s>>>(
+        sorted_keys, L, d, max_size, (u32)cap, tkey.get(), tlevel.get(), tint.get(), tlen.get(),
+        toff.get(), st_dev, lb.get(), tickets.get() + L, nullptr);
+    }
+    BSJ_CHECK_LAUNCH();
+  }
+  tm.mark("tree_levels");
+
+  tree_state h{};
+  BSJ_CUDA_TRY(cudaMemcpyAsync(&h, st_dev, sizeof(h), cudaMemcpyDeviceToHost, s));
+  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
+  if (h.overflow) throw error(BSJ_CUDA_ERROR, "quadtree node capacity exceeded (internal error)");
+  int const last = d >= 2 ? d - 1 : 0;
+  u64 const q    = h.level_end[last];
+
+  grid.sorted_keys      = out_keys;
+  grid.n_sorted_keys    = n;
+  out->sorted_keys      = out_keys;
+  grid.has_out_of_bbox  = (h.point_flags & 1u) ? 1 : 0;
+  grid.has_nan          = (h.point_flags & 2u) ? 1 : 0;
+  out->grid             = grid;
+  out->point_indices    = out_idx;
+  out->num_points       = n;
+  out->num_nodes        = q;
+  out->key              = oa.get<u32>(q);
+  out->level            = oa.get<u8>(q);
+  out->is_internal_node = oa.get<u8>(q);
+  out->length           = oa.get<u32>(q);
+  out->offset           = oa.get<u32>(q);
+  if (q) {
+    copy_tree_kernel<<<div_up(q, 256), 256, 0, s>>>(tkey.get(), tlevel.get(), tint.get(),
+                                                   tlen.get(), toff.get(), (u32)q, out->key,
+                                                   out->level, out->is_internal_node, out->length,
+                                                   out->offset);
+    BSJ_CHECK_LAUNCH();
+  }
+  tm.mark("finalize");
+  tm.finish();  // results are ready in stream order; no trailing host synchronisation
+  oa.commit();
+}
+}  // namespace
 
 // Host orchestration.  One stream synchronisation at the end (to learn the node count).
 void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, double x_min,
@@ -587,82 +679,42 @@ void quadtree_on_points_impl(const void* x, const void* y, int dtype, u64 n, dou
               &in_a);
   const u32* sorted_keys = in_a ? keys_a.get() : keys_b.get();
 
-  // ---- tree rows. Capacity: every node below level 0 has a parent with > max_size points, so a
-  // level holds at most 4*floor(N/(max_size+1)) nodes, and never more than N or (2^(L+1)+3)^2
-  // cells (cell indices reach 2^d + 2 under the reference's scale clamp, SURVEY.md A.1).
-  u64 cap = 64;
-  {
-    u64 const per_level = std::min<u64>(n, 4 * (n / ((u64)max_size + 1)));
-    for (int L = 1; L < d; ++L) {
-      u64 const side = (2ull << L) + 3;
-      cap += std::min(per_level, side * side);
-    }
-  }
-  dev_buf<u32> tkey(cap, s), tlen(cap, s), toff(cap, s);
-  dev_buf<u8> tlevel(cap, s), tint(cap, s);
-  // one look-back descriptor per tile of the largest level: 256-node tiles in the thread kernel,
-  // 8-node tiles in the warp kernel (which only runs on levels with <= kWarpLevelNodes nodes)
-  u32 const max_tiles = (u32)std::max<u64>(div_up(cap, kExpandBlock),
-                                           div_up(std::min<u64>(cap, kWarpLevelNodes), kExpandWarpNodes)) + 1;
-  dev_buf<u64> lb(max_tiles, s);
-  dev_buf<u32> tickets(16, s);
-  BSJ_CUDA_TRY(cudaMemsetAsync(lb.get(), 0, max_tiles * sizeof(u64), s));
-  BSJ_CUDA_TRY(cudaMemsetAsync(tickets.get(), 0, 16 * sizeof(u32), s));
+  finish_tree(sorted_keys, out_keys, out_idx, n, d, max_size, st.get(), grid, oa, tm, s, out);
+}
 
-  int const shift0 = d >= 1 ? 2 * (d - 1) : 0;
-  level0_kernel<<<1, 32, 0, s>>>(sorted_keys, (u32)n, shift0, (u32)cap, tkey.get(), tlevel.get(),
-                                 tint.get(), tlen.get(), toff.get(), st.get());
-  BSJ_CHECK_LAUNCH();
-  for (int L = 0; L + 1 < d; ++L) {
-    // level L holds at most min(cap, (2^(L+1)+3)^2) nodes; size the grid for that
-    u64 const geo  = ((2ull << L) + 3) * ((2ull << L) + 3);
-    int const grid = (int)std::min<u64>((u64)num_sms() * 8,
-                                        std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandBlock)));
-    if (geo <= kWarpLevelNodes) {  // few, huge nodes: warp-cooperative child search
-      int const wgrid = (int)std::max<u64>(1, div_up(std::min<u64>(geo, cap), kExpandWarpNodes));
-      expand_level_warp_kernel<<<wgrid, kExpandBlock, 0, s>>>(
-        sorted_keys, L, d, max_size, (u32)cap, tkey.get(), tlevel.get(), tint.get(), tlen.get(),
-        toff.get(), st.get(), lb.get(), tickets.get() + L);
-    } else {
-      expand_level_kernel<<<grid, kExpandBlock, 0, s>>>(
-        sorted_keys, L, d, max_size, (u32)cap, tkey.get(), tlevel.get(), tint.get(), tlen.get(),
-        toff.get(), st.get(), lb.get(), tickets.get() + L, nullptr);
-    }
-    BSJ_CHECK_LAUNCH();
-  }
-  tm.mark("tree_levels");
-
-  tree_state h{};
-  BSJ_CUDA_TRY(cudaMemcpyAsync(&h, st.get(), sizeof(h), cudaMemcpyDeviceToHost, s));
-  BSJ_CUDA_TRY(cudaStreamSynchronize(s));
-  if (h.overflow) throw error(BSJ_CUDA_ERROR, "quadtree node capacity exceeded (internal error)");
-  int const last = d >= 2 ? d - 1 : 0;
-  u64 const q    = h.level_end[last];
-
-  grid.sorted_keys      = out_keys;
-  grid.n_sorted_keys    = n;
-  out->sorted_keys      = out_keys;
-  grid.has_out_of_bbox  = (h.point_flags & 1u) ? 1 : 0;
-  grid.has_nan          = (h.point_flags & 2u) ? 1 : 0;
-  out->grid             = grid;
-  out->point_indices    = out_idx;
-  out->num_points       = n;
-  out->num_nodes        = q;
-  out->key              = oa.get<u32>(q);
-  out->level            = oa.get<u8>(q);
-  out->is_internal_node = oa.get<u8>(q);
-  out->length           = oa.get<u32>(q);
-  out->offset           = oa.get<u32>(q);
-  if (q) {
-    copy_tree_kernel<<<div_up(q, 256), 256, 0, s>>>(tkey.get(), tlevel.get(), tint.get(),
-                                                   tlen.get(), toff.get(), (u32)q, out->key,
-                                                   out->level, out->is_internal_node, out->length,
-                                                   out->offset);
-    BSJ_CHECK_LAUNCH();
-  }
-  tm.mark("finalize");
-  tm.finish();  // results are ready in stream order; no trailing host synchronisation
-  oa.commit();
+// Quadtree from Morton keys that were computed elsewhere (multi-GPU: the keys a rank RECEIVES for
+// its key range, with the points' global ids as sort payload).  Same stable sort and the same tree
+// rows as quadtree_on_points on the corresponding points; out->point_indices = the payload in
+// sorted order.  `keys` and `values` are scratch: the sort overwrites them.
+void quadtree_on_keys_impl(u32* keys, u32* values, u64 n, const bsj_grid* g, int max_size_in,
+                           const bsj_allocator* mr, cudaStream_t s, bsj_quadtree* out)
+{
+  *out = bsj_quadtree{};
+  if (n == 0) return;
+  BSJ_EXPECTS(n < 0xFFFFC000ull, "number of points must fit uint32 indices");
+  BSJ_EXPECTS(g != nullptr && g->valid, "key geometry (bsj_grid) must be given");
+  u32 const max_size = (u32)std::max(1, max_size_in);
+  int const d        = std::max(0, std::min(15, (int)g->max_depth));
+  stage_timer tm(s);
+  int const key_bits = std::min(32, 2 * (d + 2));
+  out_alloc oa(mr, s);
+  u32* out_idx  = oa.get<u32>(n);
+  u32* out_keys = oa.get<u32>(n);
+  dev_buf<u32> keys_tmp(n, s), vals_tmp(n, s);
+  sort_workspace ws;
+  ws.alloc(n, s);
+  sort_workspace_reset(ws, s);
+  sort_histogram(keys, n, 0, key_bits, ws, s);
+  tm.mark("key_hist");
+  sort_passes_to(keys, values, keys_tmp.get(), vals_tmp.get(), out_keys, out_idx, n, 0, key_bits,
+                 ws, s);
+  dev_buf<tree_state> st(1, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(st.get(), 0, sizeof(tree_state), s));
+  u32 const flags = (g->has_out_of_bbox ? 1u : 0u) | (g->has_nan ? 2u : 0u);
+  BSJ_CUDA_TRY(cudaMemcpyAsync(&st.get()->point_flags, &flags, sizeof(u32), cudaMemcpyHostToDevice,
+                               s));
+  bsj_grid grid = *g;
+  finish_tree(out_keys, out_keys, out_idx, n, d, max_size, st.get(), grid, oa, tm, s, out);
 }
 
 }  // namespace bsj

@@ -359,4 +359,30 @@ void sort_passes(u32* keys_a, u32* vals_a, bool iota_values, u32* keys_b, u32* v
   *result_in_a = in_a;
 }
 
+// Three-buffer form: passes ping-pong between the input and a temporary, the last one writes the
+// caller's output buffers.  The INPUT buffers are scratch (overwritten when there are >= 3
+// passes).  Used where the sorted result must land in freshly allocated output columns while the
+// input lives in a buffer the sort may not keep (the multi-GPU receive buffers).
+void sort_passes_to(u32* keys_in, u32* vals_in, u32* keys_tmp, u32* vals_tmp, u32* keys_out,
+                    u32* vals_out, u64 n, int begin_bit, int end_bit, sort_workspace& ws,
+                    cudaStream_t s, const char* profile_label)
+{
+  set_kernel_attrs();
+  int const passes = passes_for_bits(begin_bit, end_bit);
+  for (int p = 0; p < passes; ++p) {
+    bool const from_in = (p % 2) == 0;                 // X -> Y -> X -> ... , last -> Z
+    bool const last    = p == passes - 1;
+    u32* kin  = from_in ? keys_in : keys_tmp;
+    u32* vin  = from_in ? vals_in : vals_tmp;
+    u32* kout = last ? keys_out : (from_in ? keys_tmp : keys_in);
+    u32* vout = last ? vals_out : (from_in ? vals_tmp : vals_in);
+    u32 const tag_agg = 2u * (p + 1), tag_pre = 2u * (p + 1) + 1u;
+    onesweep_kernel<false><<<ws.num_tiles, kSortBlock, sizeof(sort_smem), s>>>(
+      kin, vin, kout, vout, (u32)n, begin_bit + p * kRadixBits, ws.hist.get() + p * kRadixDigits,
+      ws.lookback.get(), ws.tickets.get() + p, tag_agg, tag_pre);
+    BSJ_CHECK_LAUNCH();
+    prof_mark(profile_label);
+  }
+}
+
 }  // namespace bsj

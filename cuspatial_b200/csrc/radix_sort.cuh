@@ -60,4 +60,10 @@ void sort_passes(u32* keys_a, u32* vals_a, bool iota_values, u32* keys_b, u32* v
                  int begin_bit, int end_bit, sort_workspace& ws, cudaStream_t s,
                  bool* result_in_a, const char* profile_label = "onesweep_pass");
 
+// Same passes with three buffers: input (scratch, overwritten) <-> temporary, last pass into the
+// output buffers.  Needs end_bit > begin_bit.
+void sort_passes_to(u32* keys_in, u32* vals_in, u32* keys_tmp, u32* vals_tmp, u32* keys_out,
+                    u32* vals_out, u64 n, int begin_bit, int end_bit, sort_workspace& ws,
+                    cudaStream_t s, const char* profile_label = "onesweep_pass");
+
 }  // namespace bsj

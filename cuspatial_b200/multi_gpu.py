@@ -1,58 +1,55 @@
 """Multi-GPU quadtree point-in-polygon join: one process per GPU, torch.distributed (NCCL).
 
-The reference is single-GPU; this is the sharded form of the same path:
+The reference is single-GPU; this is the sharded form of the same path.
+Points shard by contiguous Morton-key range, so that global sorted position = rank base + local
+sorted position.  Per call:
 
   1. the polygon table (offsets + vertices) is replicated by an NCCL broadcast from rank 0;
-  2. every rank computes the Morton keys of its local points and a histogram of their leading
-     16 bits (CUDA, partition.cu); the histograms are summed with ONE all-reduce and every rank
-     derives the same R-1 key splitters, placed on histogram-bin boundaries so equal keys never
-     straddle two ranks;
-  3. every rank stably partitions (x, y, global id) by destination rank (CUDA, partition.cu) and
-     the buckets are exchanged with all-to-all (NVLink); received points arrive ordered by global
-     id, so the tie order of the reference's stable sort is preserved;
-  4. every rank runs the unchanged single-GPU path on its key range with the GLOBAL area of
-     interest / scale / depth / max_size;
-  5. local results are lifted to global indices -- global sorted position = rank base + local
-     position, global point_indices = the received global ids permuted by the local sort -- and
-     the (polygon_index, point_index) tables are merged with an all-gather.
+  2. every rank computes the Morton keys of its points and a histogram of their leading bits
+     (CUDA, partition.cu); the histograms are summed with ONE all-reduce; the splitters are derived
+     ON THE DEVICE in two levels (first-level bin of each rank boundary, then a second histogram
+     of the next key bits inside those bins, one more all-reduce), as are this rank's send counts;
+     one all-gather of the send counts gives every rank its write offsets.  Everything lives in a
+     device struct (bsj_shard_plan): no host round trip up to here;
+  3. the partition kernel stably partitions (key, global id) by destination rank and its stores go
+     straight into the destination GPUs' receive buffers (symmetric memory, peer pointers over
+     NVLink; per-destination runs leave the SM as bulk copies) -- partition and all-to-all in one
+     kernel, 8 bytes per point on the wire; a device-side barrier follows.  The ONE host
+     synchronisation of the exchange reads the plan back (receive counts);
+  4. every rank sorts the keys it received (payload = global ids), builds its sub-quadtree with the
+     GLOBAL area of interest / scale / depth / max_size, filters the polygon boxes and refines.
+     Coordinates never moved: the refinement reads them through peer pointers into the owning
+     ranks' point columns (ShardedPoints, symmetric memory) for the few points whose finest cell
+     is touched by a polygon edge -- everything else is decided from the keys;
+  5. what is merged is the COMPACT result (per-pair records + ballot words, tens of MB), one
+     all-gather; every rank expands every rank's rows at HBM speed with
+     point_index = rank base + local sorted position.
 
 The merged pair SET equals a single-GPU run's bit for bit (the per-rank sub-quadtrees are not the
-global quadtree, so row order inside the table differs; compare sorted rows).
+global quadtree, so row order inside the table differs; compare sorted rows), and the concatenated
+point_indices equal the single-GPU point_indices.
 
-The three device steps are injected as callables so that the host-side logic (splitters, index
-fix-up, merge) is testable on CPU with the gloo backend (tests/test_multi_gpu_cpu.py).
+The device steps are injected as callables so that the host-side logic (plan, index fix-up, merge)
+is testable on CPU with the gloo backend (tests/test_multi_gpu_cpu.py); the functions
+refine_splitters / splitters_from_subhist / send_counts_for below are the host restatement of the
+plan kernels, and a GPU test checks the kernels against them.
 """
 import os
-import time
 
 import numpy as np
 import torch
 
-HIST_BITS = 13   # 8192 bins: privatised in shared memory by the histogram kernel
+HIST_BITS = 13   # 8192 first-level bins: privatised in shared memory by the histogram kernel
+MAX_RANKS = 32
 LAST_PROFILE = {}
 
 
-class _Prof:
-    """Optional wall-clock phase timing (BSJ_MG_PROFILE=1): synchronises, so never on by default."""
-
-    def __init__(self, dev):
-        self.on = os.environ.get("BSJ_MG_PROFILE") == "1" and dev.type == "cuda"
-        self.dev, self.t, self.out = dev, None, {}
-        if self.on:
-            torch.cuda.synchronize(dev)
-            self.t = time.perf_counter()
-
-    def mark(self, name):
-        if self.on:
-            torch.cuda.synchronize(self.dev)
-            now = time.perf_counter()
-            self.out[name] = self.out.get(name, 0.0) + 1e3 * (now - self.t)
-            self.t = now
-
-
+# ------------------------------------------------------------------------------------------------
+# host restatement of the sharding plan (CPU tests; checker of the plan kernels)
+# ------------------------------------------------------------------------------------------------
 def choose_splitters(global_hist, n_ranks, shift):
-    """R-1 ascending uint32 key splitters on bin boundaries balancing the point counts.
-    Rank r owns keys in [splitter[r-1], splitter[r])."""
+    """One-level variant: R-1 ascending uint32 key splitters on bin boundaries balancing the
+    point counts.  Rank r owns keys in [splitter[r-1], splitter[r])."""
     h = np.asarray(global_hist, dtype=np.int64)
     csum = np.cumsum(h)
     total = int(csum[-1]) if len(csum) else 0
@@ -65,13 +62,19 @@ def choose_splitters(global_hist, n_ranks, shift):
     return np.asarray(out, dtype=np.uint32)
 
 
-SUB_BITS = 10
+def sub_bits_for(n_ranks, shift):
+    """Width of the second-level histogram: (n_ranks - 1) * 2^bits counters must fit the
+    sub-histogram kernel's 48 KB of shared memory (12288 counters)."""
+    bits = 10
+    while bits > 0 and max(n_ranks - 1, 1) * (1 << bits) > 12288:
+        bits -= 1
+    return min(bits, shift)
 
 
 def refine_splitters(global_hist, n_ranks, shift):
-    """First step of the two-level splitter search: for every rank boundary the first-level bin
-    in which the target cumulative count is reached, and how many points are still missing when
-    that bin starts.  Returns (target_bins sorted unique, [(bin, missing)] per boundary)."""
+    """Level 1: for every rank boundary the first-level bin in which the target cumulative count
+    is reached, and how many points are still missing when that bin starts.
+    Returns (target_bins sorted unique, [(bin, missing)] per boundary)."""
     h = np.asarray(global_hist, dtype=np.int64)
     csum = np.cumsum(h)
     total = int(csum[-1]) if len(csum) else 0
@@ -86,7 +89,7 @@ def refine_splitters(global_hist, n_ranks, shift):
 
 
 def splitters_from_subhist(bounds, targets, sub_global, shift, shift2):
-    """Second step: inside each target bin, the sub-bin boundary where the missing count is met."""
+    """Level 2: inside each target bin, the sub-bin boundary where the missing count is met."""
     n_sub = sub_global.shape[1]
     out = []
     for b, missing in bounds:
@@ -118,130 +121,320 @@ def send_counts_for(splitters, local_hist, targets, sub_local, shift, shift2, wo
     return counts
 
 
-def cuda_sub_histogram(keys, shift, targets, shift2, n_sub):
-    import ctypes as C
-
-    from . import _lib
-    from .api import _ptr, _stream
-
-    bins = torch.zeros(len(targets) * n_sub, dtype=torch.int32, device=keys.device)
-    tg = np.ascontiguousarray(targets, dtype=np.uint32)
-    with torch.cuda.device(keys.device):
-        _lib.check(_lib.lib().bsj_key_subhistogram(
-            _ptr(keys), keys.shape[0], int(shift), tg.ctypes.data_as(C.c_void_p), len(targets),
-            int(shift2), int(n_sub), _ptr(bins), _stream(keys.device)))
-    return bins.to(torch.int64).view(len(targets), n_sub)
-
-
 def hist_shift_for(max_depth):
     key_bits = min(32, 2 * (max(0, min(15, int(max_depth))) + 2))
     return max(0, key_bits - HIST_BITS)
+
+
+class HostPlan:
+    """The plan as plain numpy (CPU tests).  Same fields as bsj_shard_plan."""
+
+    def __init__(self, ghist, sizes, n_ranks, rank, shift, sub_shift, n_sub):
+        self.n_ranks, self.rank, self.shift, self.sub_shift, self.n_sub = (n_ranks, rank, shift,
+                                                                          sub_shift, n_sub)
+        self.sizes = list(sizes)
+        self.gid_base = [int(v) for v in np.concatenate([[0], np.cumsum(self.sizes)])]
+        self.targets, self.bounds = refine_splitters(ghist, n_ranks, shift)
+
+
+# ------------------------------------------------------------------------------------------------
+# points registered for peer access
+# ------------------------------------------------------------------------------------------------
+_SYMM = {}
+
+
+def _group_key(group):
+    import torch.distributed as dist
+
+    return tuple(dist.get_process_group_ranks(group if group is not None else dist.group.WORLD))
+
+
+def _symm_alloc(dev, dtype, capacity, group, tag):
+    """A symmetric-memory buffer (same capacity on every rank, mapped into every peer), cached per
+    (device, process group, purpose, dtype) and grown collectively."""
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm
+
+    key = (dev.index, _group_key(group), tag, dtype)
+    ent = _SYMM.get(key)
+    if ent is None or ent["cap"] < capacity:
+        t = symm.empty(int(capacity), dtype=dtype, device=dev)
+        hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+        ent = {"cap": int(capacity), "buf": t, "hdl": hdl}
+        _SYMM[key] = ent
+    return ent
+
+
+class ShardedPoints:
+    """This rank's point columns, placed where every peer GPU can read them (symmetric memory),
+    plus what every rank needs to address them: all ranks' sizes and the peer pointers."""
+
+    def __init__(self, x, y, sizes, group, peers_x=None, peers_y=None):
+        self.x, self.y, self.sizes, self.group = x, y, list(sizes), group
+        self.peers_x, self.peers_y = peers_x, peers_y   # data_ptr of every rank's columns
+
+    @property
+    def dtype(self):
+        return self.x.dtype
+
+    def __len__(self):
+        return int(self.x.shape[0])
+
+
+def register_points(x, y, group=None):
+    """Copy (x, y) into symmetric memory and exchange sizes + peer pointers.  A setup step (one
+    host-synchronising all-gather): do it once per point set, outside any timed region, and write
+    new coordinates into `.x` / `.y` in place when the set changes but its size does not."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    dev = x.device
+    n = torch.tensor([x.shape[0]], dtype=torch.int64, device=dev)
+    all_n = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(all_n, n, group=group)
+    sizes = [int(v.item()) for v in all_n]
+    if sum(sizes) >= 2 ** 32 - 2 ** 14:
+        raise ValueError("total number of points must fit uint32 global indices")
+    cap = max(max(sizes), 1)
+    ex = _symm_alloc(dev, x.dtype, cap, group, "points_x")
+    ey = _symm_alloc(dev, x.dtype, cap, group, "points_y")
+    sx, sy = ex["buf"][: x.shape[0]], ey["buf"][: x.shape[0]]
+    sx.copy_(x)
+    sy.copy_(y)
+    px = [ex["hdl"].get_buffer(r, (ex["cap"],), x.dtype).data_ptr() for r in range(world)]
+    py = [ey["hdl"].get_buffer(r, (ey["cap"],), x.dtype).data_ptr() for r in range(world)]
+    torch.cuda.synchronize(dev)
+    dist.barrier(group=group)
+    return ShardedPoints(sx, sy, sizes, group, px, py)
+
+
+def _host_register(x, y, group=None):
+    """CPU stand-in of register_points (gloo tests): sizes only."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    n = torch.tensor([x.shape[0]], dtype=torch.int64)
+    all_n = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(all_n, n, group=group)
+    return ShardedPoints(x, y, [int(v.item()) for v in all_n], group)
 
 
 # ------------------------------------------------------------------------------------------------
 # device steps (CUDA through the C ABI); replaced by host callables in the CPU tests
 # ------------------------------------------------------------------------------------------------
 def cuda_keys_and_histogram(x, y, bbox, scale, max_depth, shift, n_bins):
-    import ctypes as C
-
+    """keys (int32 view of uint32) and [histogram | #out-of-box flag | #NaN flag] (int32)."""
     from . import _lib
     from .api import _DTYPE_CODE, _ptr, _stream
 
     keys = torch.empty(x.shape[0], dtype=torch.int32, device=x.device)
-    bins = torch.zeros(n_bins, dtype=torch.int32, device=x.device)
+    ext = torch.zeros(n_bins + 2, dtype=torch.int32, device=x.device)
+    flags = torch.zeros(1, dtype=torch.int32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().bsj_point_keys_histogram(
             _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], float(bbox[0]), float(bbox[1]),
             float(bbox[2]), float(bbox[3]), float(scale), int(max_depth), int(shift), _ptr(keys),
-            _ptr(bins), n_bins, _stream(x.device)))
-    return keys, bins.to(torch.int64)
+            _ptr(ext), n_bins, _ptr(flags), _stream(x.device)))
+    ext[n_bins] = flags[0] & 1          # summed by the all-reduce: > 0 means "somewhere"
+    ext[n_bins + 1] = (flags[0] >> 1) & 1
+    return keys, ext
 
 
-_SYMM = {}
+class CudaPlan:
+    """bsj_shard_plan in device memory (an int32 tensor) + a pinned host mirror."""
+
+    def __init__(self, dev):
+        import ctypes as C
+
+        from . import _lib
+
+        self.words = C.sizeof(_lib.bsj_shard_plan) // 4
+        self.dev_t = torch.zeros(self.words, dtype=torch.int32, device=dev)
+        self.host_t = torch.zeros(self.words, dtype=torch.int32).pin_memory()
+        self._struct = _lib.bsj_shard_plan
+        f = _lib.bsj_shard_plan
+        self.off_send_count = f.send_count.offset // 4
+
+    def ptr(self):
+        import ctypes as C
+
+        return C.c_void_p(self.dev_t.data_ptr())
+
+    def read_back(self):
+        """Device -> pinned host copy + the host synchronisation; returns the ctypes struct."""
+        self.host_t.copy_(self.dev_t, non_blocking=True)
+        torch.cuda.current_stream(self.dev_t.device).synchronize()
+        return self._struct.from_buffer_copy(self.host_t.numpy().tobytes())
 
 
-def _symmetric_buffers(dev, dtype, capacity, group):
-    """Receive buffers (x, y, gid) in symmetric memory, mapped into every peer: grown
-    collectively (all ranks see the same `capacity`), cached across calls."""
-    import torch.distributed._symmetric_memory as symm
-
-    key = (dev.index, dtype)
-    ent = _SYMM.get(key)
-    if ent is None or ent["cap"] < capacity:
-        cap = int(capacity * 1.25) + 4096
-        bufs, hdls = [], []
-        for dt in (dtype, dtype, torch.int32):
-            t = symm.empty(cap, dtype=dt, device=dev)
-            hdls.append(symm.rendezvous(t, group if group is not None else
-                                        torch.distributed.group.WORLD))
-            bufs.append(t)
-        ent = {"cap": cap, "bufs": bufs, "hdls": hdls}
-        _SYMM[key] = ent
-    return ent
-
-
-def cuda_partition_exchange(keys, x, y, gid_base, splitters, counts_matrix, rank, group):
-    """Stable partition by destination rank whose stores go straight into the destination GPUs'
-    receive buffers (peer memory over NVLink): partition and all-to-all in ONE kernel.
-    counts_matrix[src][dst] = points rank src sends to rank dst (identical on every rank)."""
+def cuda_plan_level1(ghist, sizes, world, rank, shift, sub_shift, n_sub):
     import ctypes as C
 
-    import torch.distributed as dist
+    from . import _lib
+    from .api import _ptr, _stream
+
+    plan = CudaPlan(ghist.device)
+    sz = (C.c_uint32 * world)(*sizes)
+    with torch.cuda.device(ghist.device):
+        _lib.check(_lib.lib().bsj_shard_plan_level1(
+            _ptr(ghist), ghist.shape[0], sz, world, rank, int(shift), int(sub_shift), int(n_sub),
+            plan.ptr(), _stream(ghist.device)))
+    return plan
+
+
+def cuda_sub_histogram(keys, plan, world, n_sub):
+    from . import _lib
+    from .api import _ptr, _stream
+
+    bins = torch.zeros(max(world - 1, 1) * n_sub, dtype=torch.int32, device=keys.device)
+    with torch.cuda.device(keys.device):
+        _lib.check(_lib.lib().bsj_shard_subhistogram(
+            _ptr(keys), keys.shape[0], plan.ptr(), world, int(n_sub), _ptr(bins),
+            _stream(keys.device)))
+    return bins
+
+
+def cuda_plan_level2(plan, local_hist, local_sub, global_sub, world):
+    """Fills splitters + send counts; returns the send counts as a VIEW of the device plan (the
+    all-gather reads it in place)."""
+    from . import _lib
+    from .api import _ptr, _stream
+
+    with torch.cuda.device(local_hist.device):
+        _lib.check(_lib.lib().bsj_shard_plan_level2(
+            _ptr(local_hist), local_hist.shape[0], _ptr(local_sub), _ptr(global_sub), plan.ptr(),
+            _stream(local_hist.device)))
+    return plan.dev_t[plan.off_send_count: plan.off_send_count + world]
+
+
+def cuda_exchange(keys, plan, counts_matrix, points, world, rank, group):
+    """Plan finalisation + fused partition/all-to-all of (key, global id) + device barrier, then
+    the one host synchronisation of the exchange (the plan comes back with the receive counts).
+    Returns (received keys, received global ids, host plan)."""
+    import ctypes as C
 
     from . import _lib
-    from .api import _DTYPE_CODE, _ptr, _stream
+    from .api import _ptr, _stream
 
-    R = len(counts_matrix)
-    dev = x.device
-    recv_tot = [sum(counts_matrix[s][d] for s in range(R)) for d in range(R)]
-    ent = _symmetric_buffers(dev, x.dtype, max(recv_tot), group)
-    cap = ent["cap"]
-    esz = x.element_size()
-    ptr_x, ptr_y, ptr_g = (C.c_void_p * R)(), (C.c_void_p * R)(), (C.c_void_p * R)()
-    for d in range(R):
-        off = sum(counts_matrix[s][d] for s in range(rank))  # where my bucket starts in rank d
-        bx = ent["hdls"][0].get_buffer(d, (cap,), x.dtype)
-        by = ent["hdls"][1].get_buffer(d, (cap,), x.dtype)
-        bg = ent["hdls"][2].get_buffer(d, (cap,), torch.int32)
-        ptr_x[d] = bx.data_ptr() + off * esz
-        ptr_y[d] = by.data_ptr() + off * esz
-        ptr_g[d] = bg.data_ptr() + off * 4
-    sp = np.ascontiguousarray(splitters, dtype=np.uint32)
+    dev = keys.device
+    total = sum(points.sizes)
+    use_bulk = 0 if os.environ.get("BSJ_MG_BULK_COPY") == "0" else 1
+    cap = int(total / world * 1.25) + 16384
+    for attempt in range(2):
+        ek = _symm_alloc(dev, torch.int32, cap, group, "recv_key")
+        eg = _symm_alloc(dev, torch.int32, cap, group, "recv_gid")
+        cap = min(ek["cap"], eg["cap"])
+        pk, pg = (C.c_void_p * world)(), (C.c_void_p * world)()
+        for d in range(world):
+            pk[d] = ek["hdl"].get_buffer(d, (ek["cap"],), torch.int32).data_ptr()
+            pg[d] = eg["hdl"].get_buffer(d, (eg["cap"],), torch.int32).data_ptr()
+        with torch.cuda.device(dev):
+            L = _lib.lib()
+            _lib.check(L.bsj_shard_plan_finalize(_ptr(counts_matrix), cap, plan.ptr(), _stream(dev)))
+            _lib.check(L.bsj_partition_keys(_ptr(keys), keys.shape[0], plan.ptr(), world, pk, pg,
+                                            use_bulk, _stream(dev)))
+        # every rank's stores must have landed before anyone reads its receive buffers: a
+        # device-side barrier over the symmetric-memory signal pads, enqueued after the partition
+        # kernel on the same stream (kernel completion makes its peer stores visible system-wide).
+        # BSJ_MG_HOST_BARRIER=1 swaps in a host synchronisation + NCCL barrier.
+        if os.environ.get("BSJ_MG_HOST_BARRIER") == "1":
+            import torch.distributed as dist
+
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)
+        else:
+            ek["hdl"].barrier(channel=0)
+        h = plan.read_back()
+        if h.status == 0:
+            n_recv = int(h.recv_total[rank])
+            return ek["buf"][:n_recv], eg["buf"][:n_recv], h
+        # a receive total exceeds the buffers (extreme skew: one key holds most points): every
+        # rank sees the same plan, so all of them grow the buffers and repeat the exchange
+        cap = int(max(h.recv_total[:world]) * 1.1) + 16384
+    raise RuntimeError("sharded exchange: receive buffers could not be sized")
+
+
+def _grid_struct(bbox, scale, max_depth, dtype, has_oob, has_nan):
+    """The key geometry exactly as the encode kernel used it (values of the coordinate type)."""
+    from . import _lib
+
+    T = np.float32 if dtype == torch.float32 else np.float64
+    x0, x1, y0, y1 = (T(v) for v in bbox)
+    d = max(0, min(15, int(max_depth)))
+    sc = max(T(scale), max(x1 - x0, y1 - y0) / T((1 << d) + 2))
+    g = _lib.bsj_grid()
+    g.valid, g.max_depth = 1, d
+    g.min_x, g.min_y, g.max_x, g.max_y = float(x0), float(y0), float(x1), float(y1)
+    g.scale = float(sc)
+    g.has_nan, g.has_out_of_bbox = int(bool(has_nan)), int(bool(has_oob))
+    return g
+
+
+def cuda_local_compact(rkeys, rgids, points, flags, polygons, bbox, scale, max_depth, max_size):
+    """Sort the received (key, global id) pairs, build the sub-quadtree, filter, refine up to the
+    COMPACT PIP result.  Coordinates are read through peer pointers (segments)."""
+    import ctypes as C
+
+    from . import _lib, api
+    from .api import _DTYPE_CODE, _TorchAllocator, _ptr, _stream
+    from .frame import Frame
+
+    dev = rkeys.device
+    n = rkeys.shape[0]
+    grid = _grid_struct(bbox, scale, max_depth, points.dtype, flags[0], flags[1])
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().bsj_partition_points(
-            _ptr(keys), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], int(gid_base),
-            sp.ctypes.data_as(C.c_void_p), R, ptr_x, ptr_y, ptr_g, _stream(dev)))
-    # every rank's stores must have landed before anyone reads its receive buffers: a device-side
-    # barrier over the symmetric-memory signal pads, enqueued after the partition kernel on the
-    # same stream (kernel completion makes its peer stores visible system-wide) -- no host
-    # synchronisation and no NCCL round trip.  BSJ_MG_HOST_BARRIER=1 restores the host barrier.
-    # The device barrier is verified at 2 and 4 GPUs; larger groups keep the host barrier (the
-    # form verified at 8 GPUs) until it has been re-run there -- BSJ_MG_DEVICE_BARRIER=1 forces it.
-    use_device = (R <= 4 or os.environ.get("BSJ_MG_DEVICE_BARRIER") == "1") and \
-        os.environ.get("BSJ_MG_HOST_BARRIER") != "1"
-    if use_device:
-        ent["hdls"][0].barrier(channel=0)
-    else:
-        torch.cuda.synchronize(dev)
-        dist.barrier(group=group)
-    n_recv = recv_tot[rank]
-    rx, ry, rg = (b[:n_recv] for b in ent["bufs"])
-    return rx, ry, rg
-
-
-def cuda_local_compact(x, y, polygons, bbox, scale, max_depth, max_size):
-    """The single-GPU path on this rank's points, stopped at the COMPACT PIP result."""
-    from . import api
-
-    pidx, tree = api.quadtree_on_points((x, y), bbox[0], bbox[1], bbox[2], bbox[3], scale,
-                                        max_depth, max_size)
+        alloc = _TorchAllocator(dev)
+        out = _lib.bsj_quadtree()
+        _lib.check(_lib.lib().bsj_quadtree_on_keys(
+            _ptr(rkeys), _ptr(rgids), n, C.byref(grid), int(max_size), C.byref(alloc.struct),
+            _stream(dev), C.byref(out)))
+    q = int(out.num_nodes)
+    pidx = alloc.take(out.point_indices, n, torch.uint32)
+    tree = Frame([
+        ("key", alloc.take(out.key, q, torch.uint32)),
+        ("level", alloc.take(out.level, q, torch.uint8)),
+        ("is_internal_node", alloc.take(out.is_internal_node, q, torch.bool)),
+        ("length", alloc.take(out.length, q, torch.uint32)),
+        ("offset", alloc.take(out.offset, q, torch.uint32)),
+    ])
+    g = _lib.bsj_grid()
+    C.memmove(C.byref(g), C.byref(out.grid), C.sizeof(_lib.bsj_grid))
+    sorted_keys = alloc.take(out.sorted_keys, n, torch.uint32)
     bb = api.polygon_bounding_boxes(polygons)
     pairs = api.join_quadtree_and_bounding_boxes(tree, bb, bbox[0], bbox[1], bbox[2], bbox[3],
                                                  scale, max_depth)
-    comp = api.quadtree_point_in_polygon_compact(pairs, tree, pidx, (x, y), polygons)
-    n_hits = comp.pop("n_hits")
-    comp = {k: (v.view(torch.int32) if v.dtype == torch.uint32 else v) for k, v in comp.items()}
-    return pidx.view(torch.int32), comp, n_hits
+    # refinement with segmented coordinates
+    po, ro, vx, vy = api._split_polygons(polygons)
+    po = api._as_cuda(po, torch.uint32 if po.dtype != torch.int32 else None)
+    ro = api._as_cuda(ro, torch.uint32 if ro.dtype != torch.int32 else None)
+    segs = _lib.bsj_coord_segments()
+    world = len(points.sizes)
+    segs.n_segments = world
+    first = 0
+    for r in range(world):
+        segs.first_id[r] = first
+        segs.x[r], segs.y[r] = points.peers_x[r], points.peers_y[r]
+        first += points.sizes[r]
+    segs.first_id[world] = first
+    pp, pq = pairs["bbox_offset"], pairs["quad_offset"]
+    tcols = api._quadtree_columns(tree)
+    with torch.cuda.device(dev):
+        alloc = _TorchAllocator(dev)
+        c = _lib.bsj_pip_compact()
+        _lib.check(_lib.lib().bsj_quadtree_point_in_polygon_compact_seg(
+            _ptr(pp), _ptr(pq), pp.shape[0], *[_ptr(t) for t in tcols], tcols[0].shape[0],
+            _ptr(pidx), C.byref(segs), _DTYPE_CODE[points.dtype], n, _ptr(po), po.shape[0],
+            _ptr(ro), ro.shape[0], _ptr(vx), _ptr(vy), vx.shape[0], C.byref(g),
+            C.byref(alloc.struct), _stream(dev), C.byref(c)))
+    comp = {"pair_poly": pp.view(torch.int32)}
+    for name, dt, cnt in api._COMPACT_FIELDS:
+        m = int(getattr(c, cnt))
+        if name == "mask_words":
+            m = max(m, 1) if getattr(c, name) else 0
+        t = alloc.take(getattr(c, name), m, dt)
+        comp[name] = t.view(torch.int32) if t.dtype == torch.uint32 else t
+    del sorted_keys
+    return pidx.view(torch.int32), comp, int(c.n_hits)
 
 
 def cuda_expand(comp, n_hits, position_base, out_poly, out_point):
@@ -277,37 +470,75 @@ def _all_gather_varlen(t, dist, group, sizes=None):
     return out, sizes
 
 
+class _Phases:
+    """Phase timing with CUDA events on the launching stream (no host synchronisation while the
+    step runs; the events are read after the step's last synchronisation)."""
+
+    def __init__(self, dev, on):
+        self.on = bool(on) and dev.type == "cuda"
+        self.dev, self.marks = dev, []
+        if self.on:
+            self.mark("begin")
+
+    def mark(self, name):
+        if self.on:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(self.dev))
+            self.marks.append((name, e))
+
+    def finish(self):
+        if not self.on:
+            return
+        torch.cuda.current_stream(self.dev).synchronize()
+        LAST_PROFILE.clear()
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            LAST_PROFILE[name] = LAST_PROFILE.get(name, 0.0) + a.elapsed_time(b)
+
+
 def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_max, scale,
                                       max_depth, max_size, group=None, gather_pairs=True,
-                                      gather_point_indices=False, steps=None):
+                                      gather_point_indices=False, steps=None, profile=False):
     """Distributed quadtree PIP join over the ranks of `group`.
 
-    points    : this rank's (x, y) shard; global point id = (sum of earlier ranks' sizes) + i
+    points    : this rank's shard -- a ShardedPoints (register_points: zero-copy, the fast path)
+                or an (x, y) pair (registered on the fly: one extra copy + host synchronisation);
+                global point id = (sum of earlier ranks' sizes) + i
     polygons  : (part_offset, ring_offset, x, y); only rank 0's content is used (broadcast)
     Returns a dict with
       polygon_index, point_index : the merged pair table (every rank, if gather_pairs) -- or this
                                    rank's rows with GLOBAL point_index if not
-      point_indices              : global sorted-position -> global point id map (this rank's key
-                                   range, or the whole array if gather_point_indices)
+      local_point_indices        : global sorted position -> global point id for this rank's key
+                                   range (a fresh tensor owned by the result)
+      point_indices              : the whole map (if gather_point_indices)
       base, counts               : first global sorted position / number of points per rank
     """
     import torch.distributed as dist
 
     steps = steps or {}
+    register = steps.get("register", register_points)
     keys_hist = steps.get("keys_hist", cuda_keys_and_histogram)
-    partition = steps.get("partition")  # host stand-in for the CPU tests
+    plan_level1 = steps.get("plan_level1", cuda_plan_level1)
+    sub_hist = steps.get("sub_hist", cuda_sub_histogram)
+    plan_level2 = steps.get("plan_level2", cuda_plan_level2)
+    exchange = steps.get("exchange", cuda_exchange)
     local_compact = steps.get("local_compact", cuda_local_compact)
     expand = steps.get("expand", cuda_expand)
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    x, y = points
+    if world > MAX_RANKS:
+        raise ValueError("at most %d ranks" % MAX_RANKS)
+    if not isinstance(points, ShardedPoints):
+        points = register(points[0], points[1], group)
+    x, y = points.x, points.y
     dev = x.device
+    if sum(points.sizes) >= 2 ** 32 - 2 ** 14:
+        raise ValueError("total number of points must fit uint32 global indices")
     bbox = (min(x_min, x_max), max(x_min, x_max), min(y_min, y_max), max(y_min, y_max))
     min_scale = max(bbox[1] - bbox[0], bbox[3] - bbox[2]) / ((1 << max_depth) + 2)
     scale = max(scale, min_scale)
 
-    prof = _Prof(dev)
+    prof = _Phases(dev, profile)
     # 1. replicate the polygon table -- two NCCL broadcasts: the four sizes, then ONE packed byte
     # buffer (each array padded to 16 bytes) that the receivers slice into typed views
     src0 = dist.get_global_rank(group, 0) if group else 0
@@ -333,65 +564,37 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
                      torch.empty(0, dtype=t.dtype, device=dev))
         o += pb
     polys = tuple(polys)
-
     prof.mark("broadcast_polygons")
-    # 2. keys + leading-bit histogram, one all-reduce, identical splitters everywhere.  The
-    # per-rank point counts (global ids are rank-major) ride in `world` extra slots of the same
-    # all-reduce, and local + global histogram come back to the host in one copy.
+
+    # 2. keys + leading-bit histogram; the plan is derived on the device from the SUMMED histograms
     shift = hist_shift_for(max_depth)
     n_bins = 1 << min(HIST_BITS, 32 - shift) if shift < 32 else 1
-    keys, hist = keys_hist(x, y, bbox, scale, max_depth, shift, n_bins)
+    sub_bits = sub_bits_for(world, shift)
+    sub_shift, n_sub = shift - sub_bits, 1 << sub_bits
+    keys, local_ext = keys_hist(x, y, bbox, scale, max_depth, shift, n_bins)
     prof.mark("keys_hist")
-    slots = torch.zeros(world, dtype=hist.dtype, device=dev)
-    slots[rank] = x.shape[0]
-    both = torch.stack([torch.cat([hist, slots])] * 2)   # row 0 stays local, row 1 is reduced
-    dist.all_reduce(both[1], op=dist.ReduceOp.SUM, group=group)
-    both_h = both.cpu().numpy()
-    local_hist, hist_h = both_h[0, :n_bins].copy(), both_h[1, :n_bins].copy()
-    all_n = [int(v) for v in both_h[1, n_bins:]]
-    gid_base = sum(all_n[:rank])
-    # two-level splitters: a first-level bin can hold a whole cluster, so the boundary is placed
-    # inside it with a second histogram of the next SUB_BITS key bits (one more all-reduce)
-    sub_hist = steps.get("sub_hist", cuda_sub_histogram)
-    shift2 = max(0, shift - SUB_BITS)
-    n_sub = 1 << (shift - shift2)
-    targets, bounds = refine_splitters(hist_h, world, shift)
-    if n_sub > 1 and targets:
-        sub = sub_hist(keys, shift, targets, shift2, n_sub)
-        sub_both = torch.stack([sub, sub])
-        dist.all_reduce(sub_both[1], op=dist.ReduceOp.SUM, group=group)
-        sub_h = sub_both.cpu().numpy()
-        sub_local = sub_h[0].copy()
-        splitters = splitters_from_subhist(bounds, targets, sub_h[1], shift, shift2)
-    else:
-        targets, sub_local = [], np.zeros((0, 1), dtype=np.int64)
-        splitters = choose_splitters(hist_h, world, shift)
-    prof.mark("allreduce_splitters")
-    # 3. stable partition by destination + all-to-all
-    send_counts = send_counts_for(splitters, local_hist, targets, sub_local, shift, shift2, world)
-    sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
-    rows = [torch.zeros_like(sc) for _ in range(world)]
-    dist.all_gather(rows, sc, group=group)       # also orders this step after every rank's
-    counts_matrix = [r_.tolist() for r_ in rows]  # previous step (receive buffers are reused)
-    recv_counts = [counts_matrix[s_][rank] for s_ in range(world)]
-    n_recv = int(sum(recv_counts))
-    if partition is None:
-        # fused partition + exchange: the kernel writes into the peers' receive buffers
-        rx, ry, rgid = cuda_partition_exchange(keys, x, y, gid_base, splitters, counts_matrix,
-                                               rank, group)
-        prof.mark("partition_exchange")
-    else:
-        sx, sy, sgid = partition(keys, x, y, gid_base, splitters, send_counts.tolist())
-        prof.mark("partition")
-        rx = torch.empty(n_recv, dtype=x.dtype, device=dev)
-        ry = torch.empty(n_recv, dtype=y.dtype, device=dev)
-        rgid = torch.empty(n_recv, dtype=torch.int32, device=dev)
-        for dst, src in ((rx, sx), (ry, sy), (rgid, sgid)):
-            dist.all_to_all_single(dst, src, output_split_sizes=recv_counts,
-                                   input_split_sizes=send_counts.tolist(), group=group)
-        prof.mark("all_to_all")
-    # 4. the unchanged single-GPU path on this rank's key range, stopped at the compact result
-    pidx_local, comp, n_hits = local_compact(rx, ry, polys, bbox, scale, max_depth, max_size)
+    global_ext = local_ext.clone()
+    dist.all_reduce(global_ext, op=dist.ReduceOp.SUM, group=group)
+    plan = plan_level1(global_ext[:n_bins], points.sizes, world, rank, shift, sub_shift, n_sub)
+    local_sub = sub_hist(keys, plan, world, n_sub)
+    global_sub = local_sub.clone()
+    dist.all_reduce(global_sub, op=dist.ReduceOp.SUM, group=group)
+    send_counts = plan_level2(plan, local_ext[:n_bins], local_sub, global_sub, world)
+    counts_matrix = torch.empty(world * world, dtype=send_counts.dtype, device=dev)
+    if dev.type == "cuda":
+        dist.all_gather_into_tensor(counts_matrix, send_counts.contiguous(), group=group)
+    else:  # gloo (CPU tests)
+        dist.all_gather(list(counts_matrix.view(world, world).unbind(0)), send_counts.contiguous(),
+                        group=group)
+    prof.mark("plan_collectives")
+    # 3. fused partition + all-to-all of (key, global id), device barrier, ONE host sync
+    rkeys, rgids, hplan = exchange(keys, plan, counts_matrix, points, world, rank, group)
+    flags = [int(v) for v in global_ext[n_bins: n_bins + 2].tolist()]
+    n_recv = int(rkeys.shape[0])
+    prof.mark("partition_exchange")
+    # 4. the single-GPU path on this rank's key range, stopped at the compact result
+    pidx_global, comp, n_hits = local_compact(rkeys, rgids, points, flags, polys, bbox, scale,
+                                              max_depth, max_size)
     prof.mark("local_join")
 
     # 5. global indices and merge.  What crosses NVLink is the COMPACT result (per-pair records +
@@ -405,9 +608,12 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     stats = [s_.tolist() for s_ in stats]
     counts = [s_[0] for s_ in stats]
     hits = [s_[1] for s_ in stats]
+    if sum(hits) >= 2 ** 32 and gather_pairs:
+        raise ValueError("merged pair table must have fewer than 2^32 rows")
     base = sum(counts[:rank])
-    out = {"base": base, "counts": counts, "rows_per_rank": hits}
-    prof.mark("global_indices")
+    out = {"base": base, "counts": counts, "rows_per_rank": hits, "splitters":
+           [int(v) for v in hplan.splitter[: world - 1]] if hasattr(hplan, "splitter") else None}
+    prof.mark("stats")
     if gather_pairs:
         # one packed byte buffer per rank -> R broadcasts in total (not R per array)
         def _bytes(t):
@@ -422,6 +628,7 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
             torch.empty(0, dtype=torch.uint8, device=dev)
         tot_b = [sum(b + p_ for b, p_ in zip(sizes_b[r], pad[r])) for r in range(world)]
         allb, _ = _all_gather_varlen(packed, dist, group, tot_b)
+        prof.mark("gather_compact")
         total = sum(hits)
         out_poly = torch.empty(total, dtype=torch.int32, device=dev)
         out_point = torch.empty(total, dtype=torch.int32, device=dev)
@@ -438,20 +645,18 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
                        out_point[row: row + hits[r]])
             row += hits[r]
         out["polygon_index"], out["point_index"] = out_poly, out_point
+        prof.mark("expand_rows")
     else:
         out_poly = torch.empty(n_hits, dtype=torch.int32, device=dev)
         out_point = torch.empty(n_hits, dtype=torch.int32, device=dev)
         if n_hits:
             expand(comp, n_hits, base, out_poly, out_point)
         out["polygon_index"], out["point_index"] = out_poly, out_point
-    # global sorted position -> global point id, for this rank's key range (lazy: a 100M-element
-    # gather that most callers of a join do not need)
-    out["local_point_indices"], out["received_global_ids"] = pidx_local, rgid
+        prof.mark("expand_rows")
+    # global sorted position -> global point id for this rank's key range
+    out["local_point_indices"] = pidx_global
     if gather_point_indices:
-        point_indices = rgid[pidx_local.to(torch.int64)] if n_recv else rgid
-        out["point_indices"], _ = _all_gather_varlen(point_indices, dist, group, counts)
-    prof.mark("all_gather")
-    if prof.on:
-        LAST_PROFILE.clear()
-        LAST_PROFILE.update(prof.out)
+        out["point_indices"], _ = _all_gather_varlen(pidx_global, dist, group, counts)
+        prof.mark("gather_point_indices")
+    prof.finish()
     return out

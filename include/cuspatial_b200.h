@@ -286,32 +286,92 @@ int bsj_polygon_bounding_boxes(const uint32_t* poly_offsets, uint64_t n_poly_off
                                void* out_x_max, void* out_y_max);
 
 /*
- * Multi-GPU sharding helpers (no reference analogue: the reference is single-GPU).  Points are
- * sharded across ranks by contiguous Morton-key range; the host layer (one process per GPU,
- * NCCL) all-reduces the histograms, agrees on splitters and exchanges the partitioned buffers.
- *
- * bsj_point_keys_histogram: keys[i] = the reference's Morton key of point i
- *   (cpp/include/cuspatial/detail/index/construction/phase_1.cuh:78-85) and, if bins != NULL,
- *   bins[keys[i] >> hist_shift] += 1 (bins are accumulated into, n_bins > max key >> hist_shift).
- * bsj_partition_points: stable partition by destination rank, destination of key k =
- *   #{r : k >= host_splitters[r]}, r < n_ranks-1.  dst_x/dst_y/dst_gid are HOST arrays of n_ranks
- *   DEVICE pointers: where this rank's bucket for destination r starts.  They may point into peer
- *   GPUs' memory (CUDA IPC / symmetric memory over NVLink): the kernel's stores then ARE the
- *   all-to-all exchange -- no staging buffer, no separate collective.  gid = gid_base + index.
+ * Multi-GPU (no reference analogue: the reference is single-GPU).  Points
+ * are sharded across ranks by contiguous Morton-key range.  One process per GPU; the host layer
+ * (cuspatial_b200/multi_gpu.py, torch.distributed over NCCL) only sums the histograms and gathers
+ * the send counts -- splitters, send counts and write offsets are computed by kernels into one
+ * device struct, and the partition kernel's stores ARE the exchange (peer memory over NVLink).
+ * What crosses NVLink is 8 bytes per point, (key, global id): the owner sorts the keys it receives
+ * (bsj_quadtree_on_keys) and the refinement reads coordinates on demand through peer pointers
+ * (bsj_coord_segments) for the few points whose finest cell is touched by a polygon edge.
  */
+#define BSJ_MAX_RANKS 32
+
+/* Device-resident sharding plan (all fields written by the bsj_shard_plan_* kernels). */
+typedef struct bsj_shard_plan {
+  uint32_t n_ranks, rank, hist_shift, sub_shift;
+  uint32_t n_sub, n_targets;
+  uint32_t status;                         /* 0 ok, 1 a receive total exceeds the capacity        */
+  uint32_t reserved;
+  uint32_t gid_base[BSJ_MAX_RANKS + 1];    /* first global point id of every rank, then the total */
+  uint32_t bound_bin[BSJ_MAX_RANKS];       /* boundary r+1: first-level bin it falls into ...     */
+  uint32_t bound_missing[BSJ_MAX_RANKS];   /* ... and points still missing when that bin starts   */
+  uint32_t target_bin[BSJ_MAX_RANKS];      /* distinct boundary bins (second-level histogram rows) */
+  uint32_t splitter[BSJ_MAX_RANKS];        /* rank r owns keys in [splitter[r-1], splitter[r])    */
+  uint32_t send_count[BSJ_MAX_RANKS];      /* points this rank sends to every destination         */
+  uint32_t send_offset[BSJ_MAX_RANKS];     /* where its bucket starts in the destination's buffer  */
+  uint32_t recv_total[BSJ_MAX_RANKS];      /* points every rank receives in total                 */
+} bsj_shard_plan;
+
+/* Coordinates spread over several arrays: point ids first_id[s] .. first_id[s+1]-1 live in
+ * (x[s], y[s]) -- one segment per rank, the pointers may be peer-GPU memory. */
+typedef struct bsj_coord_segments {
+  int32_t n_segments;
+  uint32_t first_id[BSJ_MAX_RANKS + 1];
+  const void* x[BSJ_MAX_RANKS];
+  const void* y[BSJ_MAX_RANKS];
+} bsj_coord_segments;
+
+/* keys[i] = the reference's Morton key of point i
+ *   (cpp/include/cuspatial/detail/index/construction/phase_1.cuh:78-85); if bins != NULL,
+ *   bins[keys[i] >> hist_shift] += 1 (accumulated; n_bins > max key >> hist_shift); if
+ *   point_flags != NULL (device), bit 0 is OR-ed in when a point lies outside the box and bit 1
+ *   when a coordinate is NaN.  Stream-ordered, no host synchronisation. */
 int bsj_point_keys_histogram(const void* x, const void* y, int dtype, uint64_t n, double x_min,
                              double x_max, double y_min, double y_max, double scale,
                              int8_t max_depth, int hist_shift, uint32_t* keys, uint32_t* bins,
-                             uint64_t n_bins, bsj_stream_t stream);
-/* bins[t * n_sub + ((key >> shift2) & (n_sub-1))] += 1 for every key with
- * (key >> shift1) == host_target_bins[t]; refines the splitters inside heavy first-level bins. */
-int bsj_key_subhistogram(const uint32_t* keys, uint64_t n, int shift1,
-                         const uint32_t* host_target_bins, int n_targets, int shift2,
-                         uint32_t n_sub, uint32_t* bins, bsj_stream_t stream);
-int bsj_partition_points(const uint32_t* keys, const void* x, const void* y, int dtype, uint64_t n,
-                         uint32_t gid_base, const uint32_t* host_splitters, int n_ranks,
-                         void* const* dst_x, void* const* dst_y, uint32_t* const* dst_gid,
-                         bsj_stream_t stream);
+                             uint64_t n_bins, uint32_t* point_flags, bsj_stream_t stream);
+/* Plan, level 1: from the SUMMED first-level histogram and the (host-known) rank sizes, the
+ * first-level bin holding each rank boundary.  n_sub = 1 << (hist_shift - sub_shift). */
+int bsj_shard_plan_level1(const uint32_t* global_hist, uint64_t n_bins,
+                          const uint32_t* host_rank_sizes, int n_ranks, int rank, int hist_shift,
+                          int sub_shift, uint32_t n_sub, bsj_shard_plan* plan, bsj_stream_t stream);
+/* bins[t * n_sub + ((key >> sub_shift) & (n_sub-1))] += 1 for every key whose first-level bin is
+ * plan->target_bin[t]; bins must hold (n_ranks-1) * n_sub zero-initialised counters. */
+int bsj_shard_subhistogram(const uint32_t* keys, uint64_t n, const bsj_shard_plan* plan,
+                           int n_ranks, uint32_t n_sub, uint32_t* bins, bsj_stream_t stream);
+/* Plan, level 2: splitters from the SUMMED second-level histogram; this rank's send counts from
+ * its own two histograms. */
+int bsj_shard_plan_level2(const uint32_t* local_hist, uint64_t n_bins, const uint32_t* local_sub,
+                          const uint32_t* global_sub, bsj_shard_plan* plan, bsj_stream_t stream);
+/* counts_matrix[s * n_ranks + d] = points rank s sends to rank d (the all-gathered send counts):
+ * fills send_offset / recv_total, sets status = 1 if a receive total exceeds `capacity`. */
+int bsj_shard_plan_finalize(const uint32_t* counts_matrix, uint64_t capacity, bsj_shard_plan* plan,
+                            bsj_stream_t stream);
+/* Stable partition of (key, gid_base[rank] + index) by destination rank, written straight into
+ * the destinations' receive buffers: dst_key / dst_gid are HOST arrays of n_ranks DEVICE pointers
+ * (peer memory over NVLink), 16-byte aligned.  The aligned body of every per-destination run
+ * leaves the SM as a bulk copy (cp.async.bulk, use_bulk_copy != 0) or as 128-bit stores.  Does
+ * nothing when plan->status != 0. */
+int bsj_partition_keys(const uint32_t* keys, uint64_t n, const bsj_shard_plan* plan, int n_ranks,
+                       uint32_t* const* dst_key, uint32_t* const* dst_gid, int use_bulk_copy,
+                       bsj_stream_t stream);
+/* bsj_quadtree_on_points for keys computed elsewhere: stable sort of (keys, values) and the same
+ * tree rows; out->point_indices = values in sorted order.  `grid` gives the key geometry (and the
+ * out-of-box / NaN flags of the encode).  keys / values are SCRATCH: overwritten. */
+int bsj_quadtree_on_keys(uint32_t* keys, uint32_t* values, uint64_t n, const bsj_grid* grid,
+                         int32_t max_size, const bsj_allocator* mr, bsj_stream_t stream,
+                         bsj_quadtree* out);
+/* bsj_quadtree_point_in_polygon_compact with the point coordinates given as segments indexed by
+ * the (global) ids stored in point_indices; n_points = number of sorted positions. */
+int bsj_quadtree_point_in_polygon_compact_seg(
+  const uint32_t* pair_poly, const uint32_t* pair_quad, uint64_t n_pairs, const uint32_t* key,
+  const uint8_t* level, const uint8_t* is_internal_node, const uint32_t* length,
+  const uint32_t* offset, uint64_t num_nodes, const uint32_t* point_indices,
+  const bsj_coord_segments* segments, int dtype, uint64_t n_points, const uint32_t* poly_offsets,
+  uint64_t n_poly_offsets, const uint32_t* ring_offsets, uint64_t n_ring_offsets,
+  const void* poly_points_x, const void* poly_points_y, uint64_t n_poly_points,
+  const bsj_grid* grid, const bsj_allocator* mr, bsj_stream_t stream, bsj_pip_compact* out);
 
 /* Release a buffer the library allocated with its default allocator (mr == NULL). */
 void bsj_free(void* ptr, bsj_stream_t stream);

@@ -436,56 +436,125 @@ def test_nearest_linestring_empty_and_errors():
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_sharding_kernels_on_one_gpu(dtype):
-    """The multi-GPU helpers, with every destination bucket in local memory: keys equal the
-    quadtree builder's keys, histograms equal bincounts, the partition is stable and complete."""
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_sharding_kernels_on_one_gpu(dtype, world):
+    """The multi-GPU kernels with every "rank" living on this GPU: keys equal the quadtree
+    builder's keys; the device plan (two-level splitters, send counts, offsets) equals its host
+    restatement in multi_gpu.py; the fused partition is stable and complete (bulk-copy and plain
+    store variants); quadtree_on_keys equals quadtree_on_points; the refinement with coordinate
+    segments equals the plain one."""
     import ctypes as C
 
     import torch
 
     import cuspatial_b200 as cs
     from cuspatial_b200 import _lib, multi_gpu as mg
-    from cuspatial_b200.api import _DTYPE_CODE, _ptr, _stream
+    from cuspatial_b200.api import _ptr, _stream
 
-    c = make_case(300_000, 5, 15, "c", dtype, seed=5, oob=100, dups=1000)
-    x, y = _t(c["x"]), _t(c["y"])
+    c = make_case(300_000, 40, 15, "c", dtype, seed=5, oob=100, dups=1000, median_vertices=30)
+    n = len(c["x"])
     ext = c["ext"]
+    cuts = [r * n // world for r in range(world + 1)]
+    xs = [_t(c["x"][a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    ys = [_t(c["y"][a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    sizes = [b - a for a, b in zip(cuts[:-1], cuts[1:])]
+    x, y = _t(c["x"]), _t(c["y"])
     pidx, tree = cs.quadtree_on_points((x, y), ext[0], ext[1], ext[2], ext[3], c["scale"], 15, 64)
     shift = mg.hist_shift_for(15)
     n_bins = 1 << mg.HIST_BITS
-    keys, bins = mg.cuda_keys_and_histogram(x, y, ext, c["scale"], 15, shift, n_bins)
-    k = keys.cpu().numpy().view(np.uint32)
-    np.testing.assert_array_equal(np.sort(k, kind="stable"), tree._sorted_keys.cpu().numpy())
-    np.testing.assert_array_equal(np.argsort(k, kind="stable").astype(np.uint32), pidx.cpu().numpy())
-    np.testing.assert_array_equal(bins.cpu().numpy(), np.bincount(k >> shift, minlength=n_bins))
-    # sub-histogram of the two heaviest first-level bins
-    targets = np.argsort(bins.cpu().numpy())[-2:].astype(np.uint32)
-    shift2, n_sub = max(shift - 10, 0), 1 << min(10, shift)
-    sub = mg.cuda_sub_histogram(keys, shift, targets, shift2, n_sub).cpu().numpy()
-    for t, b in enumerate(targets):
-        sel = k[(k >> shift) == b]
-        np.testing.assert_array_equal(sub[t], np.bincount((sel >> shift2) & (n_sub - 1),
-                                                          minlength=n_sub))
-    # partition into 3 local buckets
-    q = np.quantile(k, [0.3, 0.8]).astype(np.uint32)
-    dest = np.searchsorted(q, k, side="right")
-    counts = np.bincount(dest, minlength=3)
-    outs = [(torch.empty(int(n), dtype=x.dtype, device="cuda"),
-             torch.empty(int(n), dtype=x.dtype, device="cuda"),
-             torch.empty(int(n), dtype=torch.int32, device="cuda")) for n in counts]
-    px, py, pg = (C.c_void_p * 3)(), (C.c_void_p * 3)(), (C.c_void_p * 3)()
-    for d in range(3):
-        px[d], py[d], pg[d] = (outs[d][i].data_ptr() for i in range(3))
-    sp = np.ascontiguousarray(q, dtype=np.uint32)
-    _lib.check(_lib.lib().bsj_partition_points(
-        _ptr(keys), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], 7,
-        sp.ctypes.data_as(C.c_void_p), 3, px, py, pg, _stream(x.device)))
-    torch.cuda.synchronize()
-    for d in range(3):
-        ids = np.nonzero(dest == d)[0]
-        np.testing.assert_array_equal(outs[d][2].cpu().numpy(), ids.astype(np.int32) + 7)
-        np.testing.assert_array_equal(outs[d][0].cpu().numpy(), c["x"][ids])
-        np.testing.assert_array_equal(outs[d][1].cpu().numpy(), c["y"][ids])
+    sub_bits = mg.sub_bits_for(world, shift)
+    sub_shift, n_sub = shift - sub_bits, 1 << sub_bits
+    # ---- keys + histogram + flags, per virtual rank
+    keys, exts = [], []
+    for r in range(world):
+        k, e = mg.cuda_keys_and_histogram(xs[r], ys[r], ext, c["scale"], 15, shift, n_bins)
+        keys.append(k); exts.append(e)
+    kall = np.concatenate([k.cpu().numpy().view(np.uint32) for k in keys])
+    np.testing.assert_array_equal(np.sort(kall, kind="stable"), tree._sorted_keys.cpu().numpy())
+    np.testing.assert_array_equal(np.argsort(kall, kind="stable").astype(np.uint32),
+                                  pidx.cpu().numpy())
+    for r in range(world):
+        kr = keys[r].cpu().numpy().view(np.uint32)
+        np.testing.assert_array_equal(exts[r][:n_bins].cpu().numpy(),
+                                      np.bincount(kr >> shift, minlength=n_bins))
+    assert int(sum(e[n_bins] for e in exts)) >= 1       # out-of-box points were flagged
+    gext = torch.stack(exts).sum(0).to(torch.int32)
+    ghist = gext[:n_bins].cpu().numpy().astype(np.int64)
+    targets, bounds = mg.refine_splitters(ghist, world, shift)
+    # ---- plan on the device, per virtual rank; compare with the host restatement
+    plans, subs = [], []
+    for r in range(world):
+        p = mg.cuda_plan_level1(gext[:n_bins].contiguous(), sizes, world, r, shift, sub_shift, n_sub)
+        plans.append(p)
+        subs.append(mg.cuda_sub_histogram(keys[r], p, world, n_sub))
+    gsub = torch.stack(subs).sum(0).to(torch.int32)
+    sub_np = gsub.cpu().numpy().astype(np.int64).reshape(-1, n_sub)[:len(targets)]
+    want_split = mg.splitters_from_subhist(bounds, targets, sub_np, shift, sub_shift) \
+        if world > 1 else np.empty(0, np.uint32)
+    send = []
+    for r in range(world):
+        sc = mg.cuda_plan_level2(plans[r], exts[r][:n_bins].contiguous(), subs[r], gsub, world)
+        send.append(sc.clone())
+    M = torch.stack(send).contiguous()                   # [src][dst]
+    dest_all = np.searchsorted(want_split.astype(np.int64), kall.astype(np.int64), side="right")
+    for r in range(world):
+        kr = keys[r].cpu().numpy().view(np.uint32).astype(np.int64)
+        d = np.searchsorted(want_split.astype(np.int64), kr, side="right")
+        np.testing.assert_array_equal(M[r].cpu().numpy(), np.bincount(d, minlength=world))
+    recv_tot = np.bincount(dest_all, minlength=world)
+    assert recv_tot.max() < 1.05 * n / world + 2000      # balanced (two-level splitters)
+    # ---- fused partition into per-destination buffers (all local here), both store variants
+    for bulk in (1, 0):
+        cap = int(recv_tot.max()) + 64
+        bk = [torch.full((cap,), -1, dtype=torch.int32, device="cuda") for _ in range(world)]
+        bg = [torch.full((cap,), -1, dtype=torch.int32, device="cuda") for _ in range(world)]
+        pk, pg = (C.c_void_p * world)(), (C.c_void_p * world)()
+        for d in range(world):
+            pk[d], pg[d] = bk[d].data_ptr(), bg[d].data_ptr()
+        for r in range(world):
+            L = _lib.lib()
+            _lib.check(L.bsj_shard_plan_finalize(_ptr(M), cap, plans[r].ptr(), _stream(x.device)))
+            _lib.check(L.bsj_partition_keys(_ptr(keys[r]), keys[r].shape[0], plans[r].ptr(), world,
+                                            pk, pg, bulk, _stream(x.device)))
+            h = plans[r].read_back()
+            assert h.status == 0 and list(h.splitter[:world - 1]) == want_split.tolist()
+            assert list(h.recv_total[:world]) == recv_tot.tolist()
+            assert h.gid_base[r] == cuts[r] and h.n_targets == len(targets)
+        torch.cuda.synchronize()
+        for d in range(world):
+            ids = np.nonzero(dest_all == d)[0]             # ascending global id == stable order
+            np.testing.assert_array_equal(bg[d][:len(ids)].cpu().numpy().view(np.uint32), ids)
+            np.testing.assert_array_equal(bk[d][:len(ids)].cpu().numpy().view(np.uint32), kall[ids])
+            assert int((bg[d][len(ids):] != -1).sum()) == 0   # nothing written past the bucket
+    # too small a receive capacity is reported, and the partition then writes nothing
+    _lib.check(_lib.lib().bsj_shard_plan_finalize(_ptr(M), 10, plans[0].ptr(), _stream(x.device)))
+    assert plans[0].read_back().status == 1
+    # ---- owner side: quadtree_on_keys + refinement through coordinate segments, for rank 0's range
+    ids = np.nonzero(dest_all == 0)[0]
+    rk, rg = bk[0][:len(ids)].clone(), bg[0][:len(ids)].clone()
+    pts = mg.ShardedPoints(xs[0], ys[0], sizes, None, [t.data_ptr() for t in xs],
+                           [t.data_ptr() for t in ys])
+    polys = tuple(_t(a) for a in (c["po"], c["ro"], c["vx"], c["vy"]))
+    flags = [int(gext[n_bins]), int(gext[n_bins + 1])]
+    pg_, comp, n_hits = mg.cuda_local_compact(rk, rg, pts, flags, polys, ext, c["scale"], 15, 64)
+    # the same key range on the plain single-GPU path
+    xr, yr = _t(c["x"][ids]), _t(c["y"][ids])
+    pidx_r, tree_r = cs.quadtree_on_points((xr, yr), ext[0], ext[1], ext[2], ext[3], c["scale"],
+                                           15, 64)
+    np.testing.assert_array_equal(pg_.cpu().numpy().view(np.uint32),
+                                  ids[pidx_r.cpu().numpy().astype(np.int64)])
+    bb = cs.polygon_bounding_boxes(polys)
+    pairs_r = cs.join_quadtree_and_bounding_boxes(tree_r, bb, ext[0], ext[1], ext[2], ext[3],
+                                                  c["scale"], 15)
+    hits_r = cs.quadtree_point_in_polygon(pairs_r, tree_r, pidx_r, (xr, yr), polys)
+    op = torch.empty(n_hits, dtype=torch.int32, device="cuda")
+    oq = torch.empty(n_hits, dtype=torch.int32, device="cuda")
+    mg.cuda_expand(comp, n_hits, 0, op, oq)
+    np.testing.assert_array_equal(op.cpu().numpy().view(np.uint32),
+                                  hits_r["polygon_index"].cpu().numpy())
+    np.testing.assert_array_equal(oq.cpu().numpy().view(np.uint32),
+                                  hits_r["point_index"].cpu().numpy())
+    assert n_hits > 0
 
 
 def test_error_conditions_match_reference():

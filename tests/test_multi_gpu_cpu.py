@@ -23,7 +23,11 @@ def _dilate(v):
 
 
 def _host_steps(oracle):
+    """Host stand-ins (numpy + the CPU oracle) of the device steps of multi_gpu.py."""
     import torch
+    import torch.distributed as dist
+
+    from cuspatial_b200 import multi_gpu as mg
 
     def keys_hist(x, y, bbox, scale, max_depth, shift, n_bins):
         xn, yn = x.numpy(), y.numpy()
@@ -35,22 +39,65 @@ def _host_steps(oracle):
         iy = ((yn - mny) / sc).astype(np.uint32) & 0xFFFF
         k = (_dilate(iy) << 1) | _dilate(ix)
         k[oob] = (1 << (2 * max_depth)) - 1
-        hist = np.bincount(k >> shift, minlength=n_bins).astype(np.int64)
-        return torch.from_numpy(k.astype(np.int32)), torch.from_numpy(hist)
+        ext = np.zeros(n_bins + 2, dtype=np.int32)
+        ext[:n_bins] = np.bincount(k >> shift, minlength=n_bins)
+        ext[n_bins] = int(oob.any())
+        ext[n_bins + 1] = int(np.isnan(xn).any() or np.isnan(yn).any())
+        return torch.from_numpy(k.astype(np.int32)), torch.from_numpy(ext)
 
-    def partition(keys, x, y, gid_base, splitters, counts):
+    def plan_level1(ghist, sizes, world, rank, shift, sub_shift, n_sub):
+        return mg.HostPlan(ghist.numpy().view(np.uint32).astype(np.int64), sizes, world, rank,
+                           shift, sub_shift, n_sub)
+
+    def sub_hist(keys, plan, world, n_sub):
         k = keys.numpy().view(np.uint32).astype(np.int64)
-        dest = np.searchsorted(splitters.astype(np.int64), k, side="right")
-        order = np.argsort(dest, kind="stable")
-        gid = (gid_base + np.arange(len(k))).astype(np.int32)
-        assert np.bincount(dest, minlength=len(counts)).tolist() == list(counts)
-        return (torch.from_numpy(x.numpy()[order]), torch.from_numpy(y.numpy()[order]),
-                torch.from_numpy(gid[order]))
+        out = np.zeros((max(world - 1, 1), n_sub), dtype=np.int32)
+        for t, b in enumerate(plan.targets):
+            sel = k[(k >> plan.shift) == b]
+            out[t] = np.bincount((sel >> plan.sub_shift) & (n_sub - 1), minlength=n_sub)
+        return torch.from_numpy(out.reshape(-1))
 
-    def local_join(x, y, polys, bbox, scale, max_depth, max_size):
+    def plan_level2(plan, local_hist, local_sub, global_sub, world):
+        nt = len(plan.targets)
+        gs = global_sub.numpy().view(np.uint32).astype(np.int64).reshape(-1, plan.n_sub)[:nt]
+        ls = local_sub.numpy().view(np.uint32).astype(np.int64).reshape(-1, plan.n_sub)[:nt]
+        plan.splitter = mg.splitters_from_subhist(plan.bounds, plan.targets, gs, plan.shift,
+                                                  plan.sub_shift)
+        lh = local_hist.numpy().view(np.uint32).astype(np.int64)
+        plan.send_count = mg.send_counts_for(plan.splitter, lh, plan.targets, ls, plan.shift,
+                                             plan.sub_shift, world)
+        return torch.from_numpy(plan.send_count.astype(np.int32))
+
+    def exchange(keys, plan, counts_matrix, points, world, rank, group):
+        k = keys.numpy().view(np.uint32)
+        dest = np.searchsorted(plan.splitter.astype(np.int64), k.astype(np.int64), side="right")
+        order = np.argsort(dest, kind="stable")
+        gid = (plan.gid_base[rank] + np.arange(len(k))).astype(np.int32)
+        M = counts_matrix.numpy().reshape(world, world)
+        assert np.bincount(dest, minlength=world).tolist() == M[rank].tolist()
+        send, recv = M[rank].tolist(), M[:, rank].tolist()
+        rk = torch.empty(sum(recv), dtype=torch.int32)
+        rg = torch.empty(sum(recv), dtype=torch.int32)
+        for dst_t, src in ((rk, k.view(np.int32)[order]), (rg, gid[order])):
+            dist.all_to_all_single(dst_t, torch.from_numpy(np.ascontiguousarray(src)),
+                                   output_split_sizes=recv, input_split_sizes=send, group=group)
+        return rk, rg, plan
+
+    def local_compact(rkeys, rgids, points, flags, polys, bbox, scale, max_depth, max_size):
+        # coordinates of the received ids: the CPU stand-in simply gathers all points
+        world = len(points.sizes)
+        cap = max(points.sizes)
+        parts = []
+        for src in (points.x, points.y):
+            pad = torch.zeros(cap, dtype=src.dtype)
+            pad[: src.shape[0]] = src
+            got = [torch.zeros_like(pad) for _ in range(world)]
+            dist.all_gather(got, pad, group=points.group)
+            parts.append(np.concatenate([g.numpy()[:n] for g, n in zip(got, points.sizes)]))
+        gid = rgids.numpy().view(np.uint32).astype(np.int64)
+        xn, yn = parts[0][gid], parts[1][gid]
         po, ro, vx, vy = (p.numpy() for p in polys)
         po, ro = po.view(np.uint32), ro.view(np.uint32)
-        xn, yn = x.numpy(), y.numpy()
         t = oracle.quadtree_on_points(xn, yn, bbox[0], bbox[1], bbox[2], bbox[3], scale,
                                       max_depth, max_size)
         bb = oracle.polygon_bounding_boxes(po, ro, vx, vy)
@@ -59,22 +106,16 @@ def _host_steps(oracle):
                                                   yn, po, ro, vx, vy)
         comp = {"poly": torch.from_numpy(hp.view(np.int32).copy()),
                 "pos": torch.from_numpy(hq.view(np.int32).copy())}
-        return torch.from_numpy(t["point_indices"].view(np.int32).copy()), comp, len(hp)
+        pidx_global = gid[t["point_indices"].astype(np.int64)].astype(np.uint32)
+        return torch.from_numpy(pidx_global.view(np.int32).copy()), comp, len(hp)
 
     def expand(comp, n_hits, position_base, out_poly, out_point):
         out_poly.copy_(comp["poly"])
         out_point.copy_((comp["pos"].to(torch.int64) + position_base).to(torch.int32))
 
-    def sub_hist(keys, shift, targets, shift2, n_sub):
-        k = keys.numpy().view(np.uint32).astype(np.int64)
-        out = np.zeros((len(targets), n_sub), dtype=np.int64)
-        for t, b in enumerate(targets):
-            sel = k[(k >> shift) == b]
-            out[t] = np.bincount((sel >> shift2) & (n_sub - 1), minlength=n_sub)
-        return torch.from_numpy(out)
-
-    return {"keys_hist": keys_hist, "partition": partition, "local_compact": local_join,
-            "expand": expand, "sub_hist": sub_hist}
+    return {"register": mg._host_register, "keys_hist": keys_hist, "plan_level1": plan_level1,
+            "sub_hist": sub_hist, "plan_level2": plan_level2, "exchange": exchange,
+            "local_compact": local_compact, "expand": expand}
 
 
 def _worker(rank, world, port, kind, dtype_name, q, gather=True):
@@ -187,7 +228,7 @@ def test_two_level_splitters_balance_a_heavy_bin():
                                           splitters_from_subhist)
 
     rng = np.random.default_rng(1)
-    shift, shift2, n_sub = 19, 9, 1024
+    shift, shift2, n_sub = 19, 9, 1024  # sub-histogram covers key bits [9, 19)
     keys = np.concatenate([rng.integers(0, 1 << 30, 50_000),
                            (777 << shift) + rng.integers(0, 1 << shift, 150_000)])  # one heavy bin
     hist = np.bincount(keys >> shift, minlength=1 << 11)
