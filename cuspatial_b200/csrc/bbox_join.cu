@@ -7,13 +7,15 @@
 // detail/join/traversal.cuh:63-145 (descent to children).
 //
 // Design (not a port): the reference runs ~12 Thrust launches and >= 3 host synchronisations per
-// level (latency bound).  Here ONE kernel walks the tree: one warp per bounding box keeps a LIFO
-// work list of node indices in shared memory, tests 32 nodes per step (one 128-bit node load per
-// lane from a packed copy of the tree), appends leaf hits to the global pair list with one
-// warp-aggregated atomic per step and pushes the children of internal hits back with a warp scan.
-// The reference's output order (offset[node] ascending, ties by box index -- Appendix A.2 of
-// SURVEY.md) is then restored by two stable radix sorts (box, then leaf offset) of the small pair
-// list, which also makes the result independent of the atomic's arrival order.
+// level (latency bound).  Here ONE persistent kernel walks the tree level by level: the (box, node)
+// work items of a level sit in a device queue, every warp takes 32 of them at a time (one 128-bit
+// node load per lane from a packed copy of the tree), appends leaf hits to the global pair list
+// and the children of internal hits to the next level's queue with one warp-aggregated atomic
+// each, and a grid-wide barrier separates the levels.  Work is balanced at 32-item granularity
+// whatever the shape of the tree (clustered data: a few very deep subtrees) or the number of
+// boxes.  The reference's output order (offset[node] ascending, ties by box index -- Appendix A.2
+// of SURVEY.md) is then restored by two stable radix sorts (box, then leaf offset) of the small
+// pair list, which also makes the result independent of the atomics' arrival order.
 #include "radix_sort.cuh"
 
 namespace bsj {
@@ -47,10 +49,13 @@ __device__ __forceinline__ u32 undilate16(u32 v)
 }
 
 struct join_state {
-  u32 n_top;     // number of level-0 nodes (quadtree_bbox_filtering.cuh:53-56)
-  u32 n_hits;    // leaf hits found by the traversal
-  u32 overflow;  // work-list overflow (malformed tree)
-  u32 n_seeds;   // (box, node) sub-traversals queued by the seeding pass
+  unsigned long long cursor0;  // level-0 items handed out so far (boxes x level-0 nodes: 64-bit)
+  u32 n_top;        // number of level-0 nodes (quadtree_bbox_filtering.cuh:53-56)
+  u32 n_hits;       // leaf hits found by the traversal
+  u32 overflow;     // a level's queue did not fit its buffer
+  u32 barrier;      // grid barrier arrivals (monotonic)
+  u32 count[17];    // items queued for level L
+  u32 cursor[17];   // items of level L handed out so far
 };
 
 // SoA tree -> one 16-byte record per node; counts level-0 nodes on the way.
@@ -70,52 +75,63 @@ pack_tree_kernel(const u32* __restrict__ key, const u8* __restrict__ level,
   if (lane_id() == 0 && m) atomicAdd(&st->n_top, (u32)__popc(m));
 }
 
-constexpr int kJoinWarps    = 4;
-constexpr int kJoinStackCap = 4096;  // u32 entries per warp
+constexpr int kJoinBlock = 256;
+
+// all CTAs of the (co-resident) grid: arrive, then wait for everybody
+__device__ __forceinline__ void grid_barrier(u32* counter, u32 generation)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    u32 const target = (generation + 1) * gridDim.x;
+    while (*(volatile u32*)counter < target) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+}
 
 template <typename T>
-__global__ void __launch_bounds__(kJoinWarps * 32)
+__global__ void __launch_bounds__(kJoinBlock)
 traverse_kernel(const uint4* __restrict__ nodes, const T* __restrict__ bx0,
                 const T* __restrict__ by0, const T* __restrict__ bx1, const T* __restrict__ by1,
                 u32 n_boxes, T vmin_x, T vmin_y, T scale, int max_depth,
                 u32* __restrict__ out_box, u32* __restrict__ out_node, u32 capacity,
-                join_state* st, const u32* __restrict__ seed_box,
-                const u32* __restrict__ seed_node, int stop_level, u32* __restrict__ q_box,
-                u32* __restrict__ q_node, u32 q_capacity)
+                join_state* st, uint2* __restrict__ queue_a, uint2* __restrict__ queue_b,
+                u32 q_capacity)
 {
-  extern __shared__ u32 s_stack_all[];
-  int const warp      = threadIdx.x >> 5;
-  u32 const lane      = lane_id();
-  u32 const lt        = lanemask_lt();
-  u32* const stack    = s_stack_all + warp * kJoinStackCap;
-  u32 const n_top     = min(st->n_top, (u32)kJoinStackCap);
-  u32 const num_warps = gridDim.x * kJoinWarps;
-
-  // Two launches of this kernel.  Seeding pass (seed_box == nullptr): one warp per (bounding
-  // box, level-0 node) descends to `stop_level`; internal nodes hit there are not expanded but
-  // queued as (box, node) seeds.  Main pass: one warp per seed traverses that subtree.  A box then
-  // spreads over as many warps as it overlaps level-`stop_level` cells instead of serialising its
-  // whole (latency-bound) traversal in one warp.  stop_level < 0: single pass, no queue.
-  bool const seeded = seed_box != nullptr;
-  u64 const n_units = seeded ? (u64)min(st->n_seeds, q_capacity) : (u64)n_boxes * max(n_top, 1u);
-  for (u64 unit = (u64)blockIdx.x * kJoinWarps + warp; unit < n_units; unit += num_warps) {
-    u32 const box = seeded ? __ldg(seed_box + unit) : (u32)(unit / max(n_top, 1u));
-    T const qx0 = __ldg(bx0 + box), qy0 = __ldg(by0 + box);
-    T const qx1 = __ldg(bx1 + box), qy1 = __ldg(by1 + box);
-    if (lane == 0) stack[0] = seeded ? __ldg(seed_node + unit) : (u32)(unit % max(n_top, 1u));
-    u32 sp = (seeded || n_top) ? 1u : 0u;
-    __syncwarp();
-    while (sp > 0) {
-      u32 const take  = min(sp, 32u);
-      u32 const base  = sp - take;
-      bool const have = lane < take;
-      u32 const node  = have ? stack[base + lane] : 0u;
-      sp              = base;
-      __syncwarp();
-
-      bool leaf_hit = false, seed_hit = false;
+  u32 const lane = lane_id();
+  u32 const lt   = lanemask_lt();
+  u32 const n_top = st->n_top;
+  // level 0: every (box, level-0 node) combination, box-major (quadtree_bbox_filtering.cuh:94-102)
+  u64 n_in = (u64)n_boxes * n_top;
+  for (int level = 0; level < max_depth && n_in > 0; ++level) {
+    const uint2* const q_in = (level & 1) ? queue_b : queue_a;
+    uint2* const q_out      = (level & 1) ? queue_a : queue_b;
+    while (true) {
+      u64 base = 0;
+      if (lane == 0) base = level == 0 ? atomicAdd(&st->cursor0, 32ull)
+                                       : (u64)atomicAdd(&st->cursor[level], 32u);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= n_in) break;
+      u64 const i     = base + lane;
+      bool const have = i < n_in;
+      u32 box = 0, node = 0;
+      if (have) {
+        if (level == 0) {
+          box  = (u32)(i / n_top);
+          node = (u32)(i % n_top);
+        } else {
+          uint2 const it = q_in[i];
+          box  = it.x;
+          node = it.y;
+        }
+      }
+      bool leaf_hit = false;
       u32 nchild = 0, child0 = 0;
       if (have) {
+        T const qx0 = __ldg(bx0 + box), qy0 = __ldg(by0 + box);
+        T const qx1 = __ldg(bx1 + box), qy1 = __ldg(by1 + box);
         uint4 const nd   = __ldg(nodes + node);
         u32 const lv     = nd.y & 0xFFu;
         bool const inner = (nd.y >> 8) & 1u;
@@ -133,13 +149,9 @@ traverse_kernel(const uint4* __restrict__ nodes, const T* __restrict__ bx0,
         if (!miss) {
           if (!inner) {
             leaf_hit = true;
-          } else if ((int)lv + 1 < max_depth) {  // quadtree_bbox_filtering.cuh:116 loop bound
-            if (!seeded && (int)lv == stop_level) {
-              seed_hit = true;
-            } else {
-              nchild = nd.z;
-              child0 = nd.w;
-            }
+          } else if (level + 1 < max_depth) {  // quadtree_bbox_filtering.cuh:116 loop bound
+            nchild = min(nd.z, 4u);
+            child0 = nd.w;
           }
         }
       }
@@ -157,37 +169,23 @@ traverse_kernel(const uint4* __restrict__ nodes, const T* __restrict__ bx0,
           }
         }
       }
-      // ---- seeds for the main pass
-      u32 const sm_ = __ballot_sync(0xffffffffu, seed_hit);
-      if (sm_) {
-        u32 qbase = 0;
-        if (lane == 0) qbase = atomicAdd(&st->n_seeds, (u32)__popc(sm_));
-        qbase = __shfl_sync(0xffffffffu, qbase, 0);
-        if (seed_hit) {
-          u32 const o = qbase + __popc(sm_ & lt);
-          if (o < q_capacity) {
-            q_box[o]  = box;
-            q_node[o] = node;
-          } else {
-            st->overflow = 1;  // more level-k nodes than 4^(k+1) per box: malformed tree
-          }
-        }
-      }
-      // ---- children of internal hits go back on the work list
+      // ---- children of internal hits: the next level's queue
       u32 const incl  = warp_inclusive_scan(nchild);
       u32 const total = __shfl_sync(0xffffffffu, incl, 31);
       if (total) {
-        if (sp + total > (u32)kJoinStackCap) {
-          if (lane == 0) st->overflow = 1;
-          sp = 0;  // abandon this box; the host reports the error
-        } else {
-          u32 const at = sp + incl - nchild;
-          for (u32 c = 0; c < nchild; ++c) stack[at + c] = child0 + c;
-          sp += total;
+        u32 qbase = 0;
+        if (lane == 0) qbase = atomicAdd(&st->count[level + 1], total);
+        qbase = __shfl_sync(0xffffffffu, qbase, 0);
+        u64 const at = (u64)qbase + incl - nchild;
+        if (at + nchild <= (u64)q_capacity) {
+          for (u32 c = 0; c < nchild; ++c) q_out[at + c] = make_uint2(box, child0 + c);
+        } else if (nchild) {
+          st->overflow = 1;
         }
       }
-      __syncwarp();
     }
+    grid_barrier(&st->barrier, (u32)level);
+    n_in = min(st->count[level + 1], q_capacity);
   }
 }
 
@@ -226,14 +224,6 @@ void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32*
                  int max_depth, const bsj_allocator* mr, cudaStream_t s, bsj_pairs* out)
 {
   stage_timer tm(s);
-  configure_once_per_device(1, [] {  // per device, not per process
-    BSJ_CUDA_TRY(cudaFuncSetAttribute(traverse_kernel<float>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kJoinWarps * kJoinStackCap * 4));
-    BSJ_CUDA_TRY(cudaFuncSetAttribute(traverse_kernel<double>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kJoinWarps * kJoinStackCap * 4));
-  });
   dev_buf<uint4> nodes(q, s);
   dev_buf<join_state> st(1, s);
   BSJ_CUDA_TRY(cudaMemsetAsync(st.get(), 0, sizeof(join_state), s));
@@ -241,40 +231,41 @@ void join_impl_t(const u32* key, const u8* level, const u8* internal, const u32*
                                                   nodes.get(), st.get());
   BSJ_CHECK_LAUNCH();
 
-  // optimistic capacity; a second traversal runs only if it was too small
-  u64 capacity = std::max<u64>(1u << 20, n_boxes * 64);
+  // The grid barrier needs every CTA resident at once: size the grid from the occupancy.
+  int per_sm = 1;
+  BSJ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_kernel<T>,
+                                                            kJoinBlock, 0));
+  int const grid = std::max(1, std::min(per_sm, 4) * num_sms());
+  // optimistic capacities (pair list and per-level queues); a second traversal runs only if
+  // they were too small
+  u64 capacity = std::min<u64>(std::max<u64>(std::max<u64>(1u << 20, n_boxes * 64), q * 3),
+                               0xFFFFFFF0ull);
   dev_buf<u32> hit_box, hit_node;
+  dev_buf<uint2> queue_a, queue_b;
   join_state h{};
-  int const grid = (int)std::min<u64>((u64)num_sms() * 3, (u64)div_up(n_boxes * 4, kJoinWarps));
-  // seeding level k: at most 4^(k+1) level-k nodes per box; keep the queue below 2^24 entries
-  int stop_level = n_boxes <= (1u << 16) ? 3 : n_boxes <= (1u << 18) ? 2 : 1;
-  if (stop_level + 2 >= max_depth) stop_level = -1;  // shallow tree: one pass does it all
-  u64 const q_cap = stop_level >= 0 ? n_boxes << (2 * (stop_level + 1)) : 0;
-  dev_buf<u32> q_box(std::max<u64>(q_cap, 1), s), q_node(std::max<u64>(q_cap, 1), s);
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = 0; attempt < 3; ++attempt) {
     hit_box.alloc(capacity, s);
     hit_node.alloc(capacity, s);
-    traverse_kernel<T><<<grid, kJoinWarps * 32, kJoinWarps * kJoinStackCap * 4, s>>>(
+    queue_a.alloc(capacity, s);
+    queue_b.alloc(capacity, s);
+    traverse_kernel<T><<<grid, kJoinBlock, 0, s>>>(
       nodes.get(), (const T*)bx0, (const T*)by0, (const T*)bx1, (const T*)by1, (u32)n_boxes,
       (T)x_min, (T)y_min, (T)scale, max_depth, hit_box.get(), hit_node.get(), (u32)capacity,
-      st.get(), nullptr, nullptr, stop_level, q_box.get(), q_node.get(), (u32)q_cap);
+      st.get(), queue_a.get(), queue_b.get(), (u32)capacity);
     BSJ_CHECK_LAUNCH();
-    if (stop_level >= 0) {
-      traverse_kernel<T><<<num_sms() * 3, kJoinWarps * 32, kJoinWarps * kJoinStackCap * 4, s>>>(
-        nodes.get(), (const T*)bx0, (const T*)by0, (const T*)bx1, (const T*)by1, (u32)n_boxes,
-        (T)x_min, (T)y_min, (T)scale, max_depth, hit_box.get(), hit_node.get(), (u32)capacity,
-        st.get(), q_box.get(), q_node.get(), -1, nullptr, nullptr, (u32)q_cap);
-      BSJ_CHECK_LAUNCH();
-    }
     BSJ_CUDA_TRY(cudaMemcpyAsync(&h, st.get(), sizeof(h), cudaMemcpyDeviceToHost, s));
     BSJ_CUDA_TRY(cudaStreamSynchronize(s));
-    if (h.overflow)
+    u64 need = h.n_hits;
+    for (int L = 0; L < 17; ++L) need = std::max<u64>(need, h.count[L]);
+    if (!h.overflow && need <= capacity) break;
+    if (attempt == 2 || capacity >= 0xFFFFFFF0ull)
       throw error(BSJ_INVALID_ARGUMENT,
                   "quadtree traversal work list overflow (malformed quadtree table?)");
-    if (h.n_hits <= capacity) break;
-    capacity = h.n_hits;
-    BSJ_CUDA_TRY(cudaMemsetAsync(&st.get()->n_hits, 0, sizeof(u32), s));
-    BSJ_CUDA_TRY(cudaMemsetAsync(&st.get()->n_seeds, 0, sizeof(u32), s));
+    // a truncated level under-reports the levels below it: grow generously
+    capacity = std::min<u64>(std::max<u64>(need, capacity) * 4, 0xFFFFFFF0ull);
+    u32 const n_top = h.n_top;
+    BSJ_CUDA_TRY(cudaMemsetAsync(st.get(), 0, sizeof(join_state), s));
+    BSJ_CUDA_TRY(cudaMemcpyAsync(&st.get()->n_top, &n_top, sizeof(u32), cudaMemcpyHostToDevice, s));
   }
   tm.mark("traverse");
   u64 const p = h.n_hits;

@@ -33,6 +33,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 namespace bsj {
 
@@ -318,28 +319,33 @@ struct edge_index {  // device view of the per-call polygon edge index
 // key range stay on the ranks that own them and only (key, id) pairs were exchanged; `id` is then
 // a GLOBAL id and the coordinates are read from the owning rank's columns through peer pointers
 // (NVLink) -- only for the few points that need the exact predicate.
+template <typename T, bool SEG>
+struct coord_source;
 template <typename T>
-struct coord_source {
+struct coord_source<T, false> {
   const T* x;
   const T* y;
-  u32 n_ids;   // ids are valid below this
-  int n_seg;   // 0: x/y above; otherwise ids first_id[s] .. first_id[s+1]-1 live in segment s
+  u32 n_ids;  // ids are valid below this
+  __device__ __forceinline__ void load(u32 id, T& ox, T& oy) const
+  {
+    ox = __ldg(x + id);
+    oy = __ldg(y + id);
+  }
+};
+template <typename T>
+struct coord_source<T, true> {
+  u32 n_ids;
+  int n_seg;  // ids first_id[s] .. first_id[s+1]-1 live in segment s
   u32 first_id[BSJ_MAX_RANKS + 1];
   const T* sx[BSJ_MAX_RANKS];
   const T* sy[BSJ_MAX_RANKS];
-
   __device__ __forceinline__ void load(u32 id, T& ox, T& oy) const
   {
-    if (n_seg == 0) {
-      ox = __ldg(x + id);
-      oy = __ldg(y + id);
-    } else {
-      int sgm = 0;
-      while (sgm + 1 < n_seg && id >= first_id[sgm + 1]) ++sgm;
-      u32 const j = id - first_id[sgm];
-      ox = sx[sgm][j];
-      oy = sy[sgm][j];
-    }
+    int sgm = 0;
+    while (sgm + 1 < n_seg && id >= first_id[sgm + 1]) ++sgm;
+    u32 const j = id - first_id[sgm];
+    ox = sx[sgm][j];  // possibly a peer GPU's memory: plain (coherent) loads
+    oy = sy[sgm][j];
   }
 };
 
@@ -440,7 +446,7 @@ __device__ int classify_quadrant(const grid_info& g, u32 key, u32 level, const p
 __global__ void __launch_bounds__(256)
 pair_prep_kernel(const u32* __restrict__ pair_quad, u32 n_pairs, const u32* __restrict__ length,
                  const u32* __restrict__ offset, u32 num_nodes, u32* __restrict__ words,
-                 u32* __restrict__ heads, u32* __restrict__ pair_len, u32* __restrict__ pair_off)
+                 u32* __restrict__ pair_len, u32* __restrict__ pair_off)
 {
   u32 const j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_pairs) return;
@@ -449,7 +455,6 @@ pair_prep_kernel(const u32* __restrict__ pair_quad, u32 n_pairs, const u32* __re
   pair_len[j]   = len;
   pair_off[j]   = q < num_nodes ? offset[q] : 0u;
   words[j]      = len / 32 + ((len & 31) != 0);
-  heads[j]      = (j == 0 || pair_quad[j - 1] != q) ? 1u : 0u;
 }
 
 __global__ void __launch_bounds__(256)
@@ -459,22 +464,16 @@ narrow_u64_kernel(const u64* __restrict__ in, u32* __restrict__ out, u32 n)
   if (i < n) out[i] = (u32)in[i];
 }
 
-__global__ void __launch_bounds__(256)
-run_start_kernel(const u32* __restrict__ heads, const u64* __restrict__ run_idx, u32 n_pairs,
-                 const u64* __restrict__ n_runs, u32* __restrict__ run_start)
-{
-  u32 const j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_pairs) return;
-  if (heads[j]) run_start[run_idx[j]] = j;
-  if (j == n_pairs - 1) run_start[*n_runs] = n_pairs;
-}
-
 // ---------------------------------------------------------------------------------------------
-// evaluation: one warp per run of pairs sharing a quadrant
+// evaluation: one warp per (pair, point tile) unit
 // ---------------------------------------------------------------------------------------------
 constexpr int kPipWarps = 4;
 constexpr int kPPL      = 8;          // points per lane
 constexpr int kPipTile  = 32 * kPPL;  // points per tile
+
+// exact predicate of one point through the y-slab index (defined with the bitmask kernel below)
+template <typename T>
+__device__ bool pip_indexed(T px, T py, const poly_meta<T>& m, const edge_index<T>& ix);
 
 // Stage 1 of the evaluation: one warp per (polygon, quadrant) pair decides whole quadrants from
 // their cell rectangle (classify_quadrant).  Pairs are independent, so the grid keeps every SM
@@ -483,22 +482,24 @@ constexpr int kPipTile  = 32 * kPPL;  // points per tile
 template <typename T>
 __global__ void __launch_bounds__(256)
 pip_classify_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad,
-                    u32 n_pairs, const u32* __restrict__ heads, const u64* __restrict__ run_idx,
-                    const u32* __restrict__ length, const u32* __restrict__ offset, u32 num_nodes,
+                    u32 n_pairs, const u32* __restrict__ length,
+                    const u32* __restrict__ offset, u32 num_nodes,
                     u32 n_points, const poly_meta<T>* __restrict__ meta, u32 n_poly,
                     int force_reference, const u32* __restrict__ node_key,
                     const u8* __restrict__ node_level, grid_info grid, edge_index<T> ix,
-                    u8* __restrict__ cls, u32* __restrict__ hits, u32* __restrict__ run_flag,
-                    u32* __restrict__ run_list, u32* __restrict__ run_count)
+                    u8* __restrict__ cls, u32* __restrict__ hits,
+                    u32* __restrict__ run_list, u32* __restrict__ tile_list,
+                    u32* __restrict__ run_count, u32 tile_points, u32 list_capacity)
 {
   u32 const lane  = lane_id();
   u32 const warps = (gridDim.x * blockDim.x) >> 5;
   for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_pairs; j += warps) {
     u32 const quad = pair_quad[j];
     int c          = kClsOutside;
-    u32 nvalid     = 0;
+    u32 nvalid = 0, qlen = 0;
     if (quad < num_nodes) {
       u32 const len = length[quad], off = offset[quad];
+      qlen          = len;
       nvalid        = off < n_points ? min(len, n_points - off) : 0u;
       u32 const poly = pair_poly[j];
       if (len != 0 && poly < n_poly) {
@@ -508,26 +509,41 @@ pip_classify_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ p
               : kClsBoundary;
       }
     }
+    // Stage 2 works on (pair, point tile) units: bounded work per unit (one polygon against one
+    // tile) whatever the data looks like -- a dense bottom-level leaf that cannot split (many
+    // tiles) or a large sparse quadrant under hundreds of polygon boxes (many pairs) spreads over
+    // many warps instead of serialising in one.
+    u32 base = 0, n_tiles = 0;
     if (lane == 0) {
       cls[j]  = (u8)c;
-      hits[j] = c == kClsInside ? nvalid : 0u;  // boundary pairs are counted by stage 2
+      hits[j] = c == kClsInside ? nvalid : 0u;  // boundary pairs: stage 2 adds its counts
       if (c == kClsBoundary) {
-        u32 const run = (u32)run_idx[j] - (heads[j] ? 0u : 1u);
-        if (atomicExch(&run_flag[run], 1u) == 0u) run_list[atomicAdd(run_count, 1u)] = run;
+        n_tiles = max(1u, qlen / tile_points + (qlen % tile_points != 0));
+        base    = atomicAdd(run_count, n_tiles);
       }
+    }
+    n_tiles = __shfl_sync(0xffffffffu, n_tiles, 0);
+    if (n_tiles) {
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (u32 t = lane; t < n_tiles; t += 32)
+        if (base + t < list_capacity) {
+          run_list[base + t]  = j;
+          tile_list[base + t] = t;
+        }
     }
   }
 }
 
 // Stage 2: one warp per listed quadrant gathers its points once and tests them against every
 // polygon of the run that stage 1 left undecided.
-template <typename T>
+template <typename T, bool SEG>
 __global__ void __launch_bounds__(kPipWarps * 32)
 pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad,
-                const u32* __restrict__ run_start, const u32* __restrict__ run_list,
+                const u32* __restrict__ run_list,
+                const u32* __restrict__ tile_list, u32 list_capacity,
                 const u32* __restrict__ run_count, const u32* __restrict__ length,
                 const u32* __restrict__ offset, const u32* __restrict__ point_indices,
-                u32 n_points, coord_source<T> const pts,
+                u32 n_points, coord_source<T, SEG> const pts,
                 const poly_meta<T>* __restrict__ meta, u32 n_poly,
                 const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
                 const T* __restrict__ vy, const u64* __restrict__ wbase,
@@ -535,20 +551,19 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
                 int force_reference, const u8* __restrict__ cls, edge_index<T> ix)
 {
   u32 const lane   = lane_id();
-  u32 const n_list = *run_count;
+  u32 const n_list = min(*run_count, list_capacity);
 
   while (true) {
     u32 slot = 0;
     if (lane == 0) slot = atomicAdd(ticket, 1u);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot >= n_list) break;
-    u32 const r = run_list[slot];
-
-    u32 const j0 = run_start[r], j1 = run_start[r + 1];
+    u32 const j0 = run_list[slot], j1 = j0 + 1;  // one (pair, tile) unit per slot
     u32 const quad = pair_quad[j0];
     u32 const len = length[quad], off = offset[quad];
 
-    for (u32 base = 0; base < len; base += kPipTile) {
+    {
+      u32 const base = tile_list[slot] * kPipTile;
       // ---- gather this tile's points once (quadtree_point_in_polygon.cuh:66,170)
       u32 idx[kPPL];
       u32 valid = 0;
@@ -632,12 +647,21 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
                   }
                 }
               };
+              u32 kbeg = 0, kmid = 0, kend = 0;
               if (m.n_slabs) {
                 // candidate edges from the y-slab index (slabs covering the tile's y-range)
                 u32 const q0 = slab_of<T>(ty0, m), q1 = slab_of<T>(ty1, m);
-                u32 const kbeg = __ldg(ix.slab_start + m.slab_base + q0);
-                u32 const kmid = __ldg(ix.slab_start + m.slab_base + q0 + 1);
-                u32 const kend = __ldg(ix.slab_start + m.slab_base + q1 + 1);
+                kbeg = __ldg(ix.slab_start + m.slab_base + q0);
+                kmid = __ldg(ix.slab_start + m.slab_base + q0 + 1);
+                kend = __ldg(ix.slab_start + m.slab_base + q1 + 1);
+              }
+              if (m.n_slabs && kend - kbeg > 64u) {
+                // a tile spanning most of the polygon's height (large, sparse quadrant): each
+                // point through its own slab instead of every edge over the whole warp
+#pragma unroll
+                for (int i = 0; i < kPPL; ++i)
+                  if ((valid >> i) & 1u) within |= (u32)pip_indexed<T>(x[i], y[i], m, ix) << i;
+              } else if (m.n_slabs) {
                 for (u32 k0 = kbeg; k0 < kend; k0 += 32) {
                   u32 const k = k0 + lane;
                   T ax = 0, ay = 0, bx = 0, by = 0;
@@ -713,7 +737,7 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
           cnt += __popc(w);
         }
         if (lane < tile_words) mask_words[wbase[j] + base / 32 + lane] = mine;
-        if (lane == 0) hits[j] = (base == 0 ? 0u : hits[j]) + cnt;
+        if (lane == 0 && cnt) atomicAdd(&hits[j], cnt);
       }
     }
   }
@@ -734,14 +758,21 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
 // ---------------------------------------------------------------------------------------------
 constexpr int kCellPPL  = 4;
 constexpr int kCellTile = 32 * kCellPPL;
+// (tile, polygon) combinations with more candidate edges than this are evaluated point by point
+// through the y-slab index instead of edge by edge over the whole warp: a tile of a LARGE, sparse
+// quadrant spans most of the polygon's height, and walking every edge for every point costs
+// ~100x what the two or three edges of each point's own slab cost
+constexpr u32 kCoopEdges = 64;
 
-template <typename T>
+
+template <typename T, bool SEG>
 __global__ void __launch_bounds__(kPipWarps * 32, 4)
 pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad,
-                      const u32* __restrict__ run_start, const u32* __restrict__ run_list,
+                      const u32* __restrict__ run_list,
+                      const u32* __restrict__ tile_list, u32 list_capacity,
                       const u32* __restrict__ run_count, const u32* __restrict__ length,
                       const u32* __restrict__ offset, const u32* __restrict__ point_indices,
-                      u32 n_points, coord_source<T> const pts,
+                      u32 n_points, coord_source<T, SEG> const pts,
                       const poly_meta<T>* __restrict__ meta, u32 n_poly,
                       const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
                       const T* __restrict__ vy, const u64* __restrict__ wbase,
@@ -750,23 +781,26 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                       grid_info grid, const u32* __restrict__ sorted_keys)
 {
   u32 const lane   = lane_id();
-  u32 const n_list = *run_count;
+  u32 const n_list = min(*run_count, list_capacity);
   double const hw  = 0.5 * grid.scale + grid.margin_x;  // half extents of a widened finest cell
   double const hh  = 0.5 * grid.scale + grid.margin_y;
   u32 const oob_key = grid.max_depth >= 16 ? 0xFFFFFFFFu : ((1u << (2 * grid.max_depth)) - 1u);
   double const eps  = (double)fpp<T>::eps();
+  // relative allowance on the centre's line function f = v - u: the reference evaluates u and v
+  // in T (products rounded separately) and calls them equal within 4 ULP -- 5e-7 |u| for float
+  double const allow = sizeof(T) == 4 ? 2e-6 : 1e-9;
 
   while (true) {
     u32 slot = 0;
     if (lane == 0) slot = atomicAdd(ticket, 1u);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot >= n_list) break;
-    u32 const r  = run_list[slot];
-    u32 const j0 = run_start[r], j1 = run_start[r + 1];
+    u32 const j0 = run_list[slot], j1 = j0 + 1;  // one (pair, tile) unit per slot
     u32 const quad = pair_quad[j0];
     u32 const len = length[quad], off = offset[quad];
 
-    for (u32 base = 0; base < len; base += kCellTile) {
+    {
+      u32 const base = tile_list[slot] * kCellTile;
       u32 valid = 0, oob = 0;
       double cx[kCellPPL], cy[kCellPPL];
 #pragma unroll
@@ -855,6 +889,66 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                        ty0 <= fmax((double)ay, (double)by) + dl &&
                        fmax((double)ax, (double)bx) + dxl >= tx0;
               };
+              if (kend - kbeg > kCoopEdges) {
+                // ---- point-by-point form (many candidate edges: a large, sparse quadrant)
+                u32 cross = 0, near = oob;
+#pragma unroll
+                for (int i = 0; i < kCellPPL; ++i) {
+                  if (!((valid >> i) & 1u)) continue;
+                  double const pcx = cx[i], pcy = cy[i];
+                  // the point's cell clear of the polygon's (tolerance-widened) box: no edge can
+                  // touch it and the crossing parity out there is even
+                  if (pcx + hw < (double)m.xmin - dx || pcx - hw > (double)m.xmax + dx ||
+                      pcy + hh < (double)m.ymin - dy || pcy - hh > (double)m.ymax + dy)
+                    continue;
+                  u32 const s0 = slab_of<T>((T)(pcy - hh), m), s1 = slab_of<T>((T)(pcy + hh), m);
+                  u32 const pb = __ldg(ix.slab_start + m.slab_base + s0);
+                  u32 const pm = __ldg(ix.slab_start + m.slab_base + s0 + 1);
+                  u32 const pe = __ldg(ix.slab_start + m.slab_base + s1 + 1);
+                  for (u32 k = pb; k < pe; ++k) {
+                    u32 const ent = __ldg(ix.entries + k);
+                    if (k >= pm && !(ent & kFirstFlag)) continue;
+                    edge_rec<T> const e = ix.edges[ent & ~kFirstFlag];
+                    double const eax = (double)e.ax, eay = (double)e.ay;
+                    double const ebx = (double)e.bx, eby = (double)e.by;
+                    double const d =
+                      eps * fmax(fmax(fabs(eax), fabs(ebx)), fmax(fabs(eay), fabs(eby)));
+                    if (fmax(eax, ebx) + d < pcx - hw) continue;  // wholly left: cannot matter
+                    double const run = ebx - eax, rise = eby - eay;
+                    double const ddx = pcx - eax, ddy = pcy - eay;
+                    double const f   = ddx * rise - run * ddy;
+                    double const thr = (fabs(rise) * hw + fabs(run) * hh) * 1.000001 +
+                                       allow * (fabs(ddx) * fabs(rise) + fabs(run) * fabs(ddy));
+                    bool const touch = fabs(f) <= thr && pcx >= fmin(eax, ebx) - d - hw &&
+                                       pcx <= fmax(eax, ebx) + d + hw &&
+                                       pcy >= fmin(eay, eby) - d - hh &&
+                                       pcy <= fmax(eay, eby) + d + hh;
+                    near |= (u32)touch << i;
+                    bool const y1 = eay > pcy, y0 = eby > pcy;
+                    cross ^= (u32)((y1 != y0) && ((f < 0.0) != y1)) << i;
+                  }
+                  for (u32 k = 0; k < m.n_vertical; ++k) {  // x-only rule of vertical edges
+                    double const ax = (double)ix.edges[__ldg(ix.vert_edges + m.vert_begin + k)].ax;
+                    near |= (u32)(ax >= pcx - hw && ax <= pcx + hw) << i;
+                  }
+                }
+                near &= valid;
+                inside = cross & ~near;
+                if (near) {  // touched points: their real coordinates, the reference's arithmetic
+                  load_points(near);
+                  near &= valid;
+                  inside &= ~near;
+#pragma unroll
+                  for (int i = 0; i < kCellPPL; ++i)
+                    if ((near >> i) & 1u) {
+                      bool const in = ((unsafe_pt >> i) & 1u)
+                                        ? pip_reference<T>(xr[i], yr[i], ring_offsets, m.ring_begin,
+                                                           m.ring_end, vx, vy)
+                                        : pip_indexed<T>(xr[i], yr[i], m, ix);
+                      inside |= (u32)in << i;
+                    }
+                }
+              } else {
               // ---- pass 1: crossing parity of the cell centres + "an edge touches my cell"
               u32 cross = 0, near = oob;
               for (u32 k0 = kbeg; k0 < kend; k0 += 32) {
@@ -878,7 +972,7 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                   double const mdx = fmax(fabs(tx0 - eax), fabs(tx1 - eax));
                   double const mdy = fmax(fabs(ty0 - eay), fabs(ty1 - eay));
                   double const thr = (fabs(rise) * hw + fabs(run) * hh) * 1.000001 +
-                                     1e-9 * (mdx * fabs(rise) + fabs(run) * mdy);
+                                     allow * (mdx * fabs(rise) + fabs(run) * mdy);
 #pragma unroll
                   for (int i = 0; i < kCellPPL; ++i) {
                     double const ddx = cx[i] - eax, ddy = cy[i] - eay;
@@ -975,6 +1069,7 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                                                       m.ring_end, vx, vy) << i;
                 }
               }
+              }  // warp-cooperative form
             }
           }
         }
@@ -987,7 +1082,7 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
           cnt += __popc(w);
         }
         if (lane < tile_words) mask_words[wbase[j] + base / 32 + lane] = mine;
-        if (lane == 0) hits[j] = (base == 0 ? 0u : hits[j]) + cnt;
+        if (lane == 0 && cnt) atomicAdd(&hits[j], cnt);
       }
     }
   }
@@ -1347,20 +1442,22 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
                     bsj_pip_compact* c)
 {
   u32 const n_poly = (u32)(n_poly_offsets - 1);
-  coord_source<T> pts{};
+  coord_source<T, false> pts{};
   pts.x = (const T*)px;
   pts.y = (const T*)py;
   pts.n_ids = (u32)n_points;
-  if (segs && segs->n_segments > 0) {
+  coord_source<T, true> spts{};
+  bool const segmented = segs && segs->n_segments > 0;
+  if (segmented) {
     BSJ_EXPECTS(segs->n_segments <= BSJ_MAX_RANKS, "too many coordinate segments");
-    pts.n_seg = segs->n_segments;
+    spts.n_seg = segs->n_segments;
     for (int i = 0; i < segs->n_segments; ++i) {
-      pts.first_id[i] = segs->first_id[i];
-      pts.sx[i]       = (const T*)segs->x[i];
-      pts.sy[i]       = (const T*)segs->y[i];
+      spts.first_id[i] = segs->first_id[i];
+      spts.sx[i]       = (const T*)segs->x[i];
+      spts.sy[i]       = (const T*)segs->y[i];
     }
-    pts.first_id[segs->n_segments] = segs->first_id[segs->n_segments];
-    pts.n_ids                      = segs->first_id[segs->n_segments];
+    spts.first_id[segs->n_segments] = segs->first_id[segs->n_segments];
+    spts.n_ids                      = segs->first_id[segs->n_segments];
   }
   grid_info gi{};
   {
@@ -1403,55 +1500,65 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
   c->pair_class     = oa.get<u8>(n_pairs);
   c->pair_word_base = oa.get<u64>(n_pairs);
   c->pair_row_base  = oa.get<u64>(n_pairs);
-  dev_buf<u32> words(n_pairs, s), heads(n_pairs, s), run_start(n_pairs + 1, s);
-  dev_buf<u64> run_idx(n_pairs, s), totals(4, s);
+  dev_buf<u32> words(n_pairs, s);
+  dev_buf<u64> totals(4, s);
   dev_buf<u32> ticket(1, s);
   BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
   pair_prep_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(pair_quad, (u32)n_pairs, length, offset,
-                                                        (u32)num_nodes, words.get(), heads.get(),
+                                                        (u32)num_nodes, words.get(),
                                                         c->pair_length, c->pair_offset);
   BSJ_CHECK_LAUNCH();
   exclusive_scan_u32_to_u64(words.get(), c->pair_word_base, n_pairs, totals.get() + 0, s);
-  exclusive_scan_u32_to_u64(heads.get(), run_idx.get(), n_pairs, totals.get() + 1, s);
-  run_start_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(heads.get(), run_idx.get(), (u32)n_pairs,
-                                                        totals.get() + 1, run_start.get());
-  BSJ_CHECK_LAUNCH();
-  u64 h_tot[2] = {0, 0};
-  BSJ_CUDA_TRY(cudaMemcpyAsync(h_tot, totals.get(), 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  u64 h_tot[1] = {0};
+  BSJ_CUDA_TRY(cudaMemcpyAsync(h_tot, totals.get(), sizeof(u64), cudaMemcpyDeviceToHost, s));
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
-  u64 const total_words = h_tot[0], n_runs = h_tot[1];
+  u64 const total_words = h_tot[0];
   edge_index<T> ix = pidx.finish(s);
   prof_mark("pair_prep");
 
   c->n_words    = total_words;
   c->mask_words = oa.get<u32>(std::max<u64>(total_words, 1));
+  // words of settled pairs are never read; zeroing keeps malformed pair tables deterministic
+  BSJ_CUDA_TRY(cudaMemsetAsync(c->mask_words, 0, std::max<u64>(total_words, 1) * sizeof(u32), s));
   {
-    dev_buf<u32> run_flag(n_runs + 1, s), run_list(n_runs + 1, s), run_count(1, s);
-    BSJ_CUDA_TRY(cudaMemsetAsync(run_flag.get(), 0, (n_runs + 1) * sizeof(u32), s));
+    bool const cells = force_reference_mode() == 0 && gi.valid && gi.sorted_keys;
+    u32 const tile_points = cells ? (u32)kCellTile : (u32)kPipTile;
+    // (pair, tile) units of the boundary pairs: at most every tile of every pair
+    u64 const list_cap = total_words * 32 / tile_points + n_pairs + 2;
+    dev_buf<u32> run_list(list_cap, s), tile_list(list_cap, s), run_count(1, s);
     BSJ_CUDA_TRY(cudaMemsetAsync(run_count.get(), 0, sizeof(u32), s));
     int const cgrid = (int)std::min<u64>((u64)num_sms() * 16, (u64)div_up(n_pairs * 32, 256));
     pip_classify_kernel<T><<<std::max(cgrid, 1), 256, 0, s>>>(
-      pair_poly, pair_quad, (u32)n_pairs, heads.get(), run_idx.get(), length, offset,
-      (u32)num_nodes, (u32)n_points, meta.get(), n_poly, force_reference_mode(), node_key,
-      node_level, gi, ix, c->pair_class, c->pair_hits, run_flag.get(), run_list.get(),
-      run_count.get());
+      pair_poly, pair_quad, (u32)n_pairs, length, offset, (u32)num_nodes, (u32)n_points,
+      meta.get(), n_poly, force_reference_mode(), node_key, node_level, gi, ix, c->pair_class,
+      c->pair_hits, run_list.get(), tile_list.get(), run_count.get(), tile_points,
+      (u32)std::min<u64>(list_cap, 0xFFFFFFFFull));
     BSJ_CHECK_LAUNCH();
     prof_mark("pip_classify");
-    if (force_reference_mode() == 0 && gi.valid && gi.sorted_keys) {
-      int const grid_dim = (int)std::min<u64>((u64)num_sms() * 8, (u64)div_up(n_runs, kPipWarps));
-      pip_eval_cells_kernel<T><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
-        pair_poly, pair_quad, run_start.get(), run_list.get(), run_count.get(), length, offset,
-        point_indices, (u32)n_points, pts, meta.get(), n_poly,
-        ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words, c->pair_hits,
-        ticket.get(), c->pair_class, ix, gi, gi.sorted_keys);
+    u32 const list_cap32 = (u32)std::min<u64>(list_cap, 0xFFFFFFFFull);
+    if (cells) {
+      int const grid_dim = (int)std::min<u64>((u64)num_sms() * 8, (u64)div_up(list_cap, kPipWarps));
+      auto launch = [&](auto const& src) {
+        constexpr bool SEG = std::is_same<std::decay_t<decltype(src)>, coord_source<T, true>>::value;
+        pip_eval_cells_kernel<T, SEG><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
+          pair_poly, pair_quad, run_list.get(), tile_list.get(), list_cap32,
+          run_count.get(), length, offset, point_indices, (u32)n_points, src, meta.get(), n_poly,
+          ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words,
+          c->pair_hits, ticket.get(), c->pair_class, ix, gi, gi.sorted_keys);
+      };
+      if (segmented) launch(spts); else launch(pts);
       BSJ_CHECK_LAUNCH();
     } else if (force_reference_mode() != 2) {  // 2: timing experiment, classification only
-      int const grid_dim = (int)std::min<u64>((u64)num_sms() * 8, (u64)div_up(n_runs, kPipWarps));
-      pip_eval_kernel<T><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
-        pair_poly, pair_quad, run_start.get(), run_list.get(), run_count.get(), length, offset,
-        point_indices, (u32)n_points, pts, meta.get(), n_poly,
-        ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words, c->pair_hits,
-        ticket.get(), force_reference_mode(), c->pair_class, ix);
+      int const grid_dim = (int)std::min<u64>((u64)num_sms() * 8, (u64)div_up(list_cap, kPipWarps));
+      auto launch = [&](auto const& src) {
+        constexpr bool SEG = std::is_same<std::decay_t<decltype(src)>, coord_source<T, true>>::value;
+        pip_eval_kernel<T, SEG><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
+          pair_poly, pair_quad, run_list.get(), tile_list.get(), list_cap32,
+          run_count.get(), length, offset, point_indices, (u32)n_points, src, meta.get(), n_poly,
+          ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words,
+          c->pair_hits, ticket.get(), force_reference_mode(), c->pair_class, ix);
+      };
+      if (segmented) launch(spts); else launch(pts);
       BSJ_CHECK_LAUNCH();
     }
   }

@@ -134,24 +134,79 @@ def uniform_points_torch(n, extent, seed, dtype, device):
     return x, y
 
 
-def clustered_points_torch(n, extent, seed, dtype, device, components=64):
-    import torch
-
+def mixture_parameters(extent, seed, components=64):
+    """The Gaussian mixture of BASELINE.json configs[3]: centres uniform in
+    the box, sigma log-uniform in [0.2 %, 5 %] of the extent, Dirichlet(1) weights."""
     rng = np.random.default_rng(seed)
     x0, x1, y0, y1 = extent
-    w = torch.tensor(rng.dirichlet(np.ones(components)), device=device, dtype=torch.float32)
-    cx = torch.tensor(rng.uniform(x0, x1, components), device=device, dtype=torch.float64)
-    cy = torch.tensor(rng.uniform(y0, y1, components), device=device, dtype=torch.float64)
-    sig = torch.tensor(np.exp(rng.uniform(math.log(0.002), math.log(0.05), components)),
-                       device=device, dtype=torch.float64)
+    w = rng.dirichlet(np.ones(components))
+    cx = rng.uniform(x0, x1, components)
+    cy = rng.uniform(y0, y1, components)
+    sig = np.exp(rng.uniform(math.log(0.002), math.log(0.05), components))
+    return w, cx, cy, sig
+
+
+def clustered_points_torch(n, extent, seed, dtype, device, components=64, mixture_seed=None,
+                           out=None, chunk=1 << 26):
+    """`n` samples of the mixture, generated on the device in chunks (bounded temporaries: a
+    1 G-point cloud needs no more than its own 16 GB).  Samples falling outside the box are folded
+    back into it (wrap-around), then clamped to the half-open box of `dtype`.  `mixture_seed`
+    fixes the mixture independently of the sample stream (ranks of a sharded run draw different
+    samples of the SAME mixture); `out` = (x, y) tensors to fill in place."""
+    import torch
+
+    x0, x1, y0, y1 = extent
+    w, cx, cy, sig = mixture_parameters(extent, seed if mixture_seed is None else mixture_seed,
+                                        components)
+    w = torch.tensor(w, device=device, dtype=torch.float32)
+    cx = torch.tensor(cx, device=device, dtype=torch.float64)
+    cy = torch.tensor(cy, device=device, dtype=torch.float64)
+    sig = torch.tensor(sig, device=device, dtype=torch.float64)
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    comp = torch.multinomial(w, n, replacement=True, generator=g)
-    x = cx[comp] + torch.randn(n, generator=g, device=device, dtype=torch.float64) * sig[comp] * (x1 - x0)
-    y = cy[comp] + torch.randn(n, generator=g, device=device, dtype=torch.float64) * sig[comp] * (y1 - y0)
-    x = x0 + torch.remainder(x - x0, x1 - x0)
-    y = y0 + torch.remainder(y - y0, y1 - y0)
     npdt = np.dtype(str(dtype).split(".")[-1]).type
-    x = x.to(dtype).clamp_(min=float(npdt(x0)), max=float(np.nextafter(npdt(x1), -np.inf)))
-    y = y.to(dtype).clamp_(min=float(npdt(y0)), max=float(np.nextafter(npdt(y1), -np.inf)))
-    return x, y
+    lo_x, hi_x = float(npdt(x0)), float(np.nextafter(npdt(x1), -np.inf))
+    lo_y, hi_y = float(npdt(y0)), float(np.nextafter(npdt(y1), -np.inf))
+    if out is None:
+        out = (torch.empty(n, dtype=dtype, device=device), torch.empty(n, dtype=dtype, device=device))
+    ox, oy = out
+    for a in range(0, n, chunk):
+        m = min(chunk, n - a)
+        comp = torch.multinomial(w, m, replacement=True, generator=g)
+        s = sig[comp]
+        x = cx[comp] + torch.randn(m, generator=g, device=device, dtype=torch.float64) * s * (x1 - x0)
+        y = cy[comp] + torch.randn(m, generator=g, device=device, dtype=torch.float64) * s * (y1 - y0)
+        del comp, s
+        x = x0 + torch.remainder(x - x0, x1 - x0)
+        y = y0 + torch.remainder(y - y0, y1 - y0)
+        ox[a: a + m] = x.to(dtype).clamp_(min=lo_x, max=hi_x)
+        oy[a: a + m] = y.to(dtype).clamp_(min=lo_y, max=hi_y)
+        del x, y
+    return ox, oy
+
+
+def nested_rectangle_points(size, seed=0, dtype=np.float64):
+    """The reference's quadtree benchmark cloud (cpp/benchmarks/indexing/quadtree_on_points.cu:
+    33-100): golden-ratio nested rectangles inside [0, size]^2, sqrt(area * 1e6) uniform points
+    in each -- ever denser towards the spiral's centre.  Returns (x, y)."""
+    phi = (1 + math.sqrt(5)) * 0.5
+    tl, br = [0.0, 0.0], [float(size), float(size)]
+    rng = np.random.default_rng(seed)
+    xs, ys, k = [], [], 0
+    while True:
+        if k % 4 == 0:
+            br[0] = tl[0] - (tl[0] - br[0]) / phi
+        elif k % 4 == 1:
+            br[1] = tl[1] - (tl[1] - br[1]) / phi
+        elif k % 4 == 2:
+            tl[0] = tl[0] + (br[0] - tl[0]) / phi
+        else:
+            tl[1] = tl[1] + (br[1] - tl[1]) / phi
+        ax, ay = br[0] - tl[0], br[1] - tl[1]
+        m = int(math.sqrt(ax * ay * 1_000_000))
+        xs.append(tl[0] + ax * rng.random(m))
+        ys.append(tl[1] + ay * rng.random(m))
+        k += 1
+        if not (ax > 1 and ay > 1):
+            break
+    return np.concatenate(xs).astype(dtype), np.concatenate(ys).astype(dtype)

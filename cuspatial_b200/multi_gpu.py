@@ -181,31 +181,39 @@ class ShardedPoints:
         return int(self.x.shape[0])
 
 
-def register_points(x, y, group=None):
-    """Copy (x, y) into symmetric memory and exchange sizes + peer pointers.  A setup step (one
-    host-synchronising all-gather): do it once per point set, outside any timed region, and write
-    new coordinates into `.x` / `.y` in place when the set changes but its size does not."""
+def allocate_points(n, dtype, device, group=None):
+    """Point columns of length `n` in symmetric memory (uninitialised; fill `.x` / `.y` in place),
+    with the sizes and peer pointers of every rank.  A setup step (one host-synchronising
+    all-gather): do it once per point set, outside any timed region."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    dev = x.device
-    n = torch.tensor([x.shape[0]], dtype=torch.int64, device=dev)
-    all_n = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(all_n, n, group=group)
+    dev = torch.device(device)
+    nt = torch.tensor([n], dtype=torch.int64, device=dev)
+    all_n = [torch.zeros_like(nt) for _ in range(world)]
+    dist.all_gather(all_n, nt, group=group)
     sizes = [int(v.item()) for v in all_n]
     if sum(sizes) >= 2 ** 32 - 2 ** 14:
         raise ValueError("total number of points must fit uint32 global indices")
     cap = max(max(sizes), 1)
-    ex = _symm_alloc(dev, x.dtype, cap, group, "points_x")
-    ey = _symm_alloc(dev, x.dtype, cap, group, "points_y")
-    sx, sy = ex["buf"][: x.shape[0]], ey["buf"][: x.shape[0]]
-    sx.copy_(x)
-    sy.copy_(y)
-    px = [ex["hdl"].get_buffer(r, (ex["cap"],), x.dtype).data_ptr() for r in range(world)]
-    py = [ey["hdl"].get_buffer(r, (ey["cap"],), x.dtype).data_ptr() for r in range(world)]
-    torch.cuda.synchronize(dev)
+    ex = _symm_alloc(dev, dtype, cap, group, "points_x")
+    ey = _symm_alloc(dev, dtype, cap, group, "points_y")
+    px = [ex["hdl"].get_buffer(r, (ex["cap"],), dtype).data_ptr() for r in range(world)]
+    py = [ey["hdl"].get_buffer(r, (ey["cap"],), dtype).data_ptr() for r in range(world)]
+    return ShardedPoints(ex["buf"][:n], ey["buf"][:n], sizes, group, px, py)
+
+
+def register_points(x, y, group=None):
+    """Copy (x, y) into symmetric memory (allocate_points + one device copy).  When the point set
+    changes but its size does not, write the new coordinates into `.x` / `.y` in place."""
+    import torch.distributed as dist
+
+    pts = allocate_points(x.shape[0], x.dtype, x.device, group)
+    pts.x.copy_(x)
+    pts.y.copy_(y)
+    torch.cuda.synchronize(x.device)
     dist.barrier(group=group)
-    return ShardedPoints(sx, sy, sizes, group, px, py)
+    return pts
 
 
 def _host_register(x, y, group=None):

@@ -108,6 +108,8 @@ CASES = [
     (1, 3, 15, 1, "u", 0, 0, 10),
     (2, 3, 4, 1, "u", 1, 0, 10),
     (100000, 40, 15, 100000, "u", 0, 0, 50),   # a single huge leaf per top cell: many tiles per run
+    (3000, 300, 15, 512, "u", 5, 50, 60),      # large sparse quadrants under many polygons: tiles
+    (60000, 2000, 15, 256, "c", 20, 300, 40),  # span whole polygons (point-by-point evaluation)
 ]
 
 
@@ -246,6 +248,36 @@ def test_grid_aligned_polygons_and_lattice_points(oracle_lib, dtype, depth, max_
     assert_same(run_gpu(c, max_size), want, "lattice")
     assert_same(run_gpu(c, max_size, use_grid_hint=False), want, "lattice (no hint)")
     assert_same(run_gpu(c, max_size, use_grid_hint="no_keys"), want, "lattice (no keys)")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_long_edges_reaching_far_outside_the_area(oracle_lib, dtype):
+    """Polygons whose edges start hundreds of extents away: the products of the crossing test are
+    large there, so the 4-ULP on-edge band of the reference is wide in absolute terms -- the
+    cell-centre shortcut has to leave those points to the exact arithmetic (float32 above all)."""
+    c = make_case(150000, 6, 15, "u", dtype, seed=21, median_vertices=12)
+    x0, x1, y0, y1 = c["ext"]
+    w, h = x1 - x0, y1 - y0
+    far = 400.0
+    rings = [
+        [(x0 - far * w, y0 + 0.31 * h), (x1 + far * w, y0 + 0.52 * h), (x0 + 0.4 * w, y1 + far * h),
+         (x0 - far * w, y0 + 0.31 * h)],
+        [(x0 + 0.13 * w, y0 - far * h), (x0 + 0.77 * w, y1 + far * h), (x1 + far * w, y0 - far * h),
+         (x0 + 0.13 * w, y0 - far * h)],
+        [(x0 - far * w, y0 - far * h), (x1 + far * w, y1 + far * h), (x1 + far * w, y0 - far * h),
+         (x0 - far * w, y0 - far * h)],
+    ]
+    vx = np.concatenate([c["vx"]] + [np.array([p[0] for p in r], dtype=dtype) for r in rings])
+    vy = np.concatenate([c["vy"]] + [np.array([p[1] for p in r], dtype=dtype) for r in rings])
+    ro = np.concatenate([c["ro"], c["ro"][-1] + np.cumsum([len(r) for r in rings])]).astype(np.uint32)
+    po = np.concatenate([c["po"], c["po"][-1] + 1 + np.arange(len(rings))]).astype(np.uint32)
+    c2 = dict(c, po=po, ro=ro, vx=vx, vy=vy)
+    for max_size in (64, 4096):
+        want = run_host(oracle_lib, c2, max_size)
+        assert len(want["hits"][0]) > 1000
+        assert_same(run_gpu(c2, max_size), want, "long edges")
+        assert_same(run_gpu(c2, max_size, use_grid_hint=False), want, "long edges (no hint)")
+        assert_same(run_gpu(c2, max_size, use_grid_hint="no_keys"), want, "long edges (no keys)")
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
