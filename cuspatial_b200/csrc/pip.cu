@@ -1112,81 +1112,106 @@ pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
                 const u32* __restrict__ pair_len, u32 n_pairs, const u64* __restrict__ wbase,
                 const u64* __restrict__ obase, const u32* __restrict__ hits,
                 const u32* __restrict__ mask_words, const u8* __restrict__ cls, u32 position_base,
-                u32* __restrict__ out_poly, u32* __restrict__ out_point)
+                u32* __restrict__ out_poly, u32* __restrict__ out_point, u32 group)
 {
   u32 const lane  = lane_id();
   u32 const warps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_pairs; j += warps) {
-    u32 const nh = hits[j];
-    if (nh == 0) continue;
-    u32 const poly = pair_poly[j], len = pair_len[j], off = pair_off[j] + position_base;
-    u32 const words = len / 32 + ((len & 31) != 0);
-    u64 const wb    = wbase[j];
-    u64 o           = obase[j];
-    if (cls[j] == kClsInside) {  // whole quadrant inside: rows are (poly, off .. off+nh-1)
-      u32* const op = out_poly + o;
-      u32* const oq = out_point + o;
-      uintptr_t const ph = reinterpret_cast<uintptr_t>(op) & 15;
-      if (ph == (reinterpret_cast<uintptr_t>(oq) & 15)) {
-        // 128-bit streaming stores between a scalar head and tail
-        u32 const head = min((u32)(((16 - ph) & 15) >> 2), nh);
-        if (lane < head) {
-          BSJ_EMIT_STORE(op + lane, poly);
-          BSJ_EMIT_STORE(oq + lane, off + lane);
-        }
-        u32 const nvec = (nh - head) >> 2;
-        uint4* const vp = reinterpret_cast<uint4*>(op + head);
-        uint4* const vq = reinterpret_cast<uint4*>(oq + head);
-        for (u32 v = lane; v < nvec; v += 32) {
-          u32 const p0 = off + head + v * 4;
-          BSJ_EMIT_STORE(vp + v, make_uint4(poly, poly, poly, poly));
-          BSJ_EMIT_STORE(vq + v, make_uint4(p0, p0 + 1, p0 + 2, p0 + 3));
-        }
-        u32 const r = head + nvec * 4 + lane;
-        if (r < nh) {
-          BSJ_EMIT_STORE(op + r, poly);
-          BSJ_EMIT_STORE(oq + r, off + r);
-        }
-      } else {
-        for (u32 r = lane; r < nh; r += 32) {
-          BSJ_EMIT_STORE(op + r, poly);
-          BSJ_EMIT_STORE(oq + r, off + r);
-        }
-      }
-      continue;
+  // A warp takes `group` (<= 32) consecutive pairs at a time: lane l fetches the records of pair
+  // g*group + l -- seven coalesced loads in ONE latency round for the whole group instead of two
+  // dependent rounds per pair (the records may sit in a peer GPU's memory: the multi-GPU merge
+  // expands every rank's compact result in place) -- and the pairs with rows are then handed to
+  // the whole warp one by one through shuffles.
+  u64 const n_groups = ((u64)n_pairs + group - 1) / group;
+  for (u64 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+    u64 const jl = g * group + lane;
+    u32 nh_l = 0, poly_l = 0, len_l = 0, off_l = 0, cls_l = 0;
+    u64 wb_l = 0, o_l = 0;
+    if (lane < group && jl < n_pairs) {
+      nh_l   = hits[jl];
+      poly_l = pair_poly[jl];
+      len_l  = pair_len[jl];
+      off_l  = pair_off[jl];
+      cls_l  = cls[jl];
+      wb_l   = wbase[jl];
+      o_l    = obase[jl];
     }
-    for (u32 w0 = 0; w0 < words; w0 += 32) {
-      u32 const w    = w0 + lane < words ? __ldcs(mask_words + wb + w0 + lane) : 0u;
-      u32 const c    = __popc(w);
-      u32 const incl = warp_inclusive_scan(c);
-      u32 const tot  = __shfl_sync(0xffffffffu, incl, 31);
-      if (tot == 1024) {  // every candidate of the group is a hit: identity mapping
-        for (u32 r = lane; r < 1024; r += 32) {
-          BSJ_EMIT_STORE(out_poly + o + r, poly);
-          BSJ_EMIT_STORE(out_point + o + r, off + w0 * 32 + r);
-        }
-      } else {
-        for (u32 r0 = 0; r0 < tot; r0 += 32) {
-          u32 const r = r0 + lane;
-          // smallest lane index s with incl[s] > r
-          u32 s = 0;
-#pragma unroll
-          for (int step = 16; step; step >>= 1) {
-            u32 const probe = __shfl_sync(0xffffffffu, incl, s + step - 1);
-            if (probe <= r) s += step;
+    u32 live = __ballot_sync(0xffffffffu, nh_l != 0);
+    while (live) {
+      int const src = __ffs(live) - 1;
+      live &= live - 1;
+      u32 const nh   = __shfl_sync(0xffffffffu, nh_l, src);
+      u32 const poly = __shfl_sync(0xffffffffu, poly_l, src);
+      u32 const len  = __shfl_sync(0xffffffffu, len_l, src);
+      u32 const off  = __shfl_sync(0xffffffffu, off_l, src) + position_base;
+      u32 const c8   = __shfl_sync(0xffffffffu, cls_l, src);
+      u64 const wb   = __shfl_sync(0xffffffffu, wb_l, src);
+      u64 o          = __shfl_sync(0xffffffffu, o_l, src);
+      u32 const words = len / 32 + ((len & 31) != 0);
+      if (c8 == kClsInside) {  // whole quadrant inside: rows are (poly, off .. off+nh-1)
+        u32* const op = out_poly + o;
+        u32* const oq = out_point + o;
+        uintptr_t const ph = reinterpret_cast<uintptr_t>(op) & 15;
+        if (ph == (reinterpret_cast<uintptr_t>(oq) & 15)) {
+          // 128-bit stores between a scalar head and tail
+          u32 const head = min((u32)(((16 - ph) & 15) >> 2), nh);
+          if (lane < head) {
+            BSJ_EMIT_STORE(op + lane, poly);
+            BSJ_EMIT_STORE(oq + lane, off + lane);
           }
-          u32 const ws    = __shfl_sync(0xffffffffu, w, s);
-          u32 const incls = __shfl_sync(0xffffffffu, incl, s);
-          u32 const cs    = __popc(ws);
-          if (r < tot) {
-            u32 const nth = r - (incls - cs);  // 0-based rank inside word s
-            u32 const bit = __fns(ws, 0, nth + 1);
-            BSJ_EMIT_STORE(out_poly + o + r, poly);
-            BSJ_EMIT_STORE(out_point + o + r, off + (w0 + s) * 32 + bit);
+          u32 const nvec = (nh - head) >> 2;
+          uint4* const vp = reinterpret_cast<uint4*>(op + head);
+          uint4* const vq = reinterpret_cast<uint4*>(oq + head);
+          for (u32 v = lane; v < nvec; v += 32) {
+            u32 const p0 = off + head + v * 4;
+            BSJ_EMIT_STORE(vp + v, make_uint4(poly, poly, poly, poly));
+            BSJ_EMIT_STORE(vq + v, make_uint4(p0, p0 + 1, p0 + 2, p0 + 3));
+          }
+          u32 const r = head + nvec * 4 + lane;
+          if (r < nh) {
+            BSJ_EMIT_STORE(op + r, poly);
+            BSJ_EMIT_STORE(oq + r, off + r);
+          }
+        } else {
+          for (u32 r = lane; r < nh; r += 32) {
+            BSJ_EMIT_STORE(op + r, poly);
+            BSJ_EMIT_STORE(oq + r, off + r);
           }
         }
+        continue;
       }
-      o += tot;
+      for (u32 w0 = 0; w0 < words; w0 += 32) {
+        u32 const w    = w0 + lane < words ? __ldcs(mask_words + wb + w0 + lane) : 0u;
+        u32 const c    = __popc(w);
+        u32 const incl = warp_inclusive_scan(c);
+        u32 const tot  = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot == 1024) {  // every candidate of the group is a hit: identity mapping
+          for (u32 r = lane; r < 1024; r += 32) {
+            BSJ_EMIT_STORE(out_poly + o + r, poly);
+            BSJ_EMIT_STORE(out_point + o + r, off + w0 * 32 + r);
+          }
+        } else {
+          for (u32 r0 = 0; r0 < tot; r0 += 32) {
+            u32 const r = r0 + lane;
+            // smallest lane index s with incl[s] > r
+            u32 s = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+              u32 const probe = __shfl_sync(0xffffffffu, incl, s + step - 1);
+              if (probe <= r) s += step;
+            }
+            u32 const ws    = __shfl_sync(0xffffffffu, w, s);
+            u32 const incls = __shfl_sync(0xffffffffu, incl, s);
+            u32 const cs    = __popc(ws);
+            if (r < tot) {
+              u32 const nth = r - (incls - cs);  // 0-based rank inside word s
+              u32 const bit = __fns(ws, 0, nth + 1);
+              BSJ_EMIT_STORE(out_poly + o + r, poly);
+              BSJ_EMIT_STORE(out_point + o + r, off + (w0 + s) * 32 + bit);
+            }
+          }
+        }
+        o += tot;
+      }
     }
   }
 }
@@ -1574,11 +1599,17 @@ void expand_compact(const u32* pair_poly, const bsj_pip_compact* c, u32 position
                     u32* out_poly, u32* out_point, cudaStream_t s)
 {
   if (c->n_hits == 0 || c->n_pairs == 0) return;
-  int const grid_dim = (int)std::min<u64>((u64)num_sms() * BSJ_EMIT_GRID_MULT, (u64)div_up(c->n_pairs * 32, 256));
+  // pairs per warp-visit: 32 when there are plenty of pairs, fewer (>= 4) when the table is
+  // small, so that every warp of the grid still gets several groups and the tail stays balanced
+  u64 const max_warps = (u64)num_sms() * BSJ_EMIT_GRID_MULT * 8;
+  u32 group = 32;
+  while (group > 4 && div_up(c->n_pairs, (u64)group) < 4 * max_warps) group >>= 1;
+  int const grid_dim = (int)std::min<u64>((u64)num_sms() * BSJ_EMIT_GRID_MULT,
+                                          (u64)div_up(div_up(c->n_pairs, (u64)group) * 32, 256));
   pip_emit_kernel<<<std::max(grid_dim, 1), 256, 0, s>>>(
     pair_poly, c->pair_offset, c->pair_length, (u32)c->n_pairs, c->pair_word_base,
     c->pair_row_base, c->pair_hits, c->mask_words, c->pair_class, position_base, out_poly,
-    out_point);
+    out_point, group);
   BSJ_CHECK_LAUNCH();
   prof_mark("pip_emit");
 }

@@ -10,6 +10,19 @@
 #ifndef BSJ_SORT_RANK
 #define BSJ_SORT_RANK 1
 #endif
+// Tile id: 0 = blockIdx.x (CTAs of a 1-D grid are dispatched in index order, so every
+// predecessor a look-back can wait for is already resident or done -- what cub::DeviceScan has
+// always relied on); 1 = dynamic ticket (one global atomic + a barrier before the first load)
+#ifndef BSJ_SORT_TICKET
+#define BSJ_SORT_TICKET 0
+#endif
+// Tile load: 1 = the tile's keys and values arrive in shared memory as two 1-D bulk copies (TMA
+// engine, cp.async.bulk + mbarrier) issued by one thread at kernel entry -- no load instructions
+// through the LSU pipe, and the values' HBM latency hides behind the whole ranking phase without
+// holding registers; 0 = per-thread streaming loads.
+#ifndef BSJ_SORT_TMA
+#define BSJ_SORT_TMA 1
+#endif
 
 namespace bsj {
 
@@ -35,7 +48,42 @@ struct sort_smem {
   u32 warp_sums[kWarps];
   u32 gsums[kWarps];
   u32 tile;
+  alignas(8) u64 mbar;  // completion barrier of the tile's bulk loads
 };
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, u32 bytes, u64* bar)
+{
+  asm volatile(
+    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+      smem_u32(dst_smem)),
+    "l"(src), "r"(bytes), "r"(smem_u32(bar))
+    : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
+{
+  u32 done = 0;
+  while (!done) {
+    asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // generic histogram (used when the producer of the keys did not already fuse it)
@@ -77,7 +125,34 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
   int const lane = tid & 31;
   int const warp = tid >> 5;
 
+#if BSJ_SORT_TICKET
   if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  u32 const tile = sm.tile;
+#else
+  u32 const tile = blockIdx.x;
+#endif
+  u32 const tile_base = tile * (u32)kSortTile;
+  u32 const valid     = min((u32)kSortTile, n - tile_base);
+  u32 const warp_base = tile_base + warp * (kSortIPT * 32);
+
+  // ---- tile load.  Full tiles of 16-byte-aligned inputs: two bulk copies into the (still
+  // unused) slot array -- keys into its first half, values into its second half.
+  u32* const skeys = reinterpret_cast<u32*>(sm.kv);
+  u32* const svals = skeys + kSortTile;
+#if BSJ_SORT_TMA
+  bool const bulk = valid == (u32)kSortTile &&
+                    ((reinterpret_cast<uintptr_t>(keys_in) |
+                      (IOTA ? (uintptr_t)0 : reinterpret_cast<uintptr_t>(vals_in))) & 15) == 0;
+  if (bulk && tid == 0) {
+    mbar_init(&sm.mbar, 1);
+    mbar_expect_tx(&sm.mbar, (IOTA ? 1u : 2u) * (u32)kSortTile * 4u);
+    bulk_load(skeys, keys_in + tile_base, (u32)kSortTile * 4u, &sm.mbar);
+    if (!IOTA) bulk_load(svals, vals_in + tile_base, (u32)kSortTile * 4u, &sm.mbar);
+  }
+#else
+  constexpr bool bulk = false;
+#endif
 #if BSJ_SORT_RANK == 0
   for (int i = tid; i < kWarps * kRadixDigits; i += kSortBlock) sm.whist[i] = make_uint2(0u, 0u);
 #else
@@ -88,18 +163,20 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
 #endif
   }
 #endif
-  __syncthreads();
-  u32 const tile      = sm.tile;
-  u32 const tile_base = tile * (u32)kSortTile;
-  u32 const valid     = min((u32)kSortTile, n - tile_base);
-
-  // ---- load keys, warp-striped: item i of this lane is warp_base + i*32 + lane
-  u32 const warp_base = tile_base + warp * (kSortIPT * 32);
   u32 key[kSortIPT];
+  if (!bulk) {
+    // warp-striped: item i of this lane is warp_base + i*32 + lane
 #pragma unroll
-  for (int i = 0; i < kSortIPT; ++i) {
-    u32 const idx = warp_base + i * 32 + lane;
-    key[i]        = idx < n ? ld_stream(keys_in + idx) : 0xFFFFFFFFu;
+    for (int i = 0; i < kSortIPT; ++i) {
+      u32 const idx = warp_base + i * 32 + lane;
+      key[i]        = idx < n ? ld_stream(keys_in + idx) : 0xFFFFFFFFu;
+    }
+  }
+  __syncthreads();  // counters zeroed; the barrier's initialisation is visible to every waiter
+  if (bulk) {
+    mbar_wait(&sm.mbar, 0);
+#pragma unroll
+    for (int i = 0; i < kSortIPT; ++i) key[i] = skeys[warp * (kSortIPT * 32) + i * 32 + lane];
   }
   // this pass's global digit count (turned into an exclusive offset below)
   u32 gcount = 0;
@@ -238,10 +315,18 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
     }
   } else {
     u32 v[kSortIPT];
+    if (bulk) {
+      // the values have been sitting in the second half of the slot array since kernel entry;
+      // everyone takes its own before anyone overwrites the slots
 #pragma unroll
-    for (int i = 0; i < kSortIPT; ++i) {
-      u32 const idx = warp_base + i * 32 + lane;
-      v[i]          = idx < n ? ld_stream(vals_in + idx) : 0u;
+      for (int i = 0; i < kSortIPT; ++i) v[i] = svals[warp * (kSortIPT * 32) + i * 32 + lane];
+      __syncthreads();
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSortIPT; ++i) {
+        u32 const idx = warp_base + i * 32 + lane;
+        v[i]          = idx < n ? ld_stream(vals_in + idx) : 0u;
+      }
     }
 #pragma unroll
     for (int i = 0; i < kSortIPT; ++i) {

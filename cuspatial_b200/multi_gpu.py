@@ -611,9 +611,14 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     names = sorted(comp)
     stat = torch.tensor([n_recv, n_hits] + [comp[k].shape[0] for k in names], dtype=torch.int64,
                         device=dev)
-    stats = [torch.zeros_like(stat) for _ in range(world)]
-    dist.all_gather(stats, stat, group=group)
-    stats = [s_.tolist() for s_ in stats]
+    if dev.type == "cuda":  # one collective, one host read
+        allstat = torch.empty(world * stat.shape[0], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allstat, stat, group=group)
+        stats = allstat.view(world, -1).tolist()
+    else:
+        stats = [torch.zeros_like(stat) for _ in range(world)]
+        dist.all_gather(stats, stat, group=group)
+        stats = [s_.tolist() for s_ in stats]
     counts = [s_[0] for s_ in stats]
     hits = [s_[1] for s_ in stats]
     if sum(hits) >= 2 ** 32 and gather_pairs:
@@ -630,24 +635,54 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
         sizes_b = [[s_[2 + i] * comp[k].element_size() for i, k in enumerate(names)]
                    for s_ in stats]
         pad = [[(-b) % 16 for b in row] for row in sizes_b]  # keep every array 16-byte aligned
-        packed = torch.cat([torch.cat([_bytes(comp[k]),
-                                       torch.zeros(pad[rank][i], dtype=torch.uint8, device=dev)])
-                            for i, k in enumerate(names)]) if names else \
-            torch.empty(0, dtype=torch.uint8, device=dev)
         tot_b = [sum(b + p_ for b, p_ in zip(sizes_b[r], pad[r])) for r in range(world)]
-        allb, _ = _all_gather_varlen(packed, dist, group, tot_b)
+        peer_read = dev.type == "cuda" and os.environ.get("BSJ_MG_PEER_EXPAND") != "0"
+        if peer_read:
+            # Fused all-gather + expansion: every rank parks its packed compact result in
+            # symmetric memory and the expansion kernel of every other rank reads the records and
+            # ballot words straight through the peer mapping (NVLink) while it writes the rows to
+            # its own HBM -- no gathered copy of the compact result is ever materialised.
+            cap = max(tot_b)
+            cap = cap + cap // 8 + (1 << 20)
+            key = (dev.index, _group_key(group), "compact", torch.uint8)
+            if key in _SYMM and _SYMM[key]["cap"] >= max(tot_b):
+                cap = _SYMM[key]["cap"]  # same decision on every rank: all see the same sizes
+            ent = _symm_alloc(dev, torch.uint8, cap, group, "compact")
+            o = 0
+            for i, k in enumerate(names):
+                nb = sizes_b[rank][i]
+                if nb:
+                    ent["buf"][o: o + nb].copy_(_bytes(comp[k]))
+                o += nb + pad[rank][i]
+            # every rank's block is complete before anyone reads it.  The buffer is rewritten in
+            # the next call only after that call's exchange barrier, which no rank passes before
+            # its own expansion below has finished (stream order): no trailing barrier needed
+            ent["hdl"].barrier(channel=0)
+            if "peers" not in ent:
+                ent["peers"] = [ent["buf"] if r == rank else
+                                ent["hdl"].get_buffer(r, (ent["cap"],), torch.uint8)
+                                for r in range(world)]
+            srcs = ent["peers"]
+            offs = [0] * world
+        else:
+            packed = torch.cat([torch.cat([_bytes(comp[k]),
+                                           torch.zeros(pad[rank][i], dtype=torch.uint8, device=dev)])
+                                for i, k in enumerate(names)]) if names else \
+                torch.empty(0, dtype=torch.uint8, device=dev)
+            allb, _ = _all_gather_varlen(packed, dist, group, tot_b)
+            srcs = [allb] * world
+            offs = [sum(tot_b[:r]) for r in range(world)]
         prof.mark("gather_compact")
         total = sum(hits)
         out_poly = torch.empty(total, dtype=torch.int32, device=dev)
         out_point = torch.empty(total, dtype=torch.int32, device=dev)
-        row, boff = 0, 0
+        row = 0
         for r in range(world):
-            part, o = {}, boff
+            part, o = {}, offs[r]
             for i, k in enumerate(names):
                 nb = sizes_b[r][i]
-                part[k] = allb[o: o + nb].view(comp[k].dtype)
+                part[k] = srcs[r][o: o + nb].view(comp[k].dtype)
                 o += nb + pad[r][i]
-            boff += tot_b[r]
             if hits[r]:
                 expand(part, hits[r], sum(counts[:r]), out_poly[row: row + hits[r]],
                        out_point[row: row + hits[r]])
