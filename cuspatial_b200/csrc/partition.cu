@@ -30,7 +30,8 @@ namespace bsj {
 template <typename T>
 void launch_point_keys(const void* x, const void* y, u64 n, double x_min, double x_max,
                        double y_min, double y_max, double scale, int max_depth, u32* keys,
-                       u32* point_flags, cudaStream_t s);
+                       u32* point_flags, cudaStream_t s, u32* lead_bins, int bin_shift,
+                       u32 n_bins);
 
 namespace {
 
@@ -90,12 +91,26 @@ key_subhistogram_kernel(const u32* __restrict__ keys, u64 n, const bsj_shard_pla
   for (u32 i = threadIdx.x; i < total; i += blockDim.x) s_sub[i] = 0;
   __syncthreads();
   u64 const stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    u32 const k = __ldcs(keys + i);
+  auto tally = [&](u32 k) {
     u32 const b = k >> shift1;
     for (u32 t = 0; t < nt; ++t)
       if (b == s_target[t]) atomicAdd(&s_sub[t * n_sub + ((k >> shift2) & (n_sub - 1))], 1u);
+  };
+  // 128-bit loads, two in flight per thread: the kernel only has to stream the keys
+  u64 const nvec = (reinterpret_cast<uintptr_t>(keys) & 15) == 0 ? n / 4 : 0;
+  u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; v + stride < nvec; v += 2 * stride) {
+    uint4 const a = __ldcs(reinterpret_cast<const uint4*>(keys) + v);
+    uint4 const c = __ldcs(reinterpret_cast<const uint4*>(keys) + v + stride);
+    tally(a.x); tally(a.y); tally(a.z); tally(a.w);
+    tally(c.x); tally(c.y); tally(c.z); tally(c.w);
   }
+  for (; v < nvec; v += stride) {
+    uint4 const a = __ldcs(reinterpret_cast<const uint4*>(keys) + v);
+    tally(a.x); tally(a.y); tally(a.z); tally(a.w);
+  }
+  for (u64 i = nvec * 4 + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    tally(__ldcs(keys + i));
   __syncthreads();
   for (u32 i = threadIdx.x; i < total; i += blockDim.x)
     if (s_sub[i]) atomicAdd(&bins[i], s_sub[i]);
@@ -260,7 +275,7 @@ __global__ void plan_finalize_kernel(const u32* __restrict__ counts_matrix, u64 
 // ---------------------------------------------------------------------------------------------
 // fused partition + all-to-all of (key, global id)
 // ---------------------------------------------------------------------------------------------
-constexpr int kPartBlock = 512;
+constexpr int kPartBlock = 256;  // 4 CTAs per SM: a CTA idles while its peer stores complete
 constexpr int kPartIPT   = 16;
 constexpr int kPartTile  = kPartBlock * kPartIPT;       // 8192 keys
 constexpr int kPartSlots = kPartTile + 8 * kMaxRanks;  // + alignment padding per destination
@@ -279,7 +294,6 @@ struct part_smem {
   u32 count[kMaxRanks];   // elements of this tile going to the destination
   u32 gfirst[kMaxRanks];  // element index inside the destination buffer where the run starts
   u32 split[kMaxRanks];
-  u32 tile;
 };
 
 __device__ __forceinline__ u32 smem_addr(const void* p)
@@ -289,47 +303,48 @@ __device__ __forceinline__ u32 smem_addr(const void* p)
 
 // descriptors: [tile][kMaxRanks] u64 {tag, value}
 template <bool BULK>
-__global__ void __launch_bounds__(kPartBlock)
+__global__ void __launch_bounds__(kPartBlock, 4)
 partition_keys_kernel(const u32* __restrict__ keys, u32 n, const bsj_shard_plan* __restrict__ plan,
-                      key_dests_t dst, u64* __restrict__ desc, u32* __restrict__ ticket)
+                      key_dests_t dst, u64* __restrict__ desc)
 {
   extern __shared__ __align__(16) unsigned char part_smem_raw[];
   part_smem& sm = *reinterpret_cast<part_smem*>(part_smem_raw);
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (plan->status != 0) return;  // receive capacity exceeded: the host re-plans
-  int const R = (int)plan->n_ranks;
-  if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-  if (tid < kMaxRanks) sm.split[tid] = plan->splitter[tid];
-  __syncthreads();
-  u32 const tile = sm.tile;
+  // tile id = blockIdx.x: CTAs of a 1-D grid start in index order, so every predecessor the
+  // look-back below can wait for is already resident or finished
+  u32 const tile = blockIdx.x;
   // blocked-by-warp layout keeps the original order: warp w owns items [w*IPT*32, (w+1)*IPT*32)
   u32 const tile_base = tile * kPartTile;
   u32 const warp_base = tile_base + warp * (kPartIPT * 32);
   u32 const lt        = lanemask_lt();
-  u32 const gid0      = plan->gid_base[plan->rank];
 
   u32 key[kPartIPT];
-  int dest[kPartIPT];
-  u32 rank[kPartIPT];
-  u32 cnt = 0;  // lane r < R accumulates this warp's count for destination r
+  u32 dr[kPartIPT];  // destination << 16 | rank among the warp's earlier items of that destination
+  u32 cnt = 0;       // lane r < R accumulates this warp's count for destination r
 #pragma unroll
-  for (int i = 0; i < kPartIPT; ++i) {
+  for (int i = 0; i < kPartIPT; ++i) {  // the keys are in flight while the plan is read
     u32 const idx = warp_base + i * 32 + lane;
     key[i]        = idx < n ? __ldcs(keys + idx) : 0u;
   }
+  if (plan->status != 0) return;  // receive capacity exceeded: the host re-plans
+  int const R = (int)plan->n_ranks;
+  if (tid < kMaxRanks) sm.split[tid] = plan->splitter[tid];
+  u32 const gid0 = plan->gid_base[plan->rank];
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < kPartIPT; ++i) {
     u32 const idx = warp_base + i * 32 + lane;
     int d         = 0;
     for (int r = 0; r + 1 < R; ++r) d += key[i] >= sm.split[r];
-    dest[i] = idx < n ? d : -1;
-    rank[i] = 0;
+    if (idx >= n) d = -1;
+    u32 rk = 0;
     for (int r = 0; r < R; ++r) {
-      u32 const m      = __ballot_sync(0xffffffffu, dest[i] == r);
+      u32 const m      = __ballot_sync(0xffffffffu, d == r);
       u32 const before = __shfl_sync(0xffffffffu, cnt, r);
-      if (dest[i] == r) rank[i] = before + __popc(m & lt);
+      if (d == r) rk = before + __popc(m & lt);
       if (lane == r) cnt += __popc(m);
     }
+    dr[i] = d < 0 ? 0xFFFFFFFFu : ((u32)d << 16) | rk;
   }
   if (lane < R) sm.warp_cnt[warp][lane] = cnt;
   __syncthreads();
@@ -380,9 +395,9 @@ partition_keys_kernel(const u32* __restrict__ keys, u32 n, const bsj_shard_plan*
   // stage the tile ordered by (destination, original order)
 #pragma unroll
   for (int i = 0; i < kPartIPT; ++i) {
-    if (dest[i] >= 0) {
-      int const d    = dest[i];
-      u32 const slot = sm.slot0[d] + sm.warp_off[warp][d] + rank[i];
+    if (dr[i] != 0xFFFFFFFFu) {
+      int const d    = (int)(dr[i] >> 16);
+      u32 const slot = sm.slot0[d] + sm.warp_off[warp][d] + (dr[i] & 0xFFFFu);
       sm.key[slot]   = key[i];
       sm.gid[slot]   = gid0 + warp_base + i * 32 + lane;
     }
@@ -455,14 +470,20 @@ void point_keys_histogram_impl(const void* x, const void* y, int dtype, u64 n, d
 {
   if (n == 0) return;
   int const d = std::max(0, std::min(15, max_depth));
-  if (dtype == BSJ_FLOAT32)
-    launch_point_keys<float>(x, y, n, x_min, x_max, y_min, y_max, scale, d, keys, point_flags, s);
-  else
-    launch_point_keys<double>(x, y, n, x_min, x_max, y_min, y_max, scale, d, keys, point_flags, s);
-  if (bins) {
+  bool const fused = bins != nullptr && n_bins <= (u64)kHistSmemBins;
+  if (bins)
     BSJ_EXPECTS(hist_shift >= 0 && hist_shift < 32 && (0xFFFFFFFFull >> hist_shift) < n_bins,
                 "histogram does not cover the key range");
-    int const grid = (int)std::min<u64>((u64)num_sms() * 2, (u64)div_up(n, 2048));
+  // keys and the leading-bit histogram in ONE pass over the coordinates when the bins fit the
+  // encode kernel's shared memory (always the case for the sharding plan's 8192 bins)
+  if (dtype == BSJ_FLOAT32)
+    launch_point_keys<float>(x, y, n, x_min, x_max, y_min, y_max, scale, d, keys, point_flags, s,
+                             fused ? bins : nullptr, hist_shift, (u32)n_bins);
+  else
+    launch_point_keys<double>(x, y, n, x_min, x_max, y_min, y_max, scale, d, keys, point_flags, s,
+                              fused ? bins : nullptr, hist_shift, (u32)n_bins);
+  if (bins && !fused) {
+    int const grid = (int)std::min<u64>((u64)num_sms() * 4, (u64)div_up(n, 2048));
     key_histogram_kernel<<<std::max(grid, 1), 512, 0, s>>>(keys, n, hist_shift, (u32)n_bins, bins);
     BSJ_CHECK_LAUNCH();
   }
@@ -497,7 +518,7 @@ void shard_subhistogram_impl(const u32* keys, u64 n, const bsj_shard_plan* plan,
                              u32 n_sub, u32* bins, cudaStream_t s)
 {
   if (n == 0 || n_ranks <= 1) return;
-  int const grid = (int)std::min<u64>((u64)num_sms() * 2, (u64)div_up(n, 2048));
+  int const grid = (int)std::min<u64>((u64)num_sms() * 4, (u64)div_up(n, 4096));
   key_subhistogram_kernel<<<std::max(grid, 1), 512, (size_t)(n_ranks - 1) * n_sub * sizeof(u32),
                             s>>>(keys, n, plan, bins);
   BSJ_CHECK_LAUNCH();
@@ -534,9 +555,7 @@ void partition_keys_impl(const u32* keys, u64 n, const bsj_shard_plan* plan, int
   }
   u32 const tiles = (u32)div_up(n, kPartTile);
   dev_buf<u64> desc((size_t)tiles * kMaxRanks, s);
-  dev_buf<u32> ticket(1, s);
   BSJ_CUDA_TRY(cudaMemsetAsync(desc.get(), 0, desc.size() * sizeof(u64), s));
-  BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
   configure_once_per_device(2, [] {  // per device, not per process
     BSJ_CUDA_TRY(cudaFuncSetAttribute(partition_keys_kernel<true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -547,10 +566,10 @@ void partition_keys_impl(const u32* keys, u64 n, const bsj_shard_plan* plan, int
   });
   if (use_bulk_copy)
     partition_keys_kernel<true><<<tiles, kPartBlock, sizeof(part_smem), s>>>(
-      keys, (u32)n, plan, dst, desc.get(), ticket.get());
+      keys, (u32)n, plan, dst, desc.get());
   else
     partition_keys_kernel<false><<<tiles, kPartBlock, sizeof(part_smem), s>>>(
-      keys, (u32)n, plan, dst, desc.get(), ticket.get());
+      keys, (u32)n, plan, dst, desc.get());
   BSJ_CHECK_LAUNCH();
 }
 

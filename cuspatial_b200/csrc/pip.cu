@@ -34,6 +34,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 namespace bsj {
 
@@ -1105,24 +1106,36 @@ __device__ __forceinline__ void emit_store(P* p, V v)
 #define BSJ_EMIT_STORE emit_store
 #endif
 #ifndef BSJ_EMIT_GRID_MULT
-#define BSJ_EMIT_GRID_MULT 16
+#define BSJ_EMIT_GRID_MULT 8
 #endif
-__global__ void __launch_bounds__(256)
+constexpr int kEmitWarps = 8;
+__global__ void __launch_bounds__(kEmitWarps * 32)
 pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_off,
                 const u32* __restrict__ pair_len, u32 n_pairs, const u64* __restrict__ wbase,
                 const u64* __restrict__ obase, const u32* __restrict__ hits,
                 const u32* __restrict__ mask_words, const u8* __restrict__ cls, u32 position_base,
-                u32* __restrict__ out_poly, u32* __restrict__ out_point, u32 group)
+                u32* __restrict__ out_poly, u32* __restrict__ out_point, u32 group,
+                u32* __restrict__ ticket)
 {
-  u32 const lane  = lane_id();
-  u32 const warps = (gridDim.x * blockDim.x) >> 5;
+  // per-warp staging of the hit positions of one 32-word group (boundary pairs)
+  __shared__ unsigned short s_pos[kEmitWarps][1024];
+  u32 const lane = lane_id();
+  unsigned short* const pos = s_pos[threadIdx.x >> 5];
   // A warp takes `group` (<= 32) consecutive pairs at a time: lane l fetches the records of pair
   // g*group + l -- seven coalesced loads in ONE latency round for the whole group instead of two
   // dependent rounds per pair (the records may sit in a peer GPU's memory: the multi-GPU merge
   // expands every rank's compact result in place) -- and the pairs with rows are then handed to
-  // the whole warp one by one through shuffles.
+  // the whole warp one by one through shuffles.  Groups are handed out through a ticket (pairs
+  // differ in cost by orders of magnitude: a whole-quadrant fill vs. ballot words to decode), the
+  // next ticket being drawn while the current group is written.
   u64 const n_groups = ((u64)n_pairs + group - 1) / group;
-  for (u64 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+  u32 g32 = 0;
+  if (lane == 0) g32 = atomicAdd(ticket, 1u);
+  g32 = __shfl_sync(0xffffffffu, g32, 0);
+  while ((u64)g32 < n_groups) {
+    u64 const g = g32;
+    u32 next = 0;
+    if (lane == 0) next = atomicAdd(ticket, 1u);
     u64 const jl = g * group + lane;
     u32 nh_l = 0, poly_l = 0, len_l = 0, off_l = 0, cls_l = 0;
     u64 wb_l = 0, o_l = 0;
@@ -1180,7 +1193,7 @@ pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
         continue;
       }
       for (u32 w0 = 0; w0 < words; w0 += 32) {
-        u32 const w    = w0 + lane < words ? __ldcs(mask_words + wb + w0 + lane) : 0u;
+        u32 w          = w0 + lane < words ? __ldcs(mask_words + wb + w0 + lane) : 0u;
         u32 const c    = __popc(w);
         u32 const incl = warp_inclusive_scan(c);
         u32 const tot  = __shfl_sync(0xffffffffu, incl, 31);
@@ -1189,30 +1202,25 @@ pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
             BSJ_EMIT_STORE(out_poly + o + r, poly);
             BSJ_EMIT_STORE(out_point + o + r, off + w0 * 32 + r);
           }
-        } else {
-          for (u32 r0 = 0; r0 < tot; r0 += 32) {
-            u32 const r = r0 + lane;
-            // smallest lane index s with incl[s] > r
-            u32 s = 0;
-#pragma unroll
-            for (int step = 16; step; step >>= 1) {
-              u32 const probe = __shfl_sync(0xffffffffu, incl, s + step - 1);
-              if (probe <= r) s += step;
-            }
-            u32 const ws    = __shfl_sync(0xffffffffu, w, s);
-            u32 const incls = __shfl_sync(0xffffffffu, incl, s);
-            u32 const cs    = __popc(ws);
-            if (r < tot) {
-              u32 const nth = r - (incls - cs);  // 0-based rank inside word s
-              u32 const bit = __fns(ws, 0, nth + 1);
-              BSJ_EMIT_STORE(out_poly + o + r, poly);
-              BSJ_EMIT_STORE(out_point + o + r, off + (w0 + s) * 32 + bit);
-            }
+        } else if (tot) {
+          // lane l lists the set bits of word l at its place in the staging buffer, then the
+          // warp writes the rows with one lane per OUTPUT row (coalesced)
+          u32 k = incl - c;
+          while (w) {
+            pos[k++] = (unsigned short)(lane * 32 + (__ffs(w) - 1));
+            w &= w - 1;
           }
+          __syncwarp();
+          for (u32 r = lane; r < tot; r += 32) {
+            BSJ_EMIT_STORE(out_poly + o + r, poly);
+            BSJ_EMIT_STORE(out_point + o + r, off + w0 * 32 + pos[r]);
+          }
+          __syncwarp();
         }
         o += tot;
       }
     }
+    g32 = __shfl_sync(0xffffffffu, next, 0);
   }
 }
 
@@ -1249,40 +1257,204 @@ __device__ bool pip_indexed(T px, T py, const poly_meta<T>& m, const edge_index<
 }
 
 // ---------------------------------------------------------------------------------------------
-// bitmask point_in_polygon (<= 31 polygons): one thread per point
+// bitmask point_in_polygon, large point sets: a uniform grid of cell classes over the polygons'
+// common bounding box.  The argument is the one of classify_quadrant: a cell rectangle (widened
+// by the rounding margin of the point -> cell assignment) that no tolerance-widened edge box
+// touches and no vertical edge's x falls into is uniformly inside or outside a polygon, and the
+// answer is the predicate of its centre.  One table entry per cell = {bits of the polygons the
+// cell is inside of, bits of the polygons that need the exact test}; a point then costs one
+// 8-byte lookup plus the exact slab test for the (few) undecided polygons of its cell.
 // ---------------------------------------------------------------------------------------------
+struct cell_grid {
+  double min_x, min_y, scale, inv_scale, margin_x, margin_y;
+  int log2_cells;  // cells per side = 1 << log2_cells (square cells)
+  // a box that contains every polygon's rejection box (x widened by more than any polygon's own
+  // tolerance): a comfy point outside it is rejected by every polygon.  Valid only when all
+  // polygons are safe (an unsafe polygon takes the reference loop for every point).
+  int union_valid;
+  double ux0, ux1, uy0, uy1;
+};
+
+__device__ __forceinline__ u32 dilate16p(u32 v)
+{
+  v &= 0x0000FFFFu;
+  v = (v | (v << 8)) & 0x00FF00FFu;
+  v = (v | (v << 4)) & 0x0F0F0F0Fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+
+// one warp per cell; lane p pre-tests polygon p's box against the widened cell, the warp then
+// classifies the cell against the polygons that passed, one at a time
 template <typename T>
 __global__ void __launch_bounds__(256)
-pip_bitmask_kernel(const T* __restrict__ px, const T* __restrict__ py, u64 n_points,
-                   const poly_meta<T>* __restrict__ meta, u32 n_poly,
-                   const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
-                   const T* __restrict__ vy, i32* __restrict__ out, int force_reference,
-                   edge_index<T> ix)
+bitmask_grid_kernel(cell_grid cg, const poly_meta<T>* __restrict__ meta, u32 n_poly,
+                    edge_index<T> ix, uint2* __restrict__ cells)
 {
   __shared__ poly_meta<T> s_meta[31];
   for (u32 i = threadIdx.x; i < n_poly; i += blockDim.x) s_meta[i] = meta[i];
   __syncthreads();
-  u64 const stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += stride) {
-    T const x = __ldcs(px + i), y = __ldcs(py + i);
-    bool const p_ok = comfy(x) && comfy(y) && !force_reference;
-    i32 mask = 0;
-    for (u32 p = 0; p < n_poly; ++p) {
-      poly_meta<T> const& m = s_meta[p];
-      bool hit;
-      if (p_ok && m.safe) {
-        // exact rejections: no edge can straddle y outside [ymin, ymax); x beyond the widened
-        // extent decides every crossing comparison with certainty (parity even => outside)
-        T const mx = fpp<T>::eps() * fmax(fabs(m.xmin), fabs(m.xmax));
-        if (y < m.ymin || y >= m.ymax || x < m.xmin - mx || x > m.xmax + mx) continue;
-        hit = m.n_slabs ? pip_indexed<T>(x, y, m, ix)
-                        : pip_reference<T>(x, y, ring_offsets, m.ring_begin, m.ring_end, vx, vy);
-      } else {
-        hit = pip_reference<T>(x, y, ring_offsets, m.ring_begin, m.ring_end, vx, vy);
+  u32 const lane = lane_id();
+  u32 const G    = 1u << cg.log2_cells;
+  u64 const c    = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= (u64)G * G) return;
+  u32 const cx = (u32)c & (G - 1), cy = (u32)(c >> cg.log2_cells);
+  grid_info g{};
+  g.valid = 1; g.max_depth = cg.log2_cells; g.has_oob = 0;
+  g.min_x = cg.min_x; g.min_y = cg.min_y; g.scale = cg.scale;
+  g.margin_x = cg.margin_x; g.margin_y = cg.margin_y; g.sorted_keys = nullptr;
+  u32 const key   = dilate16p(cx) | (dilate16p(cy) << 1);
+  u32 const level = (u32)cg.log2_cells - 1;
+  bool cand = false;
+  if (lane < n_poly) {
+    poly_meta<T> const& m = s_meta[lane];
+    double const eps = (double)fpp<T>::eps();
+    double const x0 = cg.min_x + (double)cx * cg.scale - cg.margin_x;
+    double const x1 = cg.min_x + ((double)cx + 1.0) * cg.scale + cg.margin_x;
+    double const y0 = cg.min_y + (double)cy * cg.scale - cg.margin_y;
+    double const y1 = cg.min_y + ((double)cy + 1.0) * cg.scale + cg.margin_y;
+    double const dx = eps * fmax(fabs((double)m.xmin), fabs((double)m.xmax));
+    double const dy = eps * fmax(fabs((double)m.ymin), fabs((double)m.ymax));
+    // same rejection as classify_quadrant's own (which stays the authority for the survivors)
+    cand = !m.safe || m.n_slabs == 0 ||
+           !(x1 < (double)m.xmin - dx || x0 > (double)m.xmax + dx || y1 < (double)m.ymin - dy ||
+             y0 > (double)m.ymax + dy);
+  }
+  u32 todo = __ballot_sync(0xffffffffu, cand);
+  u32 inside = 0, boundary = 0;
+  while (todo) {
+    int const p = __ffs(todo) - 1;
+    todo &= todo - 1;
+    int const cls = classify_quadrant<T>(g, key, level, s_meta[p], ix);
+    inside |= (u32)(cls == kClsInside) << p;
+    boundary |= (u32)(cls == kClsBoundary) << p;
+  }
+  if (lane == 0) cells[c] = make_uint2(inside, boundary);
+}
+
+// exact predicate of point (x, y) against polygon p, after the exact box rejections
+template <typename T>
+__device__ __forceinline__ bool bitmask_exact(T x, T y, bool p_ok, const poly_meta<T>& m,
+                                              const u32* __restrict__ ring_offsets,
+                                              const T* __restrict__ vx, const T* __restrict__ vy,
+                                              const edge_index<T>& ix)
+{
+  if (p_ok && m.safe && m.n_slabs) return pip_indexed<T>(x, y, m, ix);
+  return pip_reference<T>(x, y, ring_offsets, m.ring_begin, m.ring_end, vx, vy);
+}
+// no edge can straddle y outside [ymin, ymax); x beyond the widened extent decides every crossing
+// comparison with certainty (parity even => outside).  Only for comfy points and safe polygons.
+template <typename T>
+__device__ __forceinline__ bool bitmask_rejects(T x, T y, const poly_meta<T>& m)
+{
+  T const mx = fpp<T>::eps() * fmax(fabs(m.xmin), fabs(m.xmax));
+  return y < m.ymin || y >= m.ymax || x < m.xmin - mx || x > m.xmax + mx;
+}
+
+// A CTA takes kBmChunk points at a time, in three phases, so that the expensive exact tests run
+// on converged warps (one thread per UNDECIDED (point, polygon) item) instead of a few lanes of
+// every warp of the streaming loop (measured: 4 of 32 lanes active):
+//   A  stream the points: cell lookup -> decided bits into the chunk's mask array (shared
+//      memory), undecided (point, polygon) items into a shared-memory queue;
+//   B  threads stride over the queue: exact test of one item each, result bit OR-ed into the
+//      mask array;
+//   C  the masks leave as coalesced 128-bit stores.
+// A full queue is not an error: the item is evaluated on the spot.
+constexpr int kBmBlock = 256;
+constexpr int kBmPPT   = 16;                   // points per thread and chunk
+constexpr int kBmChunk = kBmBlock * kBmPPT;   // 4096 points
+constexpr int kBmQueue = 6144;                // queue slots (item = polygon << 12 | point)
+
+template <typename T>
+__global__ void __launch_bounds__(kBmBlock, 3)
+pip_bitmask_kernel(const T* __restrict__ px, const T* __restrict__ py, u64 n_points,
+                   const poly_meta<T>* __restrict__ meta, u32 n_poly,
+                   const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
+                   const T* __restrict__ vy, i32* __restrict__ out, int force_reference,
+                   edge_index<T> ix, cell_grid cg, const uint2* __restrict__ cells)
+{
+  __shared__ poly_meta<T> s_meta[31];
+  __shared__ __align__(16) u32 s_mask[kBmChunk];
+  __shared__ u32 s_queue[kBmQueue];
+  __shared__ u32 s_count;
+  int const tid = threadIdx.x;
+  for (u32 i = tid; i < n_poly; i += kBmBlock) s_meta[i] = meta[i];
+  u32 const all_polys = n_poly >= 32 ? 0xFFFFFFFFu : ((1u << n_poly) - 1u);
+  double const G      = (double)(1u << cg.log2_cells);
+  u64 const n_chunks  = (n_points + kBmChunk - 1) / kBmChunk;
+  for (u64 chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    u64 const base = chunk * kBmChunk;
+    u32 const cnt  = (u32)min((u64)kBmChunk, n_points - base);
+    if (tid == 0) s_count = 0;
+    __syncthreads();  // also: s_meta loaded, previous chunk's masks written out
+    // ---- phase A
+#pragma unroll 4
+    for (int k = 0; k < kBmPPT; ++k) {
+      u32 const j = k * kBmBlock + tid;
+      if (j >= cnt) break;
+      T const x = __ldcs(px + base + j), y = __ldcs(py + base + j);
+      bool const p_ok = comfy(x) && comfy(y) && !force_reference;
+      u32 mask = 0, todo = all_polys;
+      if (p_ok && cg.union_valid &&
+          ((double)y < cg.uy0 || (double)y >= cg.uy1 || (double)x < cg.ux0 || (double)x > cg.ux1)) {
+        todo = 0;  // outside every polygon's box
+      } else if (p_ok && cells) {
+        double const fx = ((double)x - cg.min_x) * cg.inv_scale;
+        double const fy = ((double)y - cg.min_y) * cg.inv_scale;
+        if (fx >= 0.0 && fy >= 0.0 && fx < G && fy < G) {
+          uint2 const c = __ldg(cells + (((u64)(u32)fy << cg.log2_cells) + (u32)fx));
+          mask = c.x;
+          todo = c.y;
+        }
       }
-      mask |= (i32)hit << p;
+      if (p_ok && todo) {
+        // exact box rejections first: they empty `todo` for most points outside the grid
+        u32 keep = 0;
+        for (u32 t = todo; t;) {
+          int const p = __ffs(t) - 1;
+          t &= t - 1;
+          poly_meta<T> const& m = s_meta[p];
+          if (!(m.safe && bitmask_rejects<T>(x, y, m))) keep |= 1u << p;
+        }
+        todo = keep;
+      }
+      if (todo) {
+        u32 const n   = __popc(todo);
+        u32 const pos = atomicAdd(&s_count, n);
+        if (pos + n <= (u32)kBmQueue) {
+          u32 q = pos;
+          for (u32 t = todo; t; t &= t - 1) s_queue[q++] = ((u32)(__ffs(t) - 1) << 12) | j;
+        } else {  // queue full: evaluate here; the slots claimed inside the queue become no-ops
+          for (u32 q = pos; q < (u32)kBmQueue; ++q) s_queue[q] = 0xFFFFFFFFu;
+          for (u32 t = todo; t; t &= t - 1) {
+            int const p = __ffs(t) - 1;
+            mask |= (u32)bitmask_exact<T>(x, y, p_ok, s_meta[p], ring_offsets, vx, vy, ix) << p;
+          }
+        }
+      }
+      s_mask[j] = mask;
     }
-    __stcs(out + i, mask);
+    __syncthreads();
+    // ---- phase B
+    u32 const n_items = min(s_count, (u32)kBmQueue);
+    for (u32 q = tid; q < n_items; q += kBmBlock) {
+      u32 const item = s_queue[q];
+      if (item == 0xFFFFFFFFu) continue;
+      u32 const j = item & 0xFFFu, p = item >> 12;
+      T const x = __ldg(px + base + j), y = __ldg(py + base + j);
+      bool const p_ok = comfy(x) && comfy(y) && !force_reference;
+      if (bitmask_exact<T>(x, y, p_ok, s_meta[p], ring_offsets, vx, vy, ix))
+        atomicOr(&s_mask[j], 1u << p);
+    }
+    __syncthreads();
+    // ---- phase C
+    if (cnt == (u32)kBmChunk && (reinterpret_cast<uintptr_t>(out + base) & 15) == 0) {
+      for (int v = tid; v < kBmChunk / 4; v += kBmBlock)
+        __stcs(reinterpret_cast<uint4*>(out + base) + v, reinterpret_cast<const uint4*>(s_mask)[v]);
+    } else {
+      for (u32 j = tid; j < cnt; j += kBmBlock) __stcs(out + base + j, (i32)s_mask[j]);
+    }
   }
 }
 
@@ -1600,16 +1772,28 @@ void expand_compact(const u32* pair_poly, const bsj_pip_compact* c, u32 position
 {
   if (c->n_hits == 0 || c->n_pairs == 0) return;
   // pairs per warp-visit: 32 when there are plenty of pairs, fewer (>= 4) when the table is
-  // small, so that every warp of the grid still gets several groups and the tail stays balanced
-  u64 const max_warps = (u64)num_sms() * BSJ_EMIT_GRID_MULT * 8;
+  // small, so that every warp still draws several groups
+  static int mult = 0, group_min = 0, group_factor = 0;
+  if (!mult) {  // tuning knobs (A/B runs)
+    const char* e = std::getenv("BSJ_EMIT_MULT");
+    mult = e ? std::max(1, std::atoi(e)) : BSJ_EMIT_GRID_MULT;
+    e = std::getenv("BSJ_EMIT_GROUP_MIN");
+    group_min = e ? std::max(1, std::atoi(e)) : 8;
+    e = std::getenv("BSJ_EMIT_GROUP_FACTOR");
+    group_factor = e ? std::max(1, std::atoi(e)) : 8;
+  }
+  u64 const n_warps = (u64)num_sms() * mult * kEmitWarps;
   u32 group = 32;
-  while (group > 4 && div_up(c->n_pairs, (u64)group) < 4 * max_warps) group >>= 1;
-  int const grid_dim = (int)std::min<u64>((u64)num_sms() * BSJ_EMIT_GRID_MULT,
-                                          (u64)div_up(div_up(c->n_pairs, (u64)group) * 32, 256));
-  pip_emit_kernel<<<std::max(grid_dim, 1), 256, 0, s>>>(
+  while (group > (u32)group_min && div_up(c->n_pairs, (u64)group) < (u64)group_factor * n_warps)
+    group >>= 1;
+  int const grid_dim = (int)std::min<u64>((u64)num_sms() * mult,
+                                          (u64)div_up(div_up(c->n_pairs, (u64)group), kEmitWarps));
+  dev_buf<u32> ticket(1, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
+  pip_emit_kernel<<<std::max(grid_dim, 1), kEmitWarps * 32, 0, s>>>(
     pair_poly, c->pair_offset, c->pair_length, (u32)c->n_pairs, c->pair_word_base,
     c->pair_row_base, c->pair_hits, c->mask_words, c->pair_class, position_base, out_poly,
-    out_point, group);
+    out_point, group, ticket.get());
   BSJ_CHECK_LAUNCH();
   prof_mark("pip_emit");
 }
@@ -1623,13 +1807,73 @@ void pip_bitmask_t(const void* px, const void* py, u64 n_points, const u32* poly
   u32 const n_poly = (u32)(n_poly_offsets ? n_poly_offsets - 1 : 0);
   polygon_index<T> pidx;
   pidx.begin(poly_offsets, n_poly_offsets, ring_offsets, n_ring_offsets, vx, vy, n_verts, s);
+  // the polygon boxes come back with the index totals (same synchronisation): they size the grid
+  std::vector<poly_meta<T>> h_meta(n_poly);
+  if (n_poly)
+    BSJ_CUDA_TRY(cudaMemcpyAsync(h_meta.data(), pidx.meta.get(), n_poly * sizeof(poly_meta<T>),
+                                 cudaMemcpyDeviceToHost, s));
   BSJ_CUDA_TRY(cudaStreamSynchronize(s));
   edge_index<T> ix = pidx.finish(s);
   prof_mark("polygon_index");
-  int const grid = (int)std::min<u64>((u64)num_sms() * 16, (u64)div_up(n_points, 256));
-  pip_bitmask_kernel<T><<<std::max(grid, 1), 256, 0, s>>>(
+
+  // cell-class grid (see bitmask_grid_kernel): worth building when the points outnumber the
+  // cells by far; 2^9 cells per side from 2^20 points, 2^10 from 2^25
+  cell_grid cg{};
+  dev_buf<uint2> cells;
+  if (n_poly && force_reference_mode() == 0) {
+    bool all_safe = true;
+    double ux0 = INFINITY, uy0 = INFINITY, ux1 = -INFINITY, uy1 = -INFINITY, mx = 0;
+    for (auto const& m : h_meta) {
+      all_safe = all_safe && m.safe;
+      ux0 = std::min(ux0, (double)m.xmin); ux1 = std::max(ux1, (double)m.xmax);
+      uy0 = std::min(uy0, (double)m.ymin); uy1 = std::max(uy1, (double)m.ymax);
+      mx = std::max(mx, std::max(std::fabs((double)m.xmin), std::fabs((double)m.xmax)));
+    }
+    if (all_safe && std::isfinite(ux0) && std::isfinite(ux1) && std::isfinite(uy0) &&
+        std::isfinite(uy1)) {
+      // the kernel's per-polygon rejection widens x by eps * max|x| evaluated in T (possibly
+      // contracted to an FMA): 4x that bound is outside every polygon's own threshold
+      double const wx = 4.0 * (double)fpp<T>::eps() * mx + 1e-300;
+      cg.union_valid = 1;
+      cg.ux0 = ux0 - wx; cg.ux1 = ux1 + wx; cg.uy0 = uy0; cg.uy1 = uy1;
+    }
+  }
+  int log2_cells = n_points >= (1ull << 25) ? 10 : n_points >= (1ull << 20) ? 9 : 0;
+  if (const char* e = std::getenv("BSJ_BITMASK_GRID_LOG2")) log2_cells = std::atoi(e);
+  log2_cells = std::min(log2_cells, 12);
+  if (log2_cells >= 1 && n_poly && force_reference_mode() == 0) {
+    double x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
+    for (auto const& m : h_meta) {
+      if (!m.safe || m.n_slabs == 0) continue;
+      x0 = std::min(x0, (double)m.xmin); x1 = std::max(x1, (double)m.xmax);
+      y0 = std::min(y0, (double)m.ymin); y1 = std::max(y1, (double)m.ymax);
+    }
+    double const ext = std::max(x1 - x0, y1 - y0);
+    if (std::isfinite(x0) && std::isfinite(y0) && std::isfinite(ext) && ext > 0) {
+      double const G = (double)(1u << log2_cells);
+      cg.min_x = x0; cg.min_y = y0;
+      cg.scale = ext / G * (1.0 + 1e-12);
+      cg.inv_scale = 1.0 / cg.scale;
+      cg.log2_cells = log2_cells;
+      // The cell index is computed in double from the (exactly converted) coordinate: three
+      // roundings of 2^-53, i.e. a point lies at most ~1e-12 cells outside its cell; the cell's
+      // centre is rounded to T.  The margin covers both with room to spare.
+      double const rel = sizeof(T) == 8 ? 9.094947017729282e-13 /* 2^-40 */
+                                        : 2.384185791015625e-07 /* 2^-22 */;
+      cg.margin_x = rel * (std::fabs(x0) + std::fabs(x0 + ext) + ext) + 1e-9 * cg.scale;
+      cg.margin_y = rel * (std::fabs(y0) + std::fabs(y0 + ext) + ext) + 1e-9 * cg.scale;
+      u64 const n_cells = 1ull << (2 * log2_cells);
+      cells.alloc(n_cells, s);
+      bitmask_grid_kernel<T><<<(unsigned)div_up(n_cells * 32, 256), 256, 0, s>>>(
+        cg, pidx.meta.get(), n_poly, ix, cells.get());
+      BSJ_CHECK_LAUNCH();
+      prof_mark("bitmask_grid");
+    }
+  }
+  int const grid = (int)std::min<u64>((u64)num_sms() * 3, (u64)div_up(n_points, kBmChunk));
+  pip_bitmask_kernel<T><<<std::max(grid, 1), kBmBlock, 0, s>>>(
     (const T*)px, (const T*)py, n_points, pidx.meta.get(), n_poly, ring_offsets, (const T*)vx,
-    (const T*)vy, out, force_reference_mode(), ix);
+    (const T*)vy, out, force_reference_mode(), ix, cg, cells.get());
   BSJ_CHECK_LAUNCH();
   tm.mark("pip_bitmask");
   tm.finish();  // results are ready in stream order; no trailing host synchronisation

@@ -106,17 +106,23 @@ __device__ __forceinline__ u32 point_key(T x, T y, T min_x, T min_y, T max_x, T 
 // The pass count is a template parameter: the tally unrolls to one shift/mask + one shared
 // atomic with an immediate offset per pass.
 // ---------------------------------------------------------------------------------------------
+constexpr int kLeadBins = 8192;
 template <typename T, int PASSES>
 __global__ void __launch_bounds__(512)
 encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T min_x, T min_y,
                    T max_x, T max_y, T scale, u32 oob_key, u32* __restrict__ keys,
-                   u32* __restrict__ hist, u32* __restrict__ point_flags)
+                   u32* __restrict__ hist, u32* __restrict__ point_flags, int bin_shift,
+                   u32 n_bins)
 {
   u32 flags = 0;  // bit 0: a point outside the box (bit 1, a NaN coordinate, is set out of line)
   T const inv_scale = (T)1 / scale;
   constexpr int V = 16 / sizeof(T);  // points per 128-bit load
-  __shared__ u32 s_hist[(PASSES ? PASSES : 1) * kRadixDigits];  // PASSES == 0: keys only
-  for (int i = threadIdx.x; i < PASSES * kRadixDigits; i += blockDim.x) s_hist[i] = 0;
+  // PASSES == 0: keys only; PASSES < 0: ONE histogram of the keys' leading bits (key >>
+  // bin_shift, n_bins <= kLeadBins bins) -- the multi-GPU sharding plan's first level
+  constexpr int kHistWords = PASSES < 0 ? kLeadBins : (PASSES ? PASSES : 1) * kRadixDigits;
+  __shared__ u32 s_hist[kHistWords];
+  int const hist_len = PASSES < 0 ? (int)n_bins : PASSES * kRadixDigits;
+  for (int i = threadIdx.x; i < hist_len; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
 
   u64 const nvec   = n / V;
@@ -126,9 +132,13 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
     (reinterpret_cast<uintptr_t>(keys) & (4 * V - 1)) == 0;
 
   auto tally = [&](u32 k) {
+    if constexpr (PASSES < 0) {
+      atomicAdd(&s_hist[k >> bin_shift], 1u);
+    } else {
 #pragma unroll
-    for (int p = 0; p < PASSES; ++p)
-      atomicAdd(&s_hist[p * kRadixDigits + ((k >> (p * kRadixBits)) & 0xFFu)], 1u);
+      for (int p = 0; p < PASSES; ++p)
+        atomicAdd(&s_hist[p * kRadixDigits + ((k >> (p * kRadixBits)) & 0xFFu)], 1u);
+    }
   };
   auto key_of = [&](T px, T py) {
     return point_key<T>(px, py, min_x, min_y, max_x, max_y, scale, inv_scale, oob_key, flags,
@@ -165,7 +175,7 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < PASSES * kRadixDigits; i += blockDim.x)
+  for (int i = threadIdx.x; i < hist_len; i += blockDim.x)
     if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
   if (flags) atomicOr(point_flags, flags);
 }
@@ -482,7 +492,8 @@ copy_tree_kernel(const u32* __restrict__ k, const u8* __restrict__ l, const u8* 
 template <typename T>
 void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_max, double y_min,
                    double y_max, double scale_d, int max_depth, int passes, u32* keys, u32* hist,
-                   u32* point_flags, bsj_grid* grid, cudaStream_t s)
+                   u32* point_flags, bsj_grid* grid, cudaStream_t s, int bin_shift = 0,
+                   u32 n_bins = 0)
 {
   // the column API casts to T (cpp/src/indexing/point_quadtree.cu:82-84), the header API then
   // orders the corners and clamps scale in T (detail/point_quadtree.cuh:259-268)
@@ -498,9 +509,10 @@ void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_m
     constexpr int P = decltype(pass_tag)::value;
     encode_hist_kernel<T, P><<<std::max(nblk, 1), 512, 0, s>>>(
       (const T*)x, (const T*)y, n, min_x, min_y, max_x, max_y, scale, oob_key, keys, hist,
-      point_flags);
+      point_flags, bin_shift, n_bins);
   };
   switch (passes) {
+    case -1: launch(std::integral_constant<int, -1>{}); break;
     case 0: launch(std::integral_constant<int, 0>{}); break;
     case 1: launch(std::integral_constant<int, 1>{}); break;
     case 2: launch(std::integral_constant<int, 2>{}); break;
@@ -522,7 +534,8 @@ void launch_encode(const void* x, const void* y, u64 n, double x_min, double x_m
 template <typename T>
 void launch_point_keys(const void* x, const void* y, u64 n, double x_min, double x_max,
                        double y_min, double y_max, double scale, int max_depth, u32* keys,
-                       u32* point_flags, cudaStream_t s)
+                       u32* point_flags, cudaStream_t s, u32* lead_bins, int bin_shift,
+                       u32 n_bins)
 {
   dev_buf<u32> flags;
   if (!point_flags) {
@@ -531,13 +544,18 @@ void launch_point_keys(const void* x, const void* y, u64 n, double x_min, double
     point_flags = flags.get();
   }
   bsj_grid g{};
-  launch_encode<T>(x, y, n, x_min, x_max, y_min, y_max, scale, max_depth, /*passes=*/0, keys,
-                   nullptr, point_flags, &g, s);
+  // with `lead_bins` (n_bins <= 8192 counters of key >> bin_shift) the histogram is fused in
+  bool const fused = lead_bins != nullptr && n_bins <= (u32)kLeadBins;
+  launch_encode<T>(x, y, n, x_min, x_max, y_min, y_max, scale, max_depth,
+                   /*passes=*/fused ? -1 : 0, keys, fused ? lead_bins : nullptr, point_flags, &g, s,
+                   bin_shift, n_bins);
 }
 template void launch_point_keys<float>(const void*, const void*, u64, double, double, double,
-                                       double, double, int, u32*, u32*, cudaStream_t);
+                                       double, double, int, u32*, u32*, cudaStream_t, u32*, int,
+                                       u32);
 template void launch_point_keys<double>(const void*, const void*, u64, double, double, double,
-                                        double, double, int, u32*, u32*, cudaStream_t);
+                                        double, double, int, u32*, u32*, cudaStream_t, u32*, int,
+                                        u32);
 
 namespace {
 // Tree rows from the sorted keys, then the exact-size copy-out.  `st->point_flags` carries the

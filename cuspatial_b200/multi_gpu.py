@@ -564,8 +564,10 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
         packed_polys = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=dev)
     else:
         packed_polys = torch.empty(sum(padded), dtype=torch.uint8, device=dev)
-    if packed_polys.numel():
-        dist.broadcast(packed_polys, src=src0, group=group)
+    # the broadcast runs on NCCL's stream while this stream computes keys and histograms; the
+    # polygons are first needed by the local join
+    poly_work = dist.broadcast(packed_polys, src=src0, group=group, async_op=True) \
+        if packed_polys.numel() else None
     polys, o = [], 0
     for t, n, b, pb in zip(polygons, sizes, nbytes, padded):
         polys.append(packed_polys[o: o + b].view(t.dtype) if n else
@@ -600,6 +602,8 @@ def sharded_quadtree_point_in_polygon(points, polygons, x_min, x_max, y_min, y_m
     flags = [int(v) for v in global_ext[n_bins: n_bins + 2].tolist()]
     n_recv = int(rkeys.shape[0])
     prof.mark("partition_exchange")
+    if poly_work is not None:
+        poly_work.wait()   # stream-ordered for NCCL (no host synchronisation)
     # 4. the single-GPU path on this rank's key range, stopped at the compact result
     pidx_global, comp, n_hits = local_compact(rkeys, rgids, points, flags, polys, bbox, scale,
                                               max_depth, max_size)

@@ -162,9 +162,14 @@ def test_cell_aligned_polygons_at_extent(oracle_lib, ext, dtype, depth, max_size
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("grid_log2", ["0", "5", "10"])
 @pytest.mark.parametrize("ext,dtype", EXT_PARAMS)
-def test_bitmask_at_extent(oracle_lib, ext, dtype):
+def test_bitmask_at_extent(oracle_lib, ext, dtype, grid_log2, monkeypatch):
+    """grid_log2: side of the bitmask kernel's cell-class grid (0 = off; the library only turns
+    it on by itself from 2^20 points)."""
     import torch
+
+    monkeypatch.setenv("BSJ_BITMASK_GRID_LOG2", grid_log2)
 
     import cuspatial_b200 as cs
 

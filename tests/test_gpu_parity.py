@@ -80,8 +80,10 @@ def test_golden_small_join_and_pip(golden, dtype):
     assert pairs["quad_offset"].cpu().numpy().tolist() == lj["quad_offset"]
 
 
+@pytest.mark.parametrize("grid_log2", ["0", "3", "8"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_golden_bitmask_predicate_cases(golden, dtype):
+def test_golden_bitmask_predicate_cases(golden, dtype, grid_log2, monkeypatch):
+    monkeypatch.setenv("BSJ_BITMASK_GRID_LOG2", grid_log2)
     import cuspatial_b200 as cs
 
     for c in golden["pip_cases"]:
@@ -291,11 +293,20 @@ def test_special_values_fall_back_to_reference_loop(oracle_lib, dtype):
     assert_same(run_gpu(c2, 64), run_host(oracle_lib, c2, 64), "special values")
 
 
+@pytest.mark.parametrize("grid_log2", ["0", "4", "9", "11"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_bitmask_equals_oracle(oracle_lib, dtype):
+def test_bitmask_equals_oracle(oracle_lib, dtype, grid_log2, monkeypatch):
+    """Uniform points, points far outside the polygons' box, NaN / Inf / denormal coordinates;
+    with the cell-class grid off and at three resolutions (0 = off)."""
     import cuspatial_b200 as cs
 
+    monkeypatch.setenv("BSJ_BITMASK_GRID_LOG2", grid_log2)
     c = make_case(300000, 31, 8, "u", dtype, seed=3, median_vertices=60)
+    x, y = c["x"].copy(), c["y"].copy()
+    x[:20] = np.nan; y[20:40] = np.nan; x[40:50] = np.inf; y[50:60] = -np.inf
+    x[60:70] = dtype(1e-310) if dtype == np.float64 else dtype(1e-42)
+    x[100:200] += dtype(5.0); y[200:300] -= dtype(7.0); x[300:400] = -x[300:400]
+    c = dict(c, x=x, y=y)
     po, ro = c["po"].astype(np.int32), c["ro"].astype(np.int32)
     want = oracle_lib.point_in_polygon(c["x"], c["y"], po, ro, c["vx"], c["vy"])
     got = cs.point_in_polygon_bitmask((_t(c["x"]), _t(c["y"])),
