@@ -12,11 +12,12 @@ from .api import (contains_properly, join_quadtree_and_bounding_boxes,
                   polygon_bounding_boxes, quadtree_on_points, quadtree_point_in_polygon)
 from .frame import Frame
 from .geoarrow import from_linestrings_xy, from_points_xy, from_polygons_xy
+from .geopandas_reader import from_geopandas
 
 __all__ = [
     "quadtree_on_points", "join_quadtree_and_bounding_boxes", "quadtree_point_in_polygon",
     "point_in_polygon", "point_in_polygon_bitmask", "polygon_bounding_boxes",
     "pairwise_point_in_polygon", "contains_properly", "quadtree_point_to_nearest_linestring",
     "linestring_bounding_boxes", "from_points_xy", "from_polygons_xy", "from_linestrings_xy",
-    "Frame",
+    "from_geopandas", "Frame",
 ]

@@ -102,6 +102,41 @@ def _split_points(points):
     return x, y
 
 
+class _Binding:
+    """What a quadtree's cell-geometry hint (bsj_grid + sorted keys) describes: the point buffers
+    the tree was built from and its point_indices.  The source tensors are kept alive (so their
+    addresses cannot be recycled for other data) together with their in-place modification
+    counters; quadtree_point_in_polygon forwards the hint only for exactly these buffers,
+    unmodified -- any other `points` / `point_indices` take the hint-free path, whose result is
+    the reference's by construction."""
+
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+        self.versions = [t._version for t in self.tensors]
+
+    @staticmethod
+    def sources(points):
+        pts = _accessor(points, "points")
+        if hasattr(pts, "xy") and hasattr(pts, "x"):
+            srcs = [pts.xy]
+        elif isinstance(pts, (tuple, list)):
+            srcs = list(pts)
+        else:
+            srcs = [pts]
+        return srcs if all(isinstance(t, torch.Tensor) for t in srcs) else None
+
+    def matches(self, tensors):
+        if tensors is None or len(tensors) != len(self.tensors):
+            return False
+        for a, b, v in zip(self.tensors, tensors, self.versions):
+            same = a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape and
+                              a.stride() == b.stride() and a.dtype == b.dtype and
+                              a._version == b._version)
+            if not same or a._version != v:
+                return False
+        return True
+
+
 def _split_polygons(polygons):
     polygons = _accessor(polygons, "polygons")
     if hasattr(polygons, "part_offset"):
@@ -177,7 +212,26 @@ def quadtree_on_points(points, x_min, x_max, y_min, y_max, scale, max_depth, max
     tree._grid = g
     # the hint points at the sorted Morton keys: keep that buffer alive with the Frame
     tree._sorted_keys = alloc.take(out.sorted_keys, n, torch.uint32)
+    # ... and is only valid for these very buffers (see _Binding)
+    srcs = _Binding.sources(points)
+    tree._hint_points = _Binding(srcs) if srcs is not None else None
+    tree._hint_indices = _Binding([point_indices])
     return point_indices, tree
+
+
+def _hint_for(quadtree, points, point_indices):
+    """The tree's bsj_grid if `points` / `point_indices` are the buffers it was computed from."""
+    grid = getattr(quadtree, "_grid", None)
+    if grid is None:
+        return None
+    bp, bi = getattr(quadtree, "_hint_points", None), getattr(quadtree, "_hint_indices", None)
+    if bp is None or bi is None:
+        return None
+    if not bp.matches(_Binding.sources(points)):
+        return None
+    if not (isinstance(point_indices, torch.Tensor) and bi.matches([point_indices])):
+        return None
+    return grid
 
 
 def join_quadtree_and_bounding_boxes(quadtree, bounding_boxes, x_min, x_max, y_min, y_max, scale,
@@ -245,7 +299,7 @@ def quadtree_point_in_polygon(poly_quad_pairs, quadtree, point_indices, points, 
     with torch.cuda.device(dev):
         alloc = _TorchAllocator(dev)
         out = _lib.bsj_pairs()
-        grid = getattr(quadtree, "_grid", None)
+        grid = _hint_for(quadtree, points, point_indices)
         rc = _lib.lib().bsj_quadtree_point_in_polygon_ex(
             _ptr(pp), _ptr(pq), pp.shape[0], *[_ptr(t) for t in tcols], tcols[0].shape[0],
             _ptr(pi), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], _ptr(po), po.shape[0],
@@ -281,7 +335,7 @@ def quadtree_point_in_polygon_compact(poly_quad_pairs, quadtree, point_indices, 
     with torch.cuda.device(dev):
         alloc = _TorchAllocator(dev)
         out = _lib.bsj_pip_compact()
-        grid = getattr(quadtree, "_grid", None)
+        grid = _hint_for(quadtree, points, point_indices)
         rc = _lib.lib().bsj_quadtree_point_in_polygon_compact(
             _ptr(pp), _ptr(pq), pp.shape[0], *[_ptr(t) for t in tcols], tcols[0].shape[0],
             _ptr(pi), _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], _ptr(po), po.shape[0],

@@ -1,5 +1,6 @@
 // api.cu -- the C ABI (include/cuspatial_b200.h): validation, error translation, allocation
 // plumbing.  The reference-side checks are cited next to each condition.
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 
 #include <cstdlib>
@@ -179,6 +180,17 @@ stage_timer::~stage_timer()
 }
 
 namespace {
+// NVTX range over an entry point (the reference's CUSPATIAL_FUNC_RANGE,
+// cpp/include/cuspatial/detail/nvtx/ranges.hpp:25-46): header-only NVTX 3, a no-op unless a
+// profiler has injected itself.
+struct func_range {
+  explicit func_range(const char* name) { nvtxRangePushA(name); }
+  ~func_range() { nvtxRangePop(); }
+  func_range(func_range const&)            = delete;
+  func_range& operator=(func_range const&) = delete;
+};
+#define BSJ_FUNC_RANGE() ::bsj::func_range bsj_nvtx_range_(__func__)
+
 template <typename F>
 int guarded(F&& f)
 {
@@ -215,6 +227,7 @@ int bsj_quadtree_on_points(const void* x, const void* y, int dtype, uint64_t n, 
                            int8_t max_depth, int32_t max_size, const bsj_allocator* mr,
                            bsj_stream_t stream, bsj_quadtree* out)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
     *out = bsj_quadtree{};
@@ -236,6 +249,7 @@ int bsj_join_quadtree_and_bounding_boxes(const uint32_t* key, const uint8_t* lev
                                          const bsj_allocator* mr, bsj_stream_t stream,
                                          bsj_pairs* out)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
     *out = bsj_pairs{};
@@ -264,6 +278,7 @@ int bsj_quadtree_point_in_polygon_ex(const uint32_t* pair_poly, const uint32_t* 
                                      uint64_t n_poly_points, const bsj_grid* grid,
                                      const bsj_allocator* mr, bsj_stream_t stream, bsj_pairs* out)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
     *out = bsj_pairs{};
@@ -313,6 +328,7 @@ int bsj_quadtree_point_in_polygon_compact(
   const void* poly_points_x, const void* poly_points_y, uint64_t n_poly_points,
   const bsj_grid* grid, const bsj_allocator* mr, bsj_stream_t stream, bsj_pip_compact* out)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
     *out = bsj_pip_compact{};
@@ -339,6 +355,7 @@ int bsj_quadtree_point_in_polygon_compact_seg(
   const void* poly_points_x, const void* poly_points_y, uint64_t n_poly_points,
   const bsj_grid* grid, const bsj_allocator* mr, bsj_stream_t stream, bsj_pip_compact* out)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
     *out = bsj_pip_compact{};
@@ -362,6 +379,7 @@ int bsj_expand_pip_compact(const uint32_t* pair_poly, const bsj_pip_compact* c,
                            uint32_t position_base, bsj_stream_t stream,
                            uint32_t* out_polygon_index, uint32_t* out_point_index)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(c != nullptr, "compact result must not be NULL");
     BSJ_EXPECTS(c->n_hits == 0 || (pair_poly && out_polygon_index && out_point_index),
@@ -377,6 +395,7 @@ int bsj_point_in_polygon(const void* point_x, const void* point_y, int dtype, ui
                          const void* poly_points_x, const void* poly_points_y,
                          uint64_t n_poly_points, bsj_stream_t stream, int32_t* out_mask)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     check_dtype(dtype);
     // point_in_polygon.cu:118-121
@@ -395,6 +414,7 @@ int bsj_pairwise_point_in_polygon(const void* point_x, const void* point_y, int 
                                   const void* poly_points_y, uint64_t n_poly_points,
                                   bsj_stream_t stream, uint8_t* out_flags)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     check_dtype(dtype);
     // point_in_polygon.cu:108-110
@@ -416,6 +436,7 @@ int bsj_quadtree_point_to_nearest_linestring(
   bsj_stream_t stream, uint32_t* out_point_index, uint32_t* out_linestring_index,
   void* out_distance, uint64_t* out_rows)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     (void)key; (void)level; (void)is_internal_node;
     BSJ_EXPECTS(out_rows != nullptr, "output row count must not be NULL");
@@ -443,6 +464,7 @@ int bsj_linestring_bounding_boxes(const uint32_t* linestring_offsets,
                                   double expansion_radius, bsj_stream_t stream, void* out_x_min,
                                   void* out_y_min, void* out_x_max, void* out_y_max)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     check_dtype(dtype);
     // linestring_bounding_boxes.cu:135-141
@@ -462,6 +484,7 @@ int bsj_polygon_bounding_boxes(const uint32_t* poly_offsets, uint64_t n_poly_off
                                bsj_stream_t stream, void* out_x_min, void* out_y_min,
                                void* out_x_max, void* out_y_max)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     check_dtype(dtype);
     // polygon_bounding_boxes.cu:144-151
@@ -478,6 +501,7 @@ int bsj_point_keys_histogram(const void* x, const void* y, int dtype, uint64_t n
                              int8_t max_depth, int hist_shift, uint32_t* keys, uint32_t* bins,
                              uint64_t n_bins, uint32_t* point_flags, bsj_stream_t stream)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     check_dtype(dtype);
     BSJ_EXPECTS(n == 0 || (x && y && keys), "x and y columns must have the same length");
@@ -490,6 +514,7 @@ int bsj_shard_plan_level1(const uint32_t* global_hist, uint64_t n_bins,
                           const uint32_t* host_rank_sizes, int n_ranks, int rank, int hist_shift,
                           int sub_shift, uint32_t n_sub, bsj_shard_plan* plan, bsj_stream_t stream)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(global_hist && host_rank_sizes && plan, "plan inputs must not be NULL");
     shard_plan_level1_impl(global_hist, n_bins, host_rank_sizes, n_ranks, rank, hist_shift,
@@ -500,6 +525,7 @@ int bsj_shard_plan_level1(const uint32_t* global_hist, uint64_t n_bins,
 int bsj_shard_subhistogram(const uint32_t* keys, uint64_t n, const bsj_shard_plan* plan,
                            int n_ranks, uint32_t n_sub, uint32_t* bins, bsj_stream_t stream)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(n == 0 || (keys && bins && plan), "keys, bins and plan must not be NULL");
     BSJ_EXPECTS(n_ranks >= 1 && n_ranks <= BSJ_MAX_RANKS && n_sub >= 1 &&
@@ -512,6 +538,7 @@ int bsj_shard_subhistogram(const uint32_t* keys, uint64_t n, const bsj_shard_pla
 int bsj_shard_plan_level2(const uint32_t* local_hist, uint64_t n_bins, const uint32_t* local_sub,
                           const uint32_t* global_sub, bsj_shard_plan* plan, bsj_stream_t stream)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(local_hist && local_sub && global_sub && plan, "plan inputs must not be NULL");
     shard_plan_level2_impl(local_hist, n_bins, local_sub, global_sub, plan, (cudaStream_t)stream);
@@ -521,6 +548,7 @@ int bsj_shard_plan_level2(const uint32_t* local_hist, uint64_t n_bins, const uin
 int bsj_shard_plan_finalize(const uint32_t* counts_matrix, uint64_t capacity, bsj_shard_plan* plan,
                             bsj_stream_t stream)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(counts_matrix && plan, "plan inputs must not be NULL");
     shard_plan_finalize_impl(counts_matrix, capacity, plan, (cudaStream_t)stream);
@@ -531,6 +559,7 @@ int bsj_partition_keys(const uint32_t* keys, uint64_t n, const bsj_shard_plan* p
                        uint32_t* const* dst_key, uint32_t* const* dst_gid, int use_bulk_copy,
                        bsj_stream_t stream)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(plan && dst_key && dst_gid, "destination pointer tables must not be NULL");
     partition_keys_impl(keys, n, plan, n_ranks, dst_key, dst_gid, use_bulk_copy,
@@ -542,6 +571,7 @@ int bsj_quadtree_on_keys(uint32_t* keys, uint32_t* values, uint64_t n, const bsj
                          int32_t max_size, const bsj_allocator* mr, bsj_stream_t stream,
                          bsj_quadtree* out)
 {
+  BSJ_FUNC_RANGE();
   return guarded([&] {
     BSJ_EXPECTS(out != nullptr, "output struct must not be NULL");
     *out = bsj_quadtree{};

@@ -779,7 +779,7 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                       const T* __restrict__ vy, const u64* __restrict__ wbase,
                       u32* __restrict__ mask_words, u32* __restrict__ hits,
                       u32* __restrict__ ticket, const u8* __restrict__ cls, edge_index<T> ix,
-                      grid_info grid, const u32* __restrict__ sorted_keys)
+                      grid_info grid, const u32* __restrict__ sorted_keys, u32 coop_edges)
 {
   u32 const lane   = lane_id();
   u32 const n_list = min(*run_count, list_capacity);
@@ -890,7 +890,7 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                        ty0 <= fmax((double)ay, (double)by) + dl &&
                        fmax((double)ax, (double)bx) + dxl >= tx0;
               };
-              if (kend - kbeg > kCoopEdges) {
+              if (kend - kbeg > coop_edges) {
                 // ---- point-by-point form (many candidate edges: a large, sparse quadrant)
                 u32 cross = 0, near = oob;
 #pragma unroll
@@ -1735,13 +1735,19 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
     u32 const list_cap32 = (u32)std::min<u64>(list_cap, 0xFFFFFFFFull);
     if (cells) {
       int const grid_dim = (int)std::min<u64>((u64)num_sms() * 8, (u64)div_up(list_cap, kPipWarps));
+      static int coop_env = -1;
+      if (coop_env < 0) {
+        const char* e = std::getenv("BSJ_PIP_COOP_EDGES");
+        coop_env = e ? std::atoi(e) : (int)kCoopEdges;
+      }
+      u32 const coop_edges = (u32)coop_env;
       auto launch = [&](auto const& src) {
         constexpr bool SEG = std::is_same<std::decay_t<decltype(src)>, coord_source<T, true>>::value;
         pip_eval_cells_kernel<T, SEG><<<std::max(grid_dim, 1), kPipWarps * 32, 0, s>>>(
           pair_poly, pair_quad, run_list.get(), tile_list.get(), list_cap32,
           run_count.get(), length, offset, point_indices, (u32)n_points, src, meta.get(), n_poly,
           ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words,
-          c->pair_hits, ticket.get(), c->pair_class, ix, gi, gi.sorted_keys);
+          c->pair_hits, ticket.get(), c->pair_class, ix, gi, gi.sorted_keys, coop_edges);
       };
       if (segmented) launch(spts); else launch(pts);
       BSJ_CHECK_LAUNCH();

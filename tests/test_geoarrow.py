@@ -86,3 +86,51 @@ def test_geoarrow_series_through_the_whole_path(golden, dtype):
     first_two = lv[: n["line_offsets"][2]]
     assert len(lb) == 3
     assert float(lb["minx"][0]) == first_two[:, 0].min() and float(lb["maxy"][0]) == first_two[:, 1].max()
+
+
+class _Geo:
+    """Stand-in for a shapely geometry: all the reader needs is `__geo_interface__`."""
+
+    def __init__(self, kind, coords):
+        self.__geo_interface__ = {"type": kind, "coordinates": coords}
+
+
+def test_geopandas_reader_walks_the_geo_interface_like_the_reference():
+    """geopandas_reader.py:27-84 reads shapely.geometry.mapping(geom)['coordinates']; so does this
+    reader, for any object speaking __geo_interface__ (shapely itself is not installed here)."""
+    sq = lambda x0, y0: ((x0, y0), (x0 + 1, y0), (x0 + 1, y0 + 1), (x0, y0 + 1), (x0, y0))  # noqa: E731
+    hole = ((0.2, 0.2), (0.2, 0.4), (0.4, 0.4), (0.4, 0.2), (0.2, 0.2))
+    polys = cs.from_geopandas([_Geo("Polygon", (sq(0, 0), hole)),
+                               {"type": "MultiPolygon", "coordinates": [(sq(5, 5),), (sq(8, 8),)]}])
+    a = polys.polygons
+    assert len(polys) == 2 and ga.is_multi(polys)
+    assert a.geometry_offset.tolist() == [0, 1, 3] and a.part_offset.tolist() == [0, 2, 3, 4]
+    assert a.ring_offset.tolist() == [0, 5, 10, 15, 20] and a.xy.dtype == torch.float64
+    assert a.x[:5].tolist() == [0, 1, 1, 0, 0] and a.y[5:10].tolist() == [0.2, 0.4, 0.4, 0.2, 0.2]
+    pts = cs.from_geopandas([_Geo("Point", (1.5, 2.5)), _Geo("Point", (3.0, 4.0, 9.0))], np.float32)
+    assert pts.points.xy.tolist() == [1.5, 2.5, 3.0, 4.0] and pts.points.xy.dtype == torch.float32
+    ls = cs.from_geopandas([_Geo("LineString", ((0, 0), (1, 1), (2, 0))),
+                            _Geo("MultiLineString", (((5, 5), (6, 6)), ((7, 7), (8, 8), (9, 9))))])
+    assert ls.lines.part_offset.tolist() == [0, 3, 5, 8] and ls.lines.geometry_offset.tolist() == [0, 1, 3]
+    with pytest.raises(TypeError, match="mixes"):
+        cs.from_geopandas([_Geo("Point", (0, 0)), _Geo("Polygon", (sq(0, 0),))])
+    with pytest.raises(TypeError, match="unsupported geometry type"):
+        cs.from_geopandas([_Geo("MultiPoint", ((0, 0), (1, 1)))])
+    with pytest.raises(TypeError):
+        cs.from_geopandas([object()])
+
+
+def test_geopandas_reader_on_real_shapely_objects_when_installed():
+    """Run-time probe: with shapely / geopandas importable the same reader takes their objects
+    (and a GeoSeries) unchanged.  Neither can be installed offline in this image -> skipped."""
+    shapely_geometry = pytest.importorskip("shapely.geometry")
+    polys = [shapely_geometry.Polygon([(0, 0), (1, 0), (1, 1), (0, 1)]),
+             shapely_geometry.Polygon([(5, 5), (6, 5), (6, 6), (5, 6)])]
+    try:
+        import geopandas
+
+        polys = geopandas.GeoSeries(polys)
+    except ImportError:
+        pass
+    s = cs.from_geopandas(polys)
+    assert len(s) == 2 and s.polygons.ring_offset.tolist() == [0, 5, 10]

@@ -315,6 +315,52 @@ def test_bitmask_equals_oracle(oracle_lib, dtype, grid_log2, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_hint_is_bound_to_the_buffers_it_describes(oracle_lib, dtype):
+    """The cell-geometry hint rides on the quadtree Frame but describes ONE set of point buffers.
+    Passing other points of the same length (a permuted copy, or the same tensors modified in
+    place) or another point_indices must give what the reference gives for THOSE arguments --
+    the rows of the hint-free path -- not rows decided from the stale keys."""
+    import torch
+
+    import cuspatial_b200 as cs
+
+    c = make_case(50000, 30, 10, "u", dtype, seed=21, median_vertices=40)
+    ext = c["ext"]
+    x, y = _t(c["x"]), _t(c["y"])
+    polys = tuple(_t(a) for a in (c["po"], c["ro"], c["vx"], c["vy"]))
+    pidx, tree = cs.quadtree_on_points((x, y), ext[0], ext[1], ext[2], ext[3], c["scale"],
+                                       c["depth"], 32)
+    bb = cs.polygon_bounding_boxes(polys)
+    pairs = cs.join_quadtree_and_bounding_boxes(tree, bb, ext[0], ext[1], ext[2], ext[3],
+                                                c["scale"], c["depth"])
+
+    def rows(points, indices, drop_hint=False):
+        t = tree
+        if drop_hint:
+            t = cs.Frame([(k, tree[k]) for k in tree.columns])
+        h = cs.quadtree_point_in_polygon(pairs, t, indices, points, polys)
+        return h["polygon_index"].cpu().numpy(), h["point_index"].cpu().numpy()
+
+    base = rows((x, y), pidx)
+    np.testing.assert_array_equal(base[0], rows((x, y), pidx, drop_hint=True)[0])
+    perm = torch.randperm(x.shape[0], device=x.device)
+    x2, y2 = x[perm].contiguous(), y[perm].contiguous()
+    for got, want in ((rows((x2, y2), pidx), rows((x2, y2), pidx, drop_hint=True)),
+                      (rows((x, y), pidx.flip(0).contiguous()),
+                       rows((x, y), pidx.flip(0).contiguous(), drop_hint=True))):
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+    assert not (len(base[0]) == len(rows((x2, y2), pidx)[0]) and
+                np.array_equal(base[1], rows((x2, y2), pidx)[1])), "permutation changed nothing?"
+    # in-place modification of the very tensors the tree was built from
+    x.copy_(x2)
+    y.copy_(y2)
+    got, want = rows((x, y), pidx), rows((x2, y2), pidx, drop_hint=True)
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_golden_pairwise_cases(golden, dtype):
     """pairwise_point_in_polygon_test.cu known answers (point i vs polygon i)."""
     import cuspatial_b200 as cs
