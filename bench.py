@@ -565,7 +565,9 @@ def e2e_single(dev, n, tdt, polys_np, ext, scale, x, y, n_hits, steps):
         e.record(main)
     run(2)
     torch.cuda.synchronize(dev)
-    k = max(2, min(steps, 6))
+    # a pipeline has a fill (first upload) and a drain (last read-back) that no step overlaps:
+    # run enough steps for the steady state to dominate (20 by default, ~0.6 s)
+    k = max(8, min(4 * steps, 24))
     t0 = time.perf_counter()
     d2h = run(k)
     dt = (time.perf_counter() - t0) / k

@@ -7,8 +7,10 @@
 //   1  same, count and match word in separate 32-bit arrays (all 32 banks instead of 16 pairs)
 //   2  peers found with eight warp votes (no shared-memory traffic, no atomics); only the
 //      running count lives in shared memory (one 32-bit load + one leader store per round)
+//   3  as 1, but only the lowest peer touches the running count (atomicAdd returning the old
+//      value) and hands it to its peers with a shuffle: one load less per round   [default]
 #ifndef BSJ_SORT_RANK
-#define BSJ_SORT_RANK 1
+#define BSJ_SORT_RANK 3
 #endif
 // Tile id: 0 = blockIdx.x (CTAs of a 1-D grid are dispatched in index order, so every
 // predecessor a look-back can wait for is already resident or done -- what cub::DeviceScan has
@@ -39,7 +41,7 @@ struct sort_smem {
   uint2 whist[kWarps * kRadixDigits];
 #else
   u32 wcnt[kWarps * kRadixDigits];   // running count -> exclusive warp offset (+ bin start)
-#if BSJ_SORT_RANK == 1
+#if BSJ_SORT_RANK == 1 || BSJ_SORT_RANK == 3
   u32 wmask[kWarps * kRadixDigits];  // match mask of the current round
 #endif
 #endif
@@ -158,7 +160,7 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
 #else
   for (int i = tid; i < kWarps * kRadixDigits; i += kSortBlock) {
     sm.wcnt[i] = 0u;
-#if BSJ_SORT_RANK == 1
+#if BSJ_SORT_RANK == 1 || BSJ_SORT_RANK == 3
     sm.wmask[i] = 0u;
 #endif
   }
@@ -224,6 +226,29 @@ onesweep_kernel(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in
     }
     rank[i] = (unsigned short)(cnt + __popc(below));
     __syncwarp();
+  }
+#elif BSJ_SORT_RANK == 3
+  // as 1, but only the lowest peer touches the running count (atomicAdd returning the old
+  // value) and hands it to its peers with a shuffle: one shared-memory load less per round
+  u32* const wc = sm.wcnt + warp * kRadixDigits;
+  u32* const wm = sm.wmask + warp * kRadixDigits;
+  u32 const mybit = 1u << lane;
+#pragma unroll
+  for (int i = 0; i < kSortIPT; ++i) {
+    u32 const d = (key[i] >> shift) & 0xFFu;
+    atomicOr(&wm[d], mybit);
+    __syncwarp();
+    u32 const peers = wm[d];
+    u32 const below = peers & lt;
+    u32 cnt = 0;
+    __syncwarp();
+    if (below == 0) {
+      cnt   = atomicAdd(&wc[d], __popc(peers));
+      wm[d] = 0u;
+    }
+    cnt     = __shfl_sync(0xFFFFFFFFu, cnt, __ffs(peers) - 1);
+    rank[i] = (unsigned short)(cnt + __popc(below));
+    __syncwarp();  // the cleared match word is ordered before the next round's atomics
   }
 #else
   // Peers by eight votes: after bit b the mask keeps the lanes whose digit agrees with mine on

@@ -27,6 +27,11 @@ void configure_once_per_device(int, void (*f)()) { f(); }
 }  // namespace bsj
 
 using namespace bsj;
+#ifndef BSJ_SORT_RANK
+#define BSJ_SORT_RANK_PRINT -1 /* library default */
+#else
+#define BSJ_SORT_RANK_PRINT BSJ_SORT_RANK
+#endif
 
 __global__ void fill(u32* k, size_t n, u32 mask, int mode)
 {
@@ -116,7 +121,7 @@ int main(int argc, char** argv)
     bool ok  = run_once(n_big, 0x3FFFFFFFu, 0, bits, false, &ms);
     int const p = passes_for_bits(0, bits);
     printf("RANK=%d radix_bits=%d n=%zu bits=%d: best %.3f ms total, %.3f ms/pass (%s)\n",
-           BSJ_SORT_RANK, kRadixBits, n_big, bits, ms, ms / p, ok ? "ok" : "CUDA ERROR");
+           BSJ_SORT_RANK_PRINT, kRadixBits, n_big, bits, ms, ms / p, ok ? "ok" : "CUDA ERROR");
     all_ok = all_ok && ok;
   }
   return all_ok ? 0 : 1;
