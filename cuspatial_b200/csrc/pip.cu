@@ -382,10 +382,21 @@ __device__ __forceinline__ u32 undilate16p(u32 v)
   return v;
 }
 
-// warp-cooperative; all lanes return the same class
+// What the edge pass of one (quadrant, polygon) test needs.
 template <typename T>
-__device__ int classify_quadrant(const grid_info& g, u32 key, u32 level, const poly_meta<T>& m,
-                                 const edge_index<T>& ix)
+struct quad_query {
+  double ex0, ex1, ey0, ey1;   // the cell rectangle widened by the rounding margin
+  T cx, cy;                    // its centre
+  u32 kbeg, kmid, kend;        // slab entries [kbeg, kend); beyond kmid only those flagged "first"
+  u32 n_vertical, vert_begin;  // the polygon's vertical edges
+};
+
+// Part 1 (per thread, no cooperation): the rectangle, the exact box rejection, the slab range.
+// Returns kClsOutside / kClsBoundary when that already decides, -1 when the edges must be looked at.
+template <typename T>
+__device__ __forceinline__ int quadrant_setup(const grid_info& g, u32 key, u32 level,
+                                              const poly_meta<T>& m, const edge_index<T>& ix,
+                                              quad_query<T>& q)
 {
   int const sh = g.max_depth - 1 - (int)level;
   if (!g.valid || !m.safe || sh < 0 || m.n_slabs == 0) return kClsBoundary;
@@ -395,50 +406,79 @@ __device__ int classify_quadrant(const grid_info& g, u32 key, u32 level, const p
   double const kx = (double)undilate16p(key), ky = (double)undilate16p(key >> 1);
   double const x0 = g.min_x + kx * ls, x1 = g.min_x + (kx + 1.0) * ls;
   double const y0 = g.min_y + ky * ls, y1 = g.min_y + (ky + 1.0) * ls;
-  double const ex0 = x0 - g.margin_x, ex1 = x1 + g.margin_x;
-  double const ey0 = y0 - g.margin_y, ey1 = y1 + g.margin_y;
+  q.ex0 = x0 - g.margin_x; q.ex1 = x1 + g.margin_x;
+  q.ey0 = y0 - g.margin_y; q.ey1 = y1 + g.margin_y;
   double const eps = (double)fpp<T>::eps();
   {
     double const dx = eps * fmax(fabs((double)m.xmin), fabs((double)m.xmax));
     double const dy = eps * fmax(fabs((double)m.ymin), fabs((double)m.ymax));
-    if (ex1 < (double)m.xmin - dx || ex0 > (double)m.xmax + dx || ey1 < (double)m.ymin - dy ||
-        ey0 > (double)m.ymax + dy)
+    if (q.ex1 < (double)m.xmin - dx || q.ex0 > (double)m.xmax + dx ||
+        q.ey1 < (double)m.ymin - dy || q.ey0 > (double)m.ymax + dy)
       return kClsOutside;
   }
-  T const cx = (T)(0.5 * (x0 + x1)), cy = (T)(0.5 * (y0 + y1));
-  u32 const lane = lane_id();
-  bool near  = false;
-  u32 cross  = 0;
+  q.cx = (T)(0.5 * (x0 + x1));
+  q.cy = (T)(0.5 * (y0 + y1));
   // edges whose (tolerance-widened) y-range meets the rectangle's: slabs q0..q1 of the index.
   // An edge listed in several slabs is taken once: in slab q0, or where it is flagged "first".
-  u32 const q0 = slab_of<T>((T)ey0, m), q1 = slab_of<T>((T)ey1, m);
-  u32 const kbeg = __ldg(ix.slab_start + m.slab_base + q0);
-  u32 const kmid = __ldg(ix.slab_start + m.slab_base + q0 + 1);
-  u32 const kend = __ldg(ix.slab_start + m.slab_base + q1 + 1);
-  for (u32 k = kbeg + lane; k < kend; k += 32) {
-    u32 const ent = __ldg(ix.entries + k);
-    if (k >= kmid && !(ent & kFirstFlag)) continue;
-    edge_rec<T> const e = ix.edges[ent & ~kFirstFlag];
-    double const d = eps * fmax(fmax(fabs((double)e.ax), fabs((double)e.bx)),
-                                fmax(fabs((double)e.ay), fabs((double)e.by)));
-    double const lx = fmin((double)e.ax, (double)e.bx) - d, hx = fmax((double)e.ax, (double)e.bx) + d;
-    if (hx < ex0) continue;  // wholly left of the rectangle: cannot touch it, never toggles
-    double const ly = fmin((double)e.ay, (double)e.by) - d, hy = fmax((double)e.ay, (double)e.by) + d;
-    near = near || !(hx < ex0 || lx > ex1 || hy < ey0 || ly > ey1);
-    bool const f1 = e.ay > cy, f0 = e.by > cy;
-    if (f1 != f0) {
-      T const u = fpp<T>::mul(fpp<T>::sub(e.bx, e.ax), fpp<T>::sub(cy, e.ay));
-      T const v = fpp<T>::mul(fpp<T>::sub(cx, e.ax), fpp<T>::sub(e.by, e.ay));
-      cross ^= (u32)((v < u) != f1);
+  u32 const q0 = slab_of<T>((T)q.ey0, m), q1 = slab_of<T>((T)q.ey1, m);
+  q.kbeg = __ldg(ix.slab_start + m.slab_base + q0);
+  q.kmid = __ldg(ix.slab_start + m.slab_base + q0 + 1);
+  q.kend = __ldg(ix.slab_start + m.slab_base + q1 + 1);
+  q.n_vertical = m.n_vertical;
+  q.vert_begin = m.vert_begin;
+  return -1;
+}
+
+// Part 2 (cooperative over groups of W consecutive lanes, `q` uniform inside a group; every lane
+// of the warp must call it, `active` false for groups with nothing to do): the group's lanes
+// stride the candidate edges; all lanes of a group return the same class.
+template <typename T, int W>
+__device__ __forceinline__ int quadrant_edges(const quad_query<T>& q, bool active,
+                                              const edge_index<T>& ix)
+{
+  double const eps = (double)fpp<T>::eps();
+  u32 const lane = lane_id(), sub = lane % W, gsh = (lane / W) * W;
+  u32 const gm   = W == 32 ? 0xffffffffu : ((1u << (W & 31)) - 1u);
+  bool near  = false;
+  u32 cross  = 0;
+  if (active) {
+    for (u32 k = q.kbeg + sub; k < q.kend; k += W) {
+      u32 const ent = __ldg(ix.entries + k);
+      if (k >= q.kmid && !(ent & kFirstFlag)) continue;
+      edge_rec<T> const e = ix.edges[ent & ~kFirstFlag];
+      double const d = eps * fmax(fmax(fabs((double)e.ax), fabs((double)e.bx)),
+                                  fmax(fabs((double)e.ay), fabs((double)e.by)));
+      double const lx = fmin((double)e.ax, (double)e.bx) - d, hx = fmax((double)e.ax, (double)e.bx) + d;
+      if (hx < q.ex0) continue;  // wholly left of the rectangle: cannot touch it, never toggles
+      double const ly = fmin((double)e.ay, (double)e.by) - d, hy = fmax((double)e.ay, (double)e.by) + d;
+      near = near || !(hx < q.ex0 || lx > q.ex1 || hy < q.ey0 || ly > q.ey1);
+      bool const f1 = e.ay > q.cy, f0 = e.by > q.cy;
+      if (f1 != f0) {
+        T const u = fpp<T>::mul(fpp<T>::sub(e.bx, e.ax), fpp<T>::sub(q.cy, e.ay));
+        T const v = fpp<T>::mul(fpp<T>::sub(q.cx, e.ax), fpp<T>::sub(e.by, e.ay));
+        cross ^= (u32)((v < u) != f1);
+      }
+    }
+    // vertical edges reject points with the same x at ANY y
+    for (u32 k = sub; k < q.n_vertical; k += W) {
+      T const ax = ix.edges[__ldg(ix.vert_edges + q.vert_begin + k)].ax;
+      near = near || ((double)ax >= q.ex0 && (double)ax <= q.ex1);
     }
   }
-  // vertical edges reject points with the same x at ANY y
-  for (u32 k = lane; k < m.n_vertical; k += 32) {
-    T const ax = ix.edges[__ldg(ix.vert_edges + m.vert_begin + k)].ax;
-    near = near || ((double)ax >= ex0 && (double)ax <= ex1);
-  }
-  if (__any_sync(0xffffffffu, near)) return kClsBoundary;
-  return (__popc(__ballot_sync(0xffffffffu, cross & 1u)) & 1) ? kClsInside : kClsOutside;
+  u32 const nb = (__ballot_sync(0xffffffffu, near) >> gsh) & gm;
+  u32 const cb = (__ballot_sync(0xffffffffu, cross & 1u) >> gsh) & gm;
+  if (nb) return kClsBoundary;
+  return (__popc(cb) & 1) ? kClsInside : kClsOutside;
+}
+
+// warp-cooperative, warp-uniform arguments; all lanes return the same class
+template <typename T>
+__device__ int classify_quadrant(const grid_info& g, u32 key, u32 level, const poly_meta<T>& m,
+                                 const edge_index<T>& ix)
+{
+  quad_query<T> q;
+  int const c = quadrant_setup<T>(g, key, level, m, ix, q);
+  return c >= 0 ? c : quadrant_edges<T, 32>(q, true, ix);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -490,46 +530,114 @@ pip_classify_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ p
                     const u8* __restrict__ node_level, grid_info grid, edge_index<T> ix,
                     u8* __restrict__ cls, u32* __restrict__ hits,
                     u32* __restrict__ run_list, u32* __restrict__ tile_list,
-                    u32* __restrict__ run_count, u32 tile_points, u32 list_capacity)
+                    u32* __restrict__ run_count, u32 tile_points, u32 list_capacity, u32 group)
 {
-  u32 const lane  = lane_id();
-  u32 const warps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_pairs; j += warps) {
-    u32 const quad = pair_quad[j];
-    int c          = kClsOutside;
+  // A warp takes `group` (<= 32) consecutive pairs at a time.  Lane l does everything of pair l that needs no
+  // cooperation -- the chain pair -> quadrant -> (length, offset, key, level), polygon -> record
+  // -> rectangle test -> slab range -- so that those dependent loads run 32 pairs wide instead
+  // of one pair per warp; only the pairs whose edges must be looked at are then handed to the
+  // whole warp, one after the other, through shuffles (two dependent loads left per pair).
+  u32 const lane   = lane_id();
+  u32 const warps  = (gridDim.x * blockDim.x) >> 5;
+  u64 const groups = ((u64)n_pairs + group - 1) / group;
+  for (u64 grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < groups; grp += warps) {
+    u64 const j = grp * group + lane;
+    bool const mine = lane < group && j < n_pairs;
+    int c       = kClsOutside;
     u32 nvalid = 0, qlen = 0;
-    if (quad < num_nodes) {
-      u32 const len = length[quad], off = offset[quad];
-      qlen          = len;
-      nvalid        = off < n_points ? min(len, n_points - off) : 0u;
-      u32 const poly = pair_poly[j];
-      if (len != 0 && poly < n_poly) {
-        poly_meta<T> const m = meta[poly];
-        c = (grid.valid && force_reference != 1)
-              ? classify_quadrant<T>(grid, node_key[quad], node_level[quad], m, ix)
-              : kClsBoundary;
+    quad_query<T> q{};
+    bool need = false;
+    if (mine) {
+      u32 const quad = pair_quad[j];
+      if (quad < num_nodes) {
+        u32 const len = length[quad], off = offset[quad];
+        qlen          = len;
+        nvalid        = off < n_points ? min(len, n_points - off) : 0u;
+        u32 const poly = pair_poly[j];
+        if (len != 0 && poly < n_poly) {
+          if (grid.valid && force_reference != 1) {
+            c    = quadrant_setup<T>(grid, node_key[quad], node_level[quad], meta[poly], ix, q);
+            need = c < 0;
+          } else {
+            c = kClsBoundary;
+          }
+        }
       }
+    }
+    // four pairs at a time, eight lanes each: a pair typically has a handful of candidate
+    // edges, and four independent entry -> edge load chains are in flight per warp
+    // (a pair with MANY candidate edges -- a large quadrant of a sparse tree against a detailed
+    // polygon -- gets the whole warp instead)
+    constexpr int W = 8, NG = 32 / W;
+    bool const wide = need && (q.kend - q.kbeg > 64u || q.n_vertical > 64u);
+    u32 big = __ballot_sync(0xffffffffu, wide);
+    while (big) {
+      int const src = __ffs(big) - 1;
+      big &= big - 1;
+      quad_query<T> b;
+      b.ex0 = __shfl_sync(0xffffffffu, q.ex0, src); b.ex1 = __shfl_sync(0xffffffffu, q.ex1, src);
+      b.ey0 = __shfl_sync(0xffffffffu, q.ey0, src); b.ey1 = __shfl_sync(0xffffffffu, q.ey1, src);
+      b.cx  = __shfl_sync(0xffffffffu, q.cx, src);  b.cy  = __shfl_sync(0xffffffffu, q.cy, src);
+      b.kbeg = __shfl_sync(0xffffffffu, q.kbeg, src);
+      b.kmid = __shfl_sync(0xffffffffu, q.kmid, src);
+      b.kend = __shfl_sync(0xffffffffu, q.kend, src);
+      b.n_vertical = __shfl_sync(0xffffffffu, q.n_vertical, src);
+      b.vert_begin = __shfl_sync(0xffffffffu, q.vert_begin, src);
+      int const r = quadrant_edges<T, 32>(b, true, ix);
+      if ((int)lane == src) c = r;
+    }
+    u32 todo = __ballot_sync(0xffffffffu, need && !wide);
+    u32 const lt = lanemask_lt();
+    while (todo) {
+      u32 const grp_id = lane / W;
+      u32 const pick   = __fns(todo, 0, (int)grp_id + 1);  // lane of the group's pair, or ~0
+      bool const active = pick < 32u;
+      int const src     = active ? (int)pick : 0;
+      quad_query<T> b;
+      b.ex0 = __shfl_sync(0xffffffffu, q.ex0, src); b.ex1 = __shfl_sync(0xffffffffu, q.ex1, src);
+      b.ey0 = __shfl_sync(0xffffffffu, q.ey0, src); b.ey1 = __shfl_sync(0xffffffffu, q.ey1, src);
+      b.cx  = __shfl_sync(0xffffffffu, q.cx, src);  b.cy  = __shfl_sync(0xffffffffu, q.cy, src);
+      b.kbeg = __shfl_sync(0xffffffffu, q.kbeg, src);
+      b.kmid = __shfl_sync(0xffffffffu, q.kmid, src);
+      b.kend = __shfl_sync(0xffffffffu, q.kend, src);
+      b.n_vertical = __shfl_sync(0xffffffffu, q.n_vertical, src);
+      b.vert_begin = __shfl_sync(0xffffffffu, q.vert_begin, src);
+      int const r = quadrant_edges<T, W>(b, active, ix);
+      // the owner of the k-th pending pair (k < NG) takes the result of lane group k
+      u32 const k  = __popc(todo & lt);
+      int const rr = __shfl_sync(0xffffffffu, r, (int)(min(k, (u32)NG - 1u) * W));
+      if (((todo >> lane) & 1u) && k < (u32)NG) c = rr;
+#pragma unroll
+      for (int t = 0; t < NG; ++t) todo &= todo - 1;
     }
     // Stage 2 works on (pair, point tile) units: bounded work per unit (one polygon against one
     // tile) whatever the data looks like -- a dense bottom-level leaf that cannot split (many
     // tiles) or a large sparse quadrant under hundreds of polygon boxes (many pairs) spreads over
     // many warps instead of serialising in one.
-    u32 base = 0, n_tiles = 0;
-    if (lane == 0) {
+    u32 n_tiles = 0;
+    if (mine) {
       cls[j]  = (u8)c;
       hits[j] = c == kClsInside ? nvalid : 0u;  // boundary pairs: stage 2 adds its counts
-      if (c == kClsBoundary) {
-        n_tiles = max(1u, qlen / tile_points + (qlen % tile_points != 0));
-        base    = atomicAdd(run_count, n_tiles);
-      }
+      if (c == kClsBoundary) n_tiles = max(1u, qlen / tile_points + (qlen % tile_points != 0));
     }
-    n_tiles = __shfl_sync(0xffffffffu, n_tiles, 0);
-    if (n_tiles) {
-      base = __shfl_sync(0xffffffffu, base, 0);
-      for (u32 t = lane; t < n_tiles; t += 32)
-        if (base + t < list_capacity) {
-          run_list[base + t]  = j;
-          tile_list[base + t] = t;
+    // one atomic per group reserves the units of all its boundary pairs
+    u32 const incl = warp_inclusive_scan(n_tiles);
+    u32 const tot  = __shfl_sync(0xffffffffu, incl, 31);
+    if (tot == 0) continue;
+    u32 base = 0;
+    if (lane == 31) base = atomicAdd(run_count, tot);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - n_tiles;
+    u32 bnd = __ballot_sync(0xffffffffu, n_tiles != 0);
+    while (bnd) {
+      int const src = __ffs(bnd) - 1;
+      bnd &= bnd - 1;
+      u32 const nt = __shfl_sync(0xffffffffu, n_tiles, src);
+      u32 const b0 = __shfl_sync(0xffffffffu, base, src);
+      u32 const jj = (u32)(grp * group) + (u32)src;
+      for (u32 t = lane; t < nt; t += 32)
+        if (b0 + t < list_capacity) {
+          run_list[b0 + t]  = jj;
+          tile_list[b0 + t] = t;
         }
     }
   }
@@ -1724,12 +1832,17 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
     u64 const list_cap = total_words * 32 / tile_points + n_pairs + 2;
     dev_buf<u32> run_list(list_cap, s), tile_list(list_cap, s), run_count(1, s);
     BSJ_CUDA_TRY(cudaMemsetAsync(run_count.get(), 0, sizeof(u32), s));
-    int const cgrid = (int)std::min<u64>((u64)num_sms() * 16, (u64)div_up(n_pairs * 32, 256));
+    // pairs per warp visit: 32 when there are plenty of pairs, fewer for small tables so that
+    // the work still spreads over the whole GPU
+    u32 cgroup = 32;
+    while (cgroup > 2 && (u64)n_pairs / cgroup < (u64)num_sms() * 64) cgroup >>= 1;
+    int const cgrid = (int)std::min<u64>((u64)num_sms() * 16,
+                                         (u64)div_up(div_up(n_pairs, (u64)cgroup), 8));
     pip_classify_kernel<T><<<std::max(cgrid, 1), 256, 0, s>>>(
       pair_poly, pair_quad, (u32)n_pairs, length, offset, (u32)num_nodes, (u32)n_points,
       meta.get(), n_poly, force_reference_mode(), node_key, node_level, gi, ix, c->pair_class,
       c->pair_hits, run_list.get(), tile_list.get(), run_count.get(), tile_points,
-      (u32)std::min<u64>(list_cap, 0xFFFFFFFFull));
+      (u32)std::min<u64>(list_cap, 0xFFFFFFFFull), cgroup);
     BSJ_CHECK_LAUNCH();
     prof_mark("pip_classify");
     u32 const list_cap32 = (u32)std::min<u64>(list_cap, 0xFFFFFFFFull);
