@@ -52,3 +52,21 @@ def test_sharded_join_all_visible_gpus_nccl():
     if n < 2:
         pytest.skip("needs at least two GPUs")
     _run(min(n, 8))
+
+
+def test_second_device_in_the_same_process(oracle_lib):
+    """Kernel attributes (dynamic shared memory above 48 KB) and the memory-pool set-up are per
+    DEVICE: after a call on cuda:0 the same process must run unchanged on cuda:1
+    (configure_once_per_device in csrc/api.cu; round 1 kept one flag per process)."""
+    import numpy as np
+    import torch
+
+    from util import assert_same, make_case, run_gpu, run_host
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    c = make_case(300000, 40, 12, "c", np.float64, seed=5, median_vertices=40, oob=50)
+    want = run_host(oracle_lib, c, 64)
+    for dev in (0, 1, 0):
+        with torch.cuda.device(dev):
+            assert_same(run_gpu(c, 64), want, "cuda:%d" % dev)
