@@ -868,10 +868,12 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
 constexpr int kCellPPL  = 4;
 constexpr int kCellTile = 32 * kCellPPL;
 // (tile, polygon) combinations with more candidate edges than this are evaluated point by point
-// through the y-slab index instead of edge by edge over the whole warp: a tile of a LARGE, sparse
-// quadrant spans most of the polygon's height, and walking every edge for every point costs
-// ~100x what the two or three edges of each point's own slab cost
-constexpr u32 kCoopEdges = 64;
+// through the y-slab index instead of edge by edge over the whole warp (a tile spanning the whole
+// height of a very detailed polygon).  Measured with the right-side shortcut of the edge-by-edge
+// form in place (ms of this kernel at thresholds 64 / 1024 / never): configs[3] at 125 M points
+// 4.04 / 2.97 / 3.30, at 1 G 8.0 / 7.6 / 7.8; configs[4] at 250 M 63 / 23.9 / 22.6; configs[1]
+// 0.59 either way.
+constexpr u32 kCoopEdges = 1024;
 
 
 template <typename T, bool SEG>
@@ -912,6 +914,7 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
       u32 const base = tile_list[slot] * kCellTile;
       u32 valid = 0, oob = 0;
       double cx[kCellPPL], cy[kCellPPL];
+      u32 ixmin = 0xFFFFFFFFu, ixmax = 0u, iymin = 0xFFFFFFFFu, iymax = 0u;
 #pragma unroll
       for (int i = 0; i < kCellPPL; ++i) {
         u32 const l   = base + i * 32 + lane;
@@ -919,24 +922,23 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
         u32 const k   = ok ? __ldcs(sorted_keys + off + l) : 0u;
         valid |= (u32)ok << i;
         oob |= (u32)(ok && grid.has_oob && k == oob_key) << i;
-        cx[i] = grid.min_x + ((double)undilate16p(k) + 0.5) * grid.scale;
-        cy[i] = grid.min_y + ((double)undilate16p(k >> 1) + 0.5) * grid.scale;
-      }
-      // tile extent (cell squares of the valid points)
-      double tx0 = 1e300, tx1 = -1e300, ty0 = 1e300, ty1 = -1e300;
-#pragma unroll
-      for (int i = 0; i < kCellPPL; ++i)
-        if ((valid >> i) & 1u) {
-          tx0 = fmin(tx0, cx[i] - hw); tx1 = fmax(tx1, cx[i] + hw);
-          ty0 = fmin(ty0, cy[i] - hh); ty1 = fmax(ty1, cy[i] + hh);
+        u32 const ix = undilate16p(k), iy = undilate16p(k >> 1);
+        if (ok) {
+          ixmin = min(ixmin, ix); ixmax = max(ixmax, ix);
+          iymin = min(iymin, iy); iymax = max(iymax, iy);
         }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        tx0 = fmin(tx0, __shfl_xor_sync(0xffffffffu, tx0, o));
-        ty0 = fmin(ty0, __shfl_xor_sync(0xffffffffu, ty0, o));
-        tx1 = fmax(tx1, __shfl_xor_sync(0xffffffffu, tx1, o));
-        ty1 = fmax(ty1, __shfl_xor_sync(0xffffffffu, ty1, o));
+        cx[i] = grid.min_x + ((double)ix + 0.5) * grid.scale;
+        cy[i] = grid.min_y + ((double)iy + 0.5) * grid.scale;
       }
+      // tile extent (cell squares of the valid points): the centre is monotone in the cell
+      // index, so the extremes come from four integer warp reductions
+      ixmin = __reduce_min_sync(0xffffffffu, ixmin); ixmax = __reduce_max_sync(0xffffffffu, ixmax);
+      iymin = __reduce_min_sync(0xffffffffu, iymin); iymax = __reduce_max_sync(0xffffffffu, iymax);
+      bool const any_pt = ixmin <= ixmax;
+      double const tx0 = any_pt ? grid.min_x + ((double)ixmin + 0.5) * grid.scale - hw : 1e300;
+      double const tx1 = any_pt ? grid.min_x + ((double)ixmax + 0.5) * grid.scale + hw : -1e300;
+      double const ty0 = any_pt ? grid.min_y + ((double)iymin + 0.5) * grid.scale - hh : 1e300;
+      double const ty1 = any_pt ? grid.min_y + ((double)iymax + 0.5) * grid.scale + hh : -1e300;
       // real coordinates, gathered lazily and only for the points that need them
       T xr[kCellPPL], yr[kCellPPL];
       u32 loaded = 0, unsafe_pt = 0;
@@ -1073,6 +1075,19 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                   double const eby = (double)__shfl_sync(0xffffffffu, by, src);
                   double const run = ebx - eax, rise = eby - eay;
                   double const d   = eps * fmax(fmax(fabs(eax), fabs(ebx)), fmax(fabs(eay), fabs(eby)));
+                  if (fmin(eax, ebx) - d > tx1) {
+                    // the edge lies wholly to the RIGHT of every cell square of the tile (beyond
+                    // its tolerance): it touches none of them, and a point left of both
+                    // endpoints crosses it exactly when its y is straddled -- for rise > 0 the
+                    // straddle means y1 = 0 and the point is on the f < 0 side, for rise < 0
+                    // y1 = 1 and f > 0: (f < 0) != y1 holds either way
+#pragma unroll
+                    for (int i = 0; i < kCellPPL; ++i) {
+                      bool const y1 = eay > cy[i], y0 = eby > cy[i];
+                      cross ^= (u32)(y1 != y0) << i;
+                    }
+                    continue;
+                  }
                   // per-edge constants (warp-uniform): the edge's extent widened by its tolerance
                   // AND by the cell half-size, and the |f| threshold.  The rounding allowance of f
                   // uses the largest |ddx|, |ddy| any cell centre of this tile can have.

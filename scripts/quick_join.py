@@ -20,9 +20,12 @@ a = ap.parse_args()
 w = bench.WORKLOADS[a.workload]
 dev = torch.device("cuda", 0)
 polys_np, ext, scale = bench.make_polygons(w["n_poly"])
+tdt = torch.float64 if w["dtype"] == "f64" else torch.float32
+if tdt == torch.float32:
+    polys_np = (polys_np[0], polys_np[1], polys_np[2].astype("float32"), polys_np[3].astype("float32"))
 polys = tuple(torch.as_tensor(p, device=dev) for p in polys_np)
 n = a.points or w["points"]
-x, y = bench.gen_points(w["kind"], n, ext, bench.SEED, torch.float64, dev)
+x, y = bench.gen_points(w["kind"], n, ext, bench.SEED, tdt, dev)
 for _ in range(2):
     r = bench.join_step(cs, x, y, polys, ext, scale)
 torch.cuda.synchronize()
@@ -41,4 +44,4 @@ torch.cuda.synchronize()
 st = {}
 for k, v in _lib.get_profile():
     st[k] = st.get(k, 0.0) + v / a.steps
-print(json.dumps({"ms_per_step": round(ms, 4), "stages": {k: round(v, 4) for k, v in st.items()}}))
+print(json.dumps({"nodes": len(r[1]), "pairs": len(r[2]), "hits": len(r[3]), "ms_per_step": round(ms, 4), "stages": {k: round(v, 4) for k, v in st.items()}}))

@@ -360,6 +360,34 @@ def test_hint_is_bound_to_the_buffers_it_describes(oracle_lib, dtype):
     np.testing.assert_array_equal(got[1], want[1])
 
 
+@pytest.mark.parametrize("grid_log2", ["0", "6", "9"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_bitmask_concentric_ngons_overflow_the_exact_test_queue(oracle_lib, dtype, grid_log2,
+                                                                monkeypatch):
+    """The reference benchmark's shape (31 regular n-gons sharing one centroid,
+    cpp/benchmarks/point_in_polygon/point_in_polygon.cu:41-102) with the points concentrated on
+    the common outline: every point there is undecided for all 31 polygons, which overflows the
+    kernel's shared-memory queue of exact tests (its evaluate-on-the-spot path) in every chunk."""
+    import cuspatial_b200 as cs
+    from cuspatial_b200 import datagen as D
+
+    monkeypatch.setenv("BSJ_BITMASK_GRID_LOG2", grid_log2)
+    po, ro, vx, vy = D.regular_ngons(31, 10, 10.0, centroid=(3.0, -2.0), dtype=dtype)
+    rng = np.random.default_rng(5)
+    n = 120000
+    th = rng.uniform(0, 2 * np.pi, n)
+    r = 10.0 * np.cos(np.pi / 10) / np.cos((th % (2 * np.pi / 10)) - np.pi / 10)  # on the outline
+    r = r + rng.choice([0.0, 1e-9, -1e-9, 1e-4, -1e-4, 0.3, -0.3, 5.0], n)
+    x = (3.0 + r * np.cos(th)).astype(dtype)
+    y = (-2.0 + r * np.sin(th)).astype(dtype)
+    x[:64] = vx[:64]; y[:64] = vy[:64]                          # the vertices themselves
+    want = oracle_lib.point_in_polygon(x, y, po.astype(np.int32), ro.astype(np.int32), vx, vy)
+    got = cs.point_in_polygon_bitmask((_t(x), _t(y)), (_t(po.astype(np.int32)),
+                                                        _t(ro.astype(np.int32)), _t(vx), _t(vy)))
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    assert 0 < int((want != 0).sum()) < n
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_golden_pairwise_cases(golden, dtype):
     """pairwise_point_in_polygon_test.cu known answers (point i vs polygon i)."""
