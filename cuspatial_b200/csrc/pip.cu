@@ -509,6 +509,7 @@ narrow_u64_kernel(const u64* __restrict__ in, u32* __restrict__ out, u32 n)
 // evaluation: one warp per (pair, point tile) unit
 // ---------------------------------------------------------------------------------------------
 constexpr int kPipWarps = 4;
+constexpr u32 kEvalSlices = 32;
 constexpr int kPPL      = 8;          // points per lane
 constexpr int kPipTile  = 32 * kPPL;  // points per tile
 
@@ -657,16 +658,25 @@ pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
                 const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
                 const T* __restrict__ vy, const u64* __restrict__ wbase,
                 u32* __restrict__ mask_words, u32* __restrict__ hits, u32* __restrict__ ticket,
-                int force_reference, const u8* __restrict__ cls, edge_index<T> ix)
+                u32 n_slices, int force_reference, const u8* __restrict__ cls,
+                edge_index<T> ix)
 {
   u32 const lane   = lane_id();
   u32 const n_list = min(*run_count, list_capacity);
+  // units are drawn from n_slices <= kEvalSlices counters (a single counter serialises the whole
+  // grid's atomics in L2)
+  u32 const slice = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) % n_slices;
+  ticket += slice;
 
   while (true) {
-    u32 slot = 0;
-    if (lane == 0) slot = atomicAdd(ticket, 1u);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    if (slot >= n_list) break;
+    u32 t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    // slice s owns units s, s + n_slices, s + 2 n_slices, ...: neighbouring units (similar cost:
+    // they come from neighbouring pairs) spread over all slices
+    u64 const slot64 = (u64)t * n_slices + slice;
+    if (slot64 >= n_list) break;
+    u32 const slot = (u32)slot64;
     u32 const j0 = run_list[slot], j1 = j0 + 1;  // one (pair, tile) unit per slot
     u32 const quad = pair_quad[j0];
     u32 const len = length[quad], off = offset[quad];
@@ -888,7 +898,8 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
                       const u32* __restrict__ ring_offsets, const T* __restrict__ vx,
                       const T* __restrict__ vy, const u64* __restrict__ wbase,
                       u32* __restrict__ mask_words, u32* __restrict__ hits,
-                      u32* __restrict__ ticket, const u8* __restrict__ cls, edge_index<T> ix,
+                      u32* __restrict__ ticket, u32 n_slices, const u8* __restrict__ cls,
+                      edge_index<T> ix,
                       grid_info grid, const u32* __restrict__ sorted_keys, u32 coop_edges)
 {
   u32 const lane   = lane_id();
@@ -900,12 +911,20 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
   // relative allowance on the centre's line function f = v - u: the reference evaluates u and v
   // in T (products rounded separately) and calls them equal within 4 ULP -- 5e-7 |u| for float
   double const allow = sizeof(T) == 4 ? 2e-6 : 1e-9;
+  // units are drawn from n_slices <= kEvalSlices counters (a single counter serialises the whole
+  // grid's atomics in L2)
+  u32 const slice = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) % n_slices;
+  ticket += slice;
 
   while (true) {
-    u32 slot = 0;
-    if (lane == 0) slot = atomicAdd(ticket, 1u);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    if (slot >= n_list) break;
+    u32 t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    // slice s owns units s, s + n_slices, s + 2 n_slices, ...: neighbouring units (similar cost:
+    // they come from neighbouring pairs) spread over all slices
+    u64 const slot64 = (u64)t * n_slices + slice;
+    if (slot64 >= n_list) break;
+    u32 const slot = (u32)slot64;
     u32 const j0 = run_list[slot], j1 = j0 + 1;  // one (pair, tile) unit per slot
     u32 const quad = pair_quad[j0];
     u32 const len = length[quad], off = offset[quad];
@@ -1232,13 +1251,14 @@ __device__ __forceinline__ void emit_store(P* p, V v)
 #define BSJ_EMIT_GRID_MULT 8
 #endif
 constexpr int kEmitWarps = 8;
+constexpr u32 kEmitSlices = 64;
 __global__ void __launch_bounds__(kEmitWarps * 32)
 pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_off,
                 const u32* __restrict__ pair_len, u32 n_pairs, const u64* __restrict__ wbase,
                 const u64* __restrict__ obase, const u32* __restrict__ hits,
                 const u32* __restrict__ mask_words, const u8* __restrict__ cls, u32 position_base,
                 u32* __restrict__ out_poly, u32* __restrict__ out_point, u32 group,
-                u32* __restrict__ ticket)
+                u32* __restrict__ ticket, u32 n_slices)
 {
   // per-warp staging of the hit positions of one 32-word group (boundary pairs)
   __shared__ unsigned short s_pos[kEmitWarps][1024];
@@ -1251,12 +1271,18 @@ pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
   // the whole warp one by one through shuffles.  Groups are handed out through a ticket (pairs
   // differ in cost by orders of magnitude: a whole-quadrant fill vs. ballot words to decode), the
   // next ticket being drawn while the current group is written.
-  u64 const n_groups = ((u64)n_pairs + group - 1) / group;
+  // (n_slices <= kEmitSlices counters, each shared by the warps whose index is congruent to
+  // it: ten thousand warps drawing from ONE address serialise in L2 -- 20 % of this kernel's
+  // stall samples with a single counter)
+  u64 const n_groups  = ((u64)n_pairs + group - 1) / group;
+  u32 const slice = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) % n_slices;
+  ticket += slice;
   u32 g32 = 0;
   if (lane == 0) g32 = atomicAdd(ticket, 1u);
   g32 = __shfl_sync(0xffffffffu, g32, 0);
-  while ((u64)g32 < n_groups) {
-    u64 const g = g32;
+  // slice s owns groups s, s + n_slices, s + 2 n_slices, ...
+  while ((u64)g32 * n_slices + slice < n_groups) {
+    u64 const g = (u64)g32 * n_slices + slice;
     u32 next = 0;
     if (lane == 0) next = atomicAdd(ticket, 1u);
     u64 const jl = g * group + lane;
@@ -1822,8 +1848,11 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
   c->pair_row_base  = oa.get<u64>(n_pairs);
   dev_buf<u32> words(n_pairs, s);
   dev_buf<u64> totals(4, s);
-  dev_buf<u32> ticket(1, s);
-  BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
+  dev_buf<u32> ticket(kEvalSlices, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, kEvalSlices * sizeof(u32), s));
+  auto eval_slices = [](int grid_dim) {  // every slice needs at least one warp
+    return (u32)std::min<u64>(kEvalSlices, (u64)std::max(grid_dim, 1) * kPipWarps);
+  };
   pair_prep_kernel<<<div_up(n_pairs, 256), 256, 0, s>>>(pair_quad, (u32)n_pairs, length, offset,
                                                         (u32)num_nodes, words.get(),
                                                         c->pair_length, c->pair_offset);
@@ -1875,7 +1904,8 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
           pair_poly, pair_quad, run_list.get(), tile_list.get(), list_cap32,
           run_count.get(), length, offset, point_indices, (u32)n_points, src, meta.get(), n_poly,
           ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words,
-          c->pair_hits, ticket.get(), c->pair_class, ix, gi, gi.sorted_keys, coop_edges);
+          c->pair_hits, ticket.get(), eval_slices(grid_dim), c->pair_class, ix, gi,
+          gi.sorted_keys, coop_edges);
       };
       if (segmented) launch(spts); else launch(pts);
       BSJ_CHECK_LAUNCH();
@@ -1887,7 +1917,8 @@ void qpip_compact_t(const u32* pair_poly, const u32* pair_quad, u64 n_pairs, con
           pair_poly, pair_quad, run_list.get(), tile_list.get(), list_cap32,
           run_count.get(), length, offset, point_indices, (u32)n_points, src, meta.get(), n_poly,
           ring_offsets, (const T*)vx, (const T*)vy, c->pair_word_base, c->mask_words,
-          c->pair_hits, ticket.get(), force_reference_mode(), c->pair_class, ix);
+          c->pair_hits, ticket.get(), eval_slices(grid_dim), force_reference_mode(),
+          c->pair_class, ix);
       };
       if (segmented) launch(spts); else launch(pts);
       BSJ_CHECK_LAUNCH();
@@ -1922,12 +1953,14 @@ void expand_compact(const u32* pair_poly, const bsj_pip_compact* c, u32 position
     group >>= 1;
   int const grid_dim = (int)std::min<u64>((u64)num_sms() * mult,
                                           (u64)div_up(div_up(c->n_pairs, (u64)group), kEmitWarps));
-  dev_buf<u32> ticket(1, s);
-  BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, sizeof(u32), s));
+  dev_buf<u32> ticket(kEmitSlices, s);
+  BSJ_CUDA_TRY(cudaMemsetAsync(ticket.get(), 0, kEmitSlices * sizeof(u32), s));
+  // every slice needs at least one warp
+  u32 const n_slices = (u32)std::min<u64>(kEmitSlices, (u64)std::max(grid_dim, 1) * kEmitWarps);
   pip_emit_kernel<<<std::max(grid_dim, 1), kEmitWarps * 32, 0, s>>>(
     pair_poly, c->pair_offset, c->pair_length, (u32)c->n_pairs, c->pair_word_base,
     c->pair_row_base, c->pair_hits, c->mask_words, c->pair_class, position_base, out_poly,
-    out_point, group, ticket.get());
+    out_point, group, ticket.get(), n_slices);
   BSJ_CHECK_LAUNCH();
   prof_mark("pip_emit");
 }

@@ -59,7 +59,9 @@ def main():
     total = sum(_i(r[ci]) for _, r in b["rows"])
     tots = sum(_i(r[cs]) for _, r in b["rows"])
     print("%s\n  %d warp instructions, %d samples" % (b["name"][:100], total, tots))
-    rows = sorted(b["rows"], key=lambda fr: -_i(fr[1][ci]))[:top]
+    import os
+    key = cs if os.environ.get("BY_SAMPLES") else ci
+    rows = sorted(b["rows"], key=lambda fr: -_i(fr[1][key]))[:top]
     for f, r in rows:
         print("%5.1f%% inst %5.1f%% smp thr %4s  %s:%s  %s" % (
             100.0 * _i(r[ci]) / max(total, 1), 100.0 * _i(r[cs]) / max(tots, 1), r[ct],
