@@ -182,3 +182,49 @@ def test_bitmask_at_extent(oracle_lib, ext, dtype, grid_log2, monkeypatch):
         got = cs.point_in_polygon_bitmask((t(cc["x"]), t(cc["y"])),
                                           (t(po), t(ro), t(cc["vx"]), t(cc["vy"])))
         np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_long_edges_reaching_far_outside_the_area_of_interest(oracle_lib, dtype):
+    """Polygons whose vertices lie up to 1000 extents outside the area of interest cross it with
+    long, nearly straight edges: the products of the reference's edge function are then huge
+    compared with the cell size, which is where the float32 allowance of the cell-centre test
+    (relative to |u|, not to the cell) has to hold.  Points cluster along those edges."""
+    rng = np.random.default_rng(17)
+    c = make_case(30000, 6, 10, "u", dtype, seed=23, median_vertices=12)
+    x0, x1, y0, y1 = c["ext"]
+    w, h = x1 - x0, y1 - y0
+    polys_x, polys_y, ro, po = [c["vx"]], [c["vy"]], list(c["ro"]), list(c["po"])
+    for k in range(6):  # thin slivers and huge triangles through the area of interest
+        far = 10.0 ** rng.uniform(0.5, 3.0)
+        ang = rng.uniform(0, np.pi)
+        cx, cy = x0 + rng.uniform(0.2, 0.8) * w, y0 + rng.uniform(0.2, 0.8) * h
+        dx, dy = np.cos(ang) * far * w, np.sin(ang) * far * h
+        nx, ny = -np.sin(ang) * rng.uniform(0.01, 0.3) * w, np.cos(ang) * rng.uniform(0.01, 0.3) * h
+        ring = np.array([[cx - dx, cy - dy], [cx + dx, cy + dy], [cx + nx, cy + ny],
+                         [cx - dx, cy - dy]], dtype=dtype)
+        polys_x.append(ring[:, 0]); polys_y.append(ring[:, 1])
+        ro.append(ro[-1] + 4); po.append(po[-1] + 1)
+    vx, vy = np.concatenate(polys_x).astype(dtype), np.concatenate(polys_y).astype(dtype)
+    # points on and next to the long edges, inside the area of interest
+    xs, ys = [c["x"]], [c["y"]]
+    for r in range(len(c["ro"]) - 1, len(ro) - 1):
+        a = ro[r]
+        for e in range(3):
+            t = rng.uniform(0.0, 1.0, 4000)
+            px = vx[a + e] + t * (vx[a + e + 1] - vx[a + e])
+            py = vy[a + e] + t * (vy[a + e + 1] - vy[a + e])
+            keep = (px > x0) & (px < x1) & (py > y0) & (py < y1)
+            px, py = px[keep].astype(dtype), py[keep].astype(dtype)
+            for ulps in (0, 1, -1, 4, -5, 50):
+                xs.append(px); ys.append(np.nextafter(py, dtype(np.inf) if ulps >= 0 else dtype(-np.inf))
+                                         if abs(ulps) == 1 else py + dtype(ulps) * np.spacing(py))
+    x, y = np.concatenate(xs).astype(dtype), np.concatenate(ys).astype(dtype)
+    keep = in_contract(x, y, c["ext"], c["scale"], c["depth"], dtype)
+    c2 = dict(c, x=x[keep], y=y[keep], vx=vx, vy=vy, ro=np.asarray(ro, np.uint32),
+              po=np.asarray(po, np.uint32))
+    for max_size in (16, 100000):
+        want = run_host(oracle_lib, c2, max_size)
+        assert len(want["hits"][0]) > 0
+        _gpu_all_modes(c2, max_size, want, "long edges")
