@@ -919,6 +919,46 @@ def run_sharded(args, workload):
     total = per * world
     value = total / (ms_step / 1e3)
     part = time_sharded(dist, dev, pts, polys, ext, scale, max(2, min(args.steps, 5)), 1, False)
+    # roofline of the dominant kernel on rank 0: one more step with the library's own CUDA events
+    # between its kernels (outside the timed region above)
+    roofline = None
+    try:
+        from cuspatial_b200 import _lib
+
+        _lib.set_profiling(True)
+        _lib.get_profile()
+        out = mg.sharded_quadtree_point_in_polygon(
+            pts, polys, ext[0], ext[1], ext[2], ext[3], scale, MAX_DEPTH, MAX_SIZE,
+            gather_pairs=True)
+        n_local = int(out["counts"][rank])
+        del out
+        torch.cuda.synchronize(dev)
+        prof = _lib.get_profile()
+        _lib.set_profiling(False)
+        st = {}
+        for name, ms in prof:
+            st.setdefault(name, []).append(ms)
+        if rank == 0 and st.get("onesweep_pass"):
+            dom = max(st, key=lambda k: sum(st[k]))
+            peak, peak_src = read_peaks()
+            sort_ms = sum(st["onesweep_pass"]) / len(st["onesweep_pass"])
+            alg = n_local * 16.0   # per pass: key + global id read, key + global id written
+            roofline = {
+                "bound": "hbm", "kernel": "onesweep_pass", "achieved": alg / (sort_ms / 1e3) / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": alg / (sort_ms / 1e3) / 1e9 / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms_per_launch": sort_ms,
+                "kernel_share_of_step": sum(st["onesweep_pass"]) / ms_step,
+                "largest_stage_on_rank0": dom,
+                "stage_ms_rank0": {k: round(sum(v), 4) for k, v in st.items()},
+                "timing": "rank 0, one instrumented step after the timed region: CUDA events "
+                          "recorded by the library between its kernels; algorithmic bytes = 16 B "
+                          "per received key per pass (all four passes carry the global ids)"}
+    except Exception as e:  # the line is still valid without it
+        roofline = {"failed": repr(e)[:200]} if rank == 0 else None
+        try:
+            _lib.set_profiling(False)
+        except Exception:
+            pass
     e2e = None
     if not args.no_e2e:
         dt, h2d, d2h = e2e_sharded(dist, dev, pts, polys_np, ext, scale, args.steps)
@@ -971,7 +1011,7 @@ def run_sharded(args, workload):
                        "merged_rows": head["rows"], "points_per_rank_after_sharding": head["counts"],
                        "parallelism": "morton-range point shards x%d, replicated polygons" % world},
             "parity": parity["parity"] if parity else None, "parity_check": parity,
-            "roofline": None, "cpu_baseline": None, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
             "gpu_launches": head["gpu_launches"], "clocks": clocks,
             "phase_ms_last_step": head["phase_ms_last_step"], "extra": extra,
         }))
