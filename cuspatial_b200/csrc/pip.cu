@@ -450,9 +450,13 @@ __device__ __forceinline__ int quadrant_edges(const quad_query<T>& q, bool activ
                                   fmax(fabs((double)e.ay), fabs((double)e.by)));
       double const lx = fmin((double)e.ax, (double)e.bx) - d, hx = fmax((double)e.ax, (double)e.bx) + d;
       if (hx < q.ex0) continue;  // wholly left of the rectangle: cannot touch it, never toggles
-      double const ly = fmin((double)e.ay, (double)e.by) - d, hy = fmax((double)e.ay, (double)e.by) + d;
-      near = near || !(hx < q.ex0 || lx > q.ex1 || hy < q.ey0 || ly > q.ey1);
       bool const f1 = e.ay > q.cy, f0 = e.by > q.cy;
+      if (lx > q.ex1) {  // wholly right: cannot touch it, toggles exactly on a y-straddle
+        cross ^= (u32)(f1 != f0);
+        continue;
+      }
+      double const ly = fmin((double)e.ay, (double)e.by) - d, hy = fmax((double)e.ay, (double)e.by) + d;
+      near = near || !(hy < q.ey0 || ly > q.ey1);
       if (f1 != f0) {
         T const u = fpp<T>::mul(fpp<T>::sub(e.bx, e.ax), fpp<T>::sub(q.cy, e.ay));
         T const v = fpp<T>::mul(fpp<T>::sub(q.cx, e.ax), fpp<T>::sub(e.by, e.ay));
@@ -1261,7 +1265,9 @@ pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
                 u32* __restrict__ ticket, u32 n_slices)
 {
   // per-warp staging of the hit positions of one 32-word group (boundary pairs)
-  __shared__ unsigned short s_pos[kEmitWarps][1024];
+  // (one slot of padding per 32: lane l lists word l's bits from slot 32 l on when the words are
+  // full -- the common case -- which would put all lanes on two banks)
+  __shared__ unsigned short s_pos[kEmitWarps][1024 + 32];
   u32 const lane = lane_id();
   unsigned short* const pos = s_pos[threadIdx.x >> 5];
   // A warp takes `group` (<= 32) consecutive pairs at a time: lane l fetches the records of pair
@@ -1356,13 +1362,14 @@ pip_emit_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_
           // warp writes the rows with one lane per OUTPUT row (coalesced)
           u32 k = incl - c;
           while (w) {
-            pos[k++] = (unsigned short)(lane * 32 + (__ffs(w) - 1));
+            pos[k + (k >> 5)] = (unsigned short)(lane * 32 + (__ffs(w) - 1));
+            ++k;
             w &= w - 1;
           }
           __syncwarp();
           for (u32 r = lane; r < tot; r += 32) {
             BSJ_EMIT_STORE(out_poly + o + r, poly);
-            BSJ_EMIT_STORE(out_point + o + r, off + w0 * 32 + pos[r]);
+            BSJ_EMIT_STORE(out_point + o + r, off + w0 * 32 + pos[r + (r >> 5)]);
           }
           __syncwarp();
         }
