@@ -14,6 +14,7 @@ wrapped with torch.as_tensor).  Outputs are torch tensors allocated through torc
 allocator (handed to the library as its output allocator, the analogue of the reference's `mr`).
 """
 import ctypes as C
+import threading
 import warnings
 
 import torch
@@ -49,8 +50,26 @@ class _TorchAllocator:
         """The tensor behind `ptr`, viewed as n elements of dtype."""
         if n == 0 or not ptr:
             return torch.empty(0, dtype=dtype, device=self.device)
-        t = self.live.pop(ptr)
-        return t.view(dtype)[:n]
+        v = self.live.pop(ptr).view(dtype)
+        return v if v.shape[0] == n else v[:n]
+
+
+_ALLOCATORS = threading.local()
+
+
+def _allocator_for(device):
+    """One _TorchAllocator per (thread, device): building the two ctypes callbacks costs ~20 us per
+    API call, which is GPU idle time when it happens right after a call's synchronisation."""
+    cache = getattr(_ALLOCATORS, "by_device", None)
+    if cache is None:
+        cache = _ALLOCATORS.by_device = {}
+    key = (device.type, device.index)
+    a = cache.get(key)
+    if a is None:
+        a = cache[key] = _TorchAllocator(device)
+    elif a.live:   # a previous call failed half-way: drop what it left behind
+        a.live.clear()
+    return a
 
 
 def _as_cuda(t, dtype=None, name="input"):
@@ -189,7 +208,7 @@ def quadtree_on_points(points, x_min, x_max, y_min, y_max, scale, max_depth, max
     x_min, x_max, y_min, y_max, scale = _clamp_scale(x_min, x_max, y_min, y_max, scale, max_depth)
     dev = x.device
     with torch.cuda.device(dev):
-        alloc = _TorchAllocator(dev)
+        alloc = _allocator_for(dev)
         out = _lib.bsj_quadtree()
         rc = _lib.lib().bsj_quadtree_on_points(
             _ptr(x), _ptr(y), _DTYPE_CODE[x.dtype], x.shape[0], float(x_min), float(x_max),
@@ -254,7 +273,7 @@ def join_quadtree_and_bounding_boxes(quadtree, bounding_boxes, x_min, x_max, y_m
     tcols = _quadtree_columns(quadtree)
     dev = bcols[0].device
     with torch.cuda.device(dev):
-        alloc = _TorchAllocator(dev)
+        alloc = _allocator_for(dev)
         out = _lib.bsj_pairs()
         rc = _lib.lib().bsj_join_quadtree_and_bounding_boxes(
             *[_ptr(t) for t in tcols], tcols[0].shape[0], *[_ptr(b) for b in bcols],
@@ -297,7 +316,7 @@ def quadtree_point_in_polygon(poly_quad_pairs, quadtree, point_indices, points, 
     tcols = _quadtree_columns(quadtree)
     dev = x.device
     with torch.cuda.device(dev):
-        alloc = _TorchAllocator(dev)
+        alloc = _allocator_for(dev)
         out = _lib.bsj_pairs()
         grid = _hint_for(quadtree, points, point_indices)
         rc = _lib.lib().bsj_quadtree_point_in_polygon_ex(
@@ -333,7 +352,7 @@ def quadtree_point_in_polygon_compact(poly_quad_pairs, quadtree, point_indices, 
     tcols = _quadtree_columns(quadtree)
     dev = x.device
     with torch.cuda.device(dev):
-        alloc = _TorchAllocator(dev)
+        alloc = _allocator_for(dev)
         out = _lib.bsj_pip_compact()
         grid = _hint_for(quadtree, points, point_indices)
         rc = _lib.lib().bsj_quadtree_point_in_polygon_compact(

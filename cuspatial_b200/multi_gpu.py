@@ -384,14 +384,14 @@ def cuda_local_compact(rkeys, rgids, points, flags, polygons, bbox, scale, max_d
     import ctypes as C
 
     from . import _lib, api
-    from .api import _DTYPE_CODE, _TorchAllocator, _ptr, _stream
+    from .api import _DTYPE_CODE, _allocator_for, _ptr, _stream
     from .frame import Frame
 
     dev = rkeys.device
     n = rkeys.shape[0]
     grid = _grid_struct(bbox, scale, max_depth, points.dtype, flags[0], flags[1])
     with torch.cuda.device(dev):
-        alloc = _TorchAllocator(dev)
+        alloc = _allocator_for(dev)
         out = _lib.bsj_quadtree()
         _lib.check(_lib.lib().bsj_quadtree_on_keys(
             _ptr(rkeys), _ptr(rgids), n, C.byref(grid), int(max_size), C.byref(alloc.struct),
@@ -427,7 +427,7 @@ def cuda_local_compact(rkeys, rgids, points, flags, polygons, bbox, scale, max_d
     pp, pq = pairs["bbox_offset"], pairs["quad_offset"]
     tcols = api._quadtree_columns(tree)
     with torch.cuda.device(dev):
-        alloc = _TorchAllocator(dev)
+        alloc = _allocator_for(dev)
         c = _lib.bsj_pip_compact()
         _lib.check(_lib.lib().bsj_quadtree_point_in_polygon_compact_seg(
             _ptr(pp), _ptr(pq), pp.shape[0], *[_ptr(t) for t in tcols], tcols[0].shape[0],
