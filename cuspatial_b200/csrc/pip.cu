@@ -10,9 +10,13 @@
 //
 // Design (not a port).  The reference tests every candidate against EVERY vertex of its polygon
 // after a ~19-step binary search and two dependent random gathers per candidate.  Here:
-//   * pairs that share a quadrant form a RUN (the join emits them adjacent); one warp owns a run,
-//     gathers the quadrant's points ONCE (256-point tiles, 8 per lane, coordinates in registers)
-//     and reuses them for every polygon of the run;
+//   * stage 1 (pip_classify_kernel) decides whole quadrants from their cell rectangle through a
+//     per-polygon y-slab edge index -- no point is read for them;
+//   * stage 2 works on (pair, point tile) UNITS of the undecided pairs, one warp per unit drawn
+//     from tickets: with the sorted Morton keys at hand (pip_eval_cells_kernel) a point is decided
+//     from the centre of its finest cell unless an edge touches that cell, and only touched points
+//     are gathered and evaluated exactly; without the keys (pip_eval_kernel) the tile's points are
+//     gathered once (256-point tiles, 8 per lane, coordinates in registers);
 //   * per (tile, polygon) the warp scans the polygon's edges 32 at a time and keeps only the
 //     edges that can influence a point of the tile -- the predicate is
 //         inside = XOR_e crossing(e)  AND NOT  OR_e on_edge(e),
@@ -648,8 +652,8 @@ pip_classify_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ p
   }
 }
 
-// Stage 2: one warp per listed quadrant gathers its points once and tests them against every
-// polygon of the run that stage 1 left undecided.
+// Stage 2 without the sorted keys: one warp per (pair, tile) unit gathers the tile's points and
+// tests them against the pair's polygon with exact edge skipping.
 template <typename T, bool SEG>
 __global__ void __launch_bounds__(kPipWarps * 32)
 pip_eval_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__ pair_quad,
@@ -1236,13 +1240,14 @@ pip_eval_cells_kernel(const u32* __restrict__ pair_poly, const u32* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// expansion of ballot words into (polygon_index, point_index) rows; one warp per pair.
-// Rows are produced 32 at a time with one lane per OUTPUT row (fully coalesced stores): lane r
-// finds the word holding the r-th hit of the current 32-word group by a shuffle binary search over
-// the lanes' inclusive popcounts and the bit inside it with __fns.
+// expansion of the compact result into (polygon_index, point_index) rows.  A warp draws groups of
+// consecutive pairs (see the kernel); whole-quadrant hits are a 128-bit identity fill, ballot
+// words are decoded through a per-warp shared-memory buffer (lane l lists the set bits of word l
+// at its prefix position) and leave with one lane per OUTPUT row, i.e. coalesced.
 // ---------------------------------------------------------------------------------------------
 // Measured on B200 (configs[1], 1.15 GB of rows): streaming (__stcs) stores 0.36 ms, plain stores
-// 0.33 ms; 8 CTAs per SM 0.36 ms, 16 per SM (better tail balance over uneven pairs) 0.32 ms.
+// 0.33 ms (round 1); this form 0.23 ms = 4.8 TB/s, the same at 4-16 CTAs per SM and group sizes
+// 8-32 (profiles/r2_notebook.md).
 template <typename P, typename V>
 __device__ __forceinline__ void emit_store(P* p, V v)
 {
