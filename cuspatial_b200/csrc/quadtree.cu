@@ -146,10 +146,10 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
   };
 
   if (aligned) {
-    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-      T xs[V], ys[V];
-      *reinterpret_cast<int4*>(xs) = __ldcs(reinterpret_cast<const int4*>(x) + v);
-      *reinterpret_cast<int4*>(ys) = __ldcs(reinterpret_cast<const int4*>(y) + v);
+    // two 128-bit vectors per coordinate in flight per thread: the kernel is bound by load
+    // latency at 2 CTAs/SM (ncu: 59 % of the stall samples on the first use of x/y), so the
+    // bytes in flight per SM are what sets its bandwidth
+    auto emit = [&](u64 v, const T* xs, const T* ys) {
       u32 ks[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
@@ -160,6 +160,22 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
         *reinterpret_cast<uint2*>(keys + v * V) = make_uint2(ks[0], ks[1]);
       else
         *reinterpret_cast<uint4*>(keys + v * V) = make_uint4(ks[0], ks[1], ks[2], ks[3]);
+    };
+    u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; v + stride < nvec; v += 2 * stride) {
+      T xa[V], ya[V], xb[V], yb[V];
+      *reinterpret_cast<int4*>(xa) = __ldcs(reinterpret_cast<const int4*>(x) + v);
+      *reinterpret_cast<int4*>(ya) = __ldcs(reinterpret_cast<const int4*>(y) + v);
+      *reinterpret_cast<int4*>(xb) = __ldcs(reinterpret_cast<const int4*>(x) + v + stride);
+      *reinterpret_cast<int4*>(yb) = __ldcs(reinterpret_cast<const int4*>(y) + v + stride);
+      emit(v, xa, ya);
+      emit(v + stride, xb, yb);
+    }
+    if (v < nvec) {
+      T xa[V], ya[V];
+      *reinterpret_cast<int4*>(xa) = __ldcs(reinterpret_cast<const int4*>(x) + v);
+      *reinterpret_cast<int4*>(ya) = __ldcs(reinterpret_cast<const int4*>(y) + v);
+      emit(v, xa, ya);
     }
     // tail
     for (u64 i = nvec * V + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
