@@ -108,7 +108,7 @@ __device__ __forceinline__ u32 point_key(T x, T y, T min_x, T min_y, T max_x, T 
 // ---------------------------------------------------------------------------------------------
 constexpr int kLeadBins = 8192;
 template <typename T, int PASSES>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T min_x, T min_y,
                    T max_x, T max_y, T scale, u32 oob_key, u32* __restrict__ keys,
                    u32* __restrict__ hist, u32* __restrict__ point_flags, int bin_shift,
@@ -162,16 +162,19 @@ encode_hist_kernel(const T* __restrict__ x, const T* __restrict__ y, u64 n, T mi
         *reinterpret_cast<uint4*>(keys + v * V) = make_uint4(ks[0], ks[1], ks[2], ks[3]);
     };
     u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; v + stride < nvec; v += 2 * stride) {
-      T xa[V], ya[V], xb[V], yb[V];
+    for (; v + 2 * stride < nvec; v += 3 * stride) {
+      T xa[V], ya[V], xb[V], yb[V], xc[V], yc[V];
       *reinterpret_cast<int4*>(xa) = __ldcs(reinterpret_cast<const int4*>(x) + v);
       *reinterpret_cast<int4*>(ya) = __ldcs(reinterpret_cast<const int4*>(y) + v);
       *reinterpret_cast<int4*>(xb) = __ldcs(reinterpret_cast<const int4*>(x) + v + stride);
       *reinterpret_cast<int4*>(yb) = __ldcs(reinterpret_cast<const int4*>(y) + v + stride);
+      *reinterpret_cast<int4*>(xc) = __ldcs(reinterpret_cast<const int4*>(x) + v + 2 * stride);
+      *reinterpret_cast<int4*>(yc) = __ldcs(reinterpret_cast<const int4*>(y) + v + 2 * stride);
       emit(v, xa, ya);
       emit(v + stride, xb, yb);
+      emit(v + 2 * stride, xc, yc);
     }
-    if (v < nvec) {
+    for (; v < nvec; v += stride) {
       T xa[V], ya[V];
       *reinterpret_cast<int4*>(xa) = __ldcs(reinterpret_cast<const int4*>(x) + v);
       *reinterpret_cast<int4*>(ya) = __ldcs(reinterpret_cast<const int4*>(y) + v);
