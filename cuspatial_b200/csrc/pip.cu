@@ -2008,8 +2008,8 @@ void pip_bitmask_t(const void* px, const void* py, u64 n_points, const u32* poly
   prof_mark("polygon_index");
 
   // cell-class grid (see bitmask_grid_kernel): worth building when the points outnumber the
-  // cells by far; 2^9 cells per side from 2^20 points, 2^10 from 2^28 (measured at 100 M points:
-  // 1.47 ms with 2^9, 1.56 ms with 2^10 -- the finer grid costs 0.14 ms more to build)
+  // cells by far (measured at 100 M points x 31 polygons: 1.47 ms with 2^9 cells per side,
+  // 1.56 ms with 2^10 -- the finer grid costs 0.14 ms more to build)
   cell_grid cg{};
   dev_buf<uint2> cells;
   if (n_poly && force_reference_mode() == 0) {
@@ -2030,7 +2030,13 @@ void pip_bitmask_t(const void* px, const void* py, u64 n_points, const u32* poly
       cg.ux0 = ux0 - wx; cg.ux1 = ux1 + wx; cg.uy0 = uy0; cg.uy1 = uy1;
     }
   }
-  int log2_cells = n_points >= (1ull << 28) ? 10 : n_points >= (1ull << 20) ? 9 : 0;
+  // resolution: classifying a cell costs about as much as a few points, and every polygon whose
+  // box meets the cell is classified -- keep cells x polygons below a quarter of the points
+  int log2_cells = 0;
+  if (n_points >= (1ull << 20)) {
+    double const budget = (double)n_points / (4.0 * (double)std::max<u32>(n_poly, 1));
+    log2_cells = std::max(6, std::min(10, (int)std::floor(0.5 * std::log2(std::max(budget, 1.0)))));
+  }
   if (const char* e = std::getenv("BSJ_BITMASK_GRID_LOG2")) log2_cells = std::atoi(e);
   log2_cells = std::min(log2_cells, 12);
   if (log2_cells >= 1 && n_poly && force_reference_mode() == 0) {

@@ -215,7 +215,8 @@ int bsj_expand_pip_compact(const uint32_t* pair_poly, const bsj_pip_compact* c,
  * (cpp/include/cuspatial/detail/point_in_polygon.cuh:93-94). out_mask: caller-allocated INT32[n_points];
  * bit i of out_mask[p] is set iff point p is inside polygon i.
  * From 2^20 points on, the call builds a grid of cell classes over the polygons' common box
- * (2^9 cells per side, 2^10 from 2^28 points; BSJ_BITMASK_GRID_LOG2 overrides, 0 = off) and a
+ * (2^6..2^10 cells per side, chosen so that cells x polygons stays below a quarter of the
+ * points; BSJ_BITMASK_GRID_LOG2 overrides, 0 = off) and a
  * point costs one lookup plus the exact test for the polygons its cell could not decide; the
  * result does not depend on the grid.  One host synchronisation (size of the edge index).
  */
