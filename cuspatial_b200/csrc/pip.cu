@@ -460,7 +460,21 @@ __device__ __forceinline__ int quadrant_edges(const quad_query<T>& q, bool activ
         continue;
       }
       double const ly = fmin((double)e.ay, (double)e.by) - d, hy = fmax((double)e.ay, (double)e.by) + d;
-      near = near || !(hy < q.ey0 || ly > q.ey1);
+      if (!(hy < q.ey0 || ly > q.ey1)) {
+        // the edge's (tolerance-widened) box meets the rectangle: does its LINE pass through it?
+        // f = (v - u) of the reference is linear, so |f(centre)| <= |rise| hw + |run| hh bounds it
+        // over the rectangle; the relative allowance covers the 4-ULP on-edge band and the
+        // rounding of the reference's products (same test as pip_eval_cells_kernel's `touch`)
+        double const eax = (double)e.ax, eay = (double)e.ay;
+        double const run = (double)e.bx - eax, rise = (double)e.by - eay;
+        double const hw = 0.5 * (q.ex1 - q.ex0), hh = 0.5 * (q.ey1 - q.ey0);
+        double const ddx = 0.5 * (q.ex0 + q.ex1) - eax, ddy = 0.5 * (q.ey0 + q.ey1) - eay;
+        double const f   = ddx * rise - run * ddy;
+        double const allow = sizeof(T) == 4 ? 2e-6 : 1e-9;
+        double const thr = (fabs(rise) * hw + fabs(run) * hh) * 1.000001 +
+                           allow * ((fabs(ddx) + hw) * fabs(rise) + fabs(run) * (fabs(ddy) + hh));
+        near = near || fabs(f) <= thr;
+      }
       if (f1 != f0) {
         T const u = fpp<T>::mul(fpp<T>::sub(e.bx, e.ax), fpp<T>::sub(q.cy, e.ay));
         T const v = fpp<T>::mul(fpp<T>::sub(q.cx, e.ax), fpp<T>::sub(e.by, e.ay));
