@@ -487,14 +487,20 @@ def shape_family_measurements(dev, steps, warmup):
         for _ in range(max(warmup, 1)):
             cs.quadtree_on_points((dx, dy), x0, x1, y0, y1, -1, 15, n // 256)
         torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        # per-step events and the median: this extra follows workloads of very different sizes in
+        # the same process, and a single step that has to regrow the memory pool (tens of ms) would
+        # otherwise dominate a five-step mean
+        per_step = []
+        for _ in range(max(steps, 3)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             _, tree = cs.quadtree_on_points((dx, dy), x0, x1, y0, y1, -1, 15, n // 256)
-        e1.record()
-        torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / steps
-    out["quadtree_nested_rectangles"] = {"points": n, "ms": ms, "points_per_s": n / (ms / 1e3),
+            e1.record()
+            torch.cuda.synchronize(dev)
+            per_step.append(e0.elapsed_time(e1))
+    ms = sorted(per_step)[len(per_step) // 2]
+    out["quadtree_nested_rectangles"] = {"points": n, "ms": ms, "ms_max": max(per_step),
+                                         "points_per_s": n / (ms / 1e3),
                                          "nodes": len(tree), "bounding_box_size": 10_000,
                                          "dtype": str(np.dtype(x.dtype))}
     return out
